@@ -1,0 +1,117 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the LIVE reference.
+
+Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py            # all cases
+    python oracle/make_golden.py lasso_200x1000_k10
+
+For each case in ``oracle.problems.CASES`` x each mode in ``MODES`` it seeds numpy's global RNG,
+builds the problem with the restated generator, then calls the unmodified reference
+``fasta.fasta(LinearMap, f, gradf, g, proxg, x0, **opts)`` (new 6-arg form, fasta/__init__.py:38)
+with the reference harness options (examples/__init__.py:74,80,86) and stores the trajectory.
+Also stores known-answer vectors for the prox operators and stop rules (``kat_*.npz``).
+The matrices are NOT stored: they are regenerated from the seed (legacy RandomState streams are
+frozen across numpy versions).
+"""
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from oracle import problems  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# TV + adaptive is chaotic: keep a short horizon for that combination
+TV_ADAPTIVE_ITERS = 40
+EXTRA_OPTS = {
+    ("tv_64", "adaptive"): dict(max_iters=TV_ADAPTIVE_ITERS),
+    ("tv_128", "adaptive"): dict(max_iters=TV_ADAPTIVE_ITERS),
+    ("tv_64", "accelerated"): dict(max_iters=200),
+    ("tv_64", "plain"): dict(max_iters=200),
+    ("tv_128", "accelerated"): dict(max_iters=120),
+    ("tv_128", "plain"): dict(max_iters=120),
+}
+
+
+def run_case(ref, case, mode, seed=0):
+    p = problems.build(case, seed)
+    apply, adjoint, vshape, wshape = problems.numpy_operator(p)
+    A = ref.linalg.LinearMap(apply, adjoint, vshape, wshape)
+    f, gradf, g, proxg = problems.numpy_callables(p)
+    opts = dict(problems.HARNESS_OPTS)
+    opts.update(problems.MODES[mode])
+    opts.update(EXTRA_OPTS.get((case, mode), {}))
+    # fasta() continues drawing from the global RNG right after construction (__init__.py:102-103)
+    res = ref.fasta(A, f, gradf, g, proxg, p.x0, **opts)
+    n = res.iteration_count
+    return dict(
+        case=case, mode=mode, seed=seed,
+        opts_keys=np.array(sorted(opts.keys())),
+        opts_vals=np.array([repr(opts[k]) for k in sorted(opts.keys())]),
+        iteration_count=n, backtracks=res.backtracks,
+        residuals=res.residuals[:n], norm_residuals=res.norm_residuals[:n],
+        stepsizes=res.stepsizes[:n], objectives=res.objectives[:n + 1],
+        solution=res.solution,
+        numpy_version=np.__version__,
+    )
+
+
+def prox_kats(ref):
+    rng = np.random.RandomState(1234)
+    out = {}
+    xs = [rng.randn(257) * 3, np.array([0.0, -0.0, 1.5, -1.5, 0.2, -0.2, 7.0]), rng.randn(1000),
+          np.array([3.0]), rng.randn(64) * 1e-3]
+    ts = [0.5, 0.2, 8.0, 1.0, 10.0]
+    for i, (x, t) in enumerate(zip(xs, ts)):
+        out[f"x{i}"] = x
+        out[f"t{i}"] = t
+        out[f"shrink{i}"] = ref.proximal.shrink(x, t)
+        out[f"l1ball{i}"] = ref.proximal.project_L1_ball(x, t)
+        out[f"tinf{i}"] = ref.proximal.project_Linf_ball(x, t)
+    X = rng.randn(7, 5)
+    out["X"] = X
+    out["Xt"] = 0.7
+    out["nuc"] = ref.proximal.project_Lnuc_ball(X, 0.7)
+    out["count"] = len(xs)
+    return out
+
+
+def stopping_kats(ref):
+    rows = []
+    for resid in (1e-7, 1e-4, 3.0):
+        for norm_resid in (1e-7, 1e-2):
+            for max_resid in (1e-4, 5.0):
+                for tol in (1e-5, 1e-3):
+                    args = (3, resid, norm_resid, max_resid, tol)
+                    rows.append(args[1:] + tuple(float(fn(*args)) for fn in (
+                        ref.stopping.residual, ref.stopping.norm_residual,
+                        ref.stopping.ratio_residual, ref.stopping.hybrid_residual)))
+    return dict(table=np.array(rows))
+
+
+def main(argv):
+    ref = ref_loader.load()
+    os.makedirs(GOLDEN, exist_ok=True)
+    cases = argv or list(problems.CASES)
+    for case in cases:
+        for mode in problems.MODES:
+            rec = run_case(ref, case, mode)
+            path = os.path.join(GOLDEN, f"{case}__{mode}.npz")
+            np.savez_compressed(path, **rec)
+            print(f"{case:28s} {mode:12s} iters={rec['iteration_count']:4d} bt={rec['backtracks']:3d} "
+                  f"obj={rec['objectives'][-1]:.15e}")
+    if not argv:
+        np.savez_compressed(os.path.join(GOLDEN, "kat_prox.npz"), **prox_kats(ref))
+        np.savez_compressed(os.path.join(GOLDEN, "kat_stopping.npz"), **stopping_kats(ref))
+        print("wrote prox / stopping known-answer vectors")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,64 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import os
+
+import numpy as np
+
+from conftest import GOLDEN
+from oracle import problems
+
+
+def load_golden(case, mode):
+    with np.load(os.path.join(GOLDEN, f"{case}__{mode}.npz")) as z:
+        rec = {k: z[k] for k in z.files}
+    opts = {k: eval(v) for k, v in zip(rec["opts_keys"], rec["opts_vals"])}   # reprs of bool/int/float
+    rec["opts"] = opts
+    rec["iteration_count"] = int(rec["iteration_count"])
+    rec["backtracks"] = int(rec["backtracks"])
+    return rec
+
+
+def golden_cases(prefixes=None, exclude=()):
+    out = []
+    for case in problems.CASES:
+        if prefixes and not any(case.startswith(p) for p in prefixes):
+            continue
+        if case in exclude:
+            continue
+        for mode in problems.MODES:
+            out.append((case, mode))
+    return out
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.linalg.norm(b.ravel())
+    if den == 0:
+        return float(np.linalg.norm(a.ravel()))
+    return float(np.linalg.norm((a - b).ravel()) / den)
+
+
+def assert_trajectory(res, gold, sol_tol=1e-9, obj_tol=1e-10, hist_tol=1e-8, label=""):
+    """The parity bar of BASELINE.json: identical iteration and backtrack counts, final iterate
+    within 1e-9 relative, objective history within 1e-10 relative (measured against the scale of
+    the initial objective so that objectives decaying to ~0, e.g. NNLS, are compared in absolute
+    terms relative to the problem scale)."""
+    n = gold["iteration_count"]
+    assert res.iteration_count == n, f"{label}: iterations {res.iteration_count} != {n}"
+    assert res.backtracks == gold["backtracks"], f"{label}: backtracks {res.backtracks} != {gold['backtracks']}"
+    sol = np.asarray(res.solution)
+    assert sol.shape == gold["solution"].shape
+    e = rel_err(sol, gold["solution"])
+    assert e <= sol_tol, f"{label}: solution rel err {e:.3e}"
+    if gold["objectives"] is not None and getattr(res, "objectives", None) is not None:
+        obj = np.asarray(res.objectives)[:n + 1]
+        scale = np.maximum(np.abs(gold["objectives"]), abs(gold["objectives"][0]) * 1e-3)
+        eo = float(np.max(np.abs(obj - gold["objectives"]) / scale))
+        assert eo <= obj_tol, f"{label}: objective history rel err {eo:.3e}"
+    for name in ("residuals", "stepsizes", "norm_residuals"):
+        got = np.asarray(getattr(res, name))[:n]
+        ref = gold[name]
+        eh = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))) if n else 0.0
+        assert eh <= hist_tol, f"{label}: {name} rel err {eh:.3e}"
+    # arrays are full length and zero padded past iteration_count (SURVEY F-13)
+    assert np.all(np.asarray(res.residuals)[n:] == 0)

@@ -1,0 +1,59 @@
+"""CPU: the numpy oracle reproduces the live-reference golden trajectories BIT FOR BIT."""
+import numpy as np
+import pytest
+
+from helpers import golden_cases, load_golden
+from oracle import fasta_oracle, problems
+
+FAST = golden_cases(exclude=("lasso_4000x10000_k500",))
+
+
+@pytest.mark.parametrize("case,mode", FAST)
+def test_oracle_matches_reference_bitwise(case, mode):
+    gold = load_golden(case, mode)
+    p = problems.build(case, int(gold["seed"]))
+    res = fasta_oracle.solve_problem(p, **gold["opts"])
+    n = gold["iteration_count"]
+    assert res.iteration_count == n
+    assert res.backtracks == gold["backtracks"]
+    if str(gold["numpy_version"]) == np.__version__:
+        # same numpy/BLAS build as the generator: exact equality
+        assert np.array_equal(res.solution, gold["solution"])
+        assert np.array_equal(res.objectives[:n + 1], gold["objectives"])
+        assert np.array_equal(res.stepsizes[:n], gold["stepsizes"])
+        assert np.array_equal(res.residuals[:n], gold["residuals"])
+        assert np.array_equal(res.norm_residuals[:n], gold["norm_residuals"])
+    else:
+        np.testing.assert_allclose(res.solution, gold["solution"], rtol=0, atol=1e-9 * np.abs(gold["solution"]).max())
+        np.testing.assert_allclose(res.objectives[:n + 1], gold["objectives"], rtol=1e-10)
+
+
+def test_oracle_midsize_lasso_adaptive():
+    gold = load_golden("lasso_4000x10000_k500", "adaptive")
+    p = problems.build("lasso_4000x10000_k500", 0)
+    res = fasta_oracle.solve_problem(p, **gold["opts"])
+    assert res.iteration_count == gold["iteration_count"] == 26
+    assert res.backtracks == 0
+    np.testing.assert_allclose(res.objectives[:27], gold["objectives"], rtol=1e-12)
+
+
+def test_oracle_prox_known_answers(golden_dir):
+    with np.load(f"{golden_dir}/kat_prox.npz") as z:
+        for i in range(int(z["count"])):
+            x, t = z[f"x{i}"], float(z[f"t{i}"])
+            assert np.array_equal(fasta_oracle.shrink(x, t), z[f"shrink{i}"])
+            assert np.array_equal(np.signbit(fasta_oracle.shrink(x, t)), np.signbit(z[f"shrink{i}"]))
+            assert np.array_equal(fasta_oracle.project_l1_ball(x, t), z[f"l1ball{i}"])
+            assert np.array_equal(fasta_oracle.prox_tinf(x, t), z[f"tinf{i}"])
+        np.testing.assert_allclose(fasta_oracle.prox_nuclear(z["X"], float(z["Xt"])), z["nuc"], rtol=1e-13, atol=1e-14)
+
+
+def test_oracle_stop_rules_truth_table(golden_dir):
+    with np.load(f"{golden_dir}/kat_stopping.npz") as z:
+        table = z["table"]
+    fns = (fasta_oracle.stop_residual, fasta_oracle.stop_norm_residual,
+           fasta_oracle.stop_ratio_residual, fasta_oracle.stop_hybrid_residual)
+    for row in table:
+        args = (3,) + tuple(row[:4])
+        for fn, want in zip(fns, row[4:]):
+            assert bool(fn(*args)) == bool(want)
