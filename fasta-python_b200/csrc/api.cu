@@ -1,0 +1,51 @@
+// C-ABI housekeeping: error text, device query, workspace sizing.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace fb200 {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = 148;   // B200
+        }
+    }
+    return n;
+}
+
+size_t dense_partial_elems(int64_t M, int64_t N);
+
+}  // namespace fb200
+
+extern "C" int fb200_abi_version(void) { return FB200_ABI_VERSION; }
+
+extern "C" const char* fb200_last_error(void) { return fb200::g_error; }
+
+extern "C" size_t fb200_workspace_bytes(int64_t M, int64_t N) {
+    if (M < 1) M = 1;
+    if (N < 1) N = 1;
+    return fb200::DENSE_OFF + fb200::dense_partial_elems(M, N) * sizeof(double);
+}

@@ -1,0 +1,203 @@
+// K11 / K12: matrix-free total-variation operators (periodic finite differences) fused with the
+// loss and Barzilai-Borwein epilogues.
+//     div : Y (n0 x n1 x 2) -> Z (n0 x n1)     reference tv_denoising.py:43-63   (solver map A)
+//     grad: R (n0 x n1) -> G (n0 x n1 x 2)     reference tv_denoising.py:26-40   (adjoint A^H)
+//
+// B200 design: HBM-bound stencils.  A thread owns one image column inside a strip of STRIP rows
+// and marches down it, so the vertical neighbour is carried in registers (each input element is
+// loaded from HBM once per strip, +1 halo row per strip = 3% re-read); the horizontal neighbour
+// comes from the adjacent lane by warp shuffle (one extra L1-hit load per warp edge).  Loads are
+// issued UNROLL rows ahead to keep >100 KB per SM in flight.  Outputs, the loss (r = gradf(z),
+// sum f) and the BB reductions are produced in the same pass, so an FBS iteration on an image
+// is three streaming kernels.  Compiled with -fmad=false (one rounding per numpy operation).
+#include "common.cuh"
+
+namespace fb200 {
+
+constexpr int TV_THREADS = 128;
+constexpr int TV_STRIP   = 32;   // minimum rows per strip; grows so the grid fits the reduction workspace
+constexpr int TV_UNROLL  = 4;
+
+// Z[i][j] = (Y[i+1][j].x - Y[i][j].x) + (Y[i][j+1].y - Y[i][j].y), indices periodic
+template <int LOSS>
+__global__ void __launch_bounds__(TV_THREADS)
+tv_div_loss_kernel(const double2* __restrict__ Y, int64_t n0, int64_t n1, const double* __restrict__ b,
+                   double* __restrict__ z, double* __restrict__ r, int strip, double* scal, double* red,
+                   unsigned* counter) {
+    const int lane   = threadIdx.x & 31;
+    const int64_t j  = int64_t(blockIdx.x) * TV_THREADS + threadIdx.x;
+    const int64_t i0 = int64_t(blockIdx.y) * strip;
+    const bool live  = j < n1;
+    const int64_t jc = live ? j : 0;
+    const int64_t jr = (jc + 1 == n1) ? 0 : jc + 1;
+    double s[1] = {0.0};
+    if (i0 < n0) {
+        const int64_t i1 = (i0 + strip < n0) ? i0 + strip : n0;
+        double2 cur = Y[i0 * n1 + jc];
+        for (int64_t ib = i0; ib < i1; ib += TV_UNROLL) {
+            double2 nxt[TV_UNROLL];
+            double  ry[TV_UNROLL];
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {
+                const int64_t i  = ib + u;
+                const int64_t in = (i + 1 >= n0) ? (i + 1 - n0) : i + 1;
+                nxt[u] = (i < i1) ? Y[in * n1 + jc] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {
+                const int64_t i  = ib + u;
+                const double2 c  = (u == 0) ? cur : nxt[u - 1];
+                double right     = __shfl_down_sync(0xffffffffu, c.y, 1);
+                if ((lane == 31 || jc + 1 == n1) && i < i1) right = Y[i * n1 + jr].y;
+                ry[u] = right;
+            }
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {
+                const int64_t i = ib + u;
+                const double2 c = (u == 0) ? cur : nxt[u - 1];
+                if (i < i1 && live) {
+                    const double t0 = nxt[u].x - c.x;
+                    const double t1 = ry[u] - c.y;
+                    const double zi = t0 + t1;
+                    const int64_t o = i * n1 + j;
+                    z[o] = zi;
+                    if (LOSS != FB200_LOSS_NONE) {
+                        double ri, fi;
+                        loss_elem<LOSS>(zi, b[o], ri, fi);
+                        r[o] = ri;
+                        s[0] += fi;
+                    }
+                }
+            }
+            cur = nxt[TV_UNROLL - 1];
+        }
+    }
+    if (LOSS != FB200_LOSS_NONE) {
+        double* const out[1] = {scal + FB200_S_F};
+        grid_sum<1>(s, red, counter, out);
+    }
+}
+
+// G[i][j] = (R[i-1][j] - R[i][j], R[i][j-1] - R[i][j]), indices periodic; fused BB reductions
+template <int BB>
+__global__ void __launch_bounds__(TV_THREADS)
+tv_grad_bb_kernel(const double* __restrict__ R, int64_t n0, int64_t n1, double2* __restrict__ g,
+                  const double2* __restrict__ x0, const double2* __restrict__ xhat, const double2* __restrict__ dx,
+                  double tau, int strip, double* scal, double* red, unsigned* counter) {
+    const int lane   = threadIdx.x & 31;
+    const int64_t j  = int64_t(blockIdx.x) * TV_THREADS + threadIdx.x;
+    const int64_t i0 = int64_t(blockIdx.y) * strip;
+    const bool live  = j < n1;
+    const int64_t jc = live ? j : 0;
+    const int64_t jl = (jc == 0) ? n1 - 1 : jc - 1;
+    double s[3] = {0.0, 0.0, 0.0};
+    if (i0 < n0) {
+        const int64_t i1 = (i0 + strip < n0) ? i0 + strip : n0;
+        double up = R[((i0 == 0) ? n0 - 1 : i0 - 1) * n1 + jc];
+        for (int64_t ib = i0; ib < i1; ib += TV_UNROLL) {
+            double c[TV_UNROLL], lf[TV_UNROLL];
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {
+                const int64_t i = ib + u;
+                c[u] = (i < i1) ? R[i * n1 + jc] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {
+                const int64_t i = ib + u;
+                double left = __shfl_up_sync(0xffffffffu, c[u], 1);
+                if ((lane == 0 || jc == 0) && i < i1) left = R[i * n1 + jl];
+                lf[u] = left;
+            }
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {
+                const int64_t i = ib + u;
+                if (i < i1 && live) {
+                    const double a = (u == 0) ? up : c[u - 1];
+                    double2 gi;
+                    gi.x = a - c[u];
+                    gi.y = lf[u] - c[u];
+                    const int64_t o = i * n1 + j;
+                    g[o] = gi;
+                    if (BB >= 1) {
+                        s[2] += gi.x * gi.x;
+                        s[2] += gi.y * gi.y;
+                    }
+                    if (BB >= 2) {
+                        const double2 h = xhat[o], p = x0[o], d = dx[o];
+                        const double dg0 = gi.x + (h.x - p.x) / tau;
+                        const double dg1 = gi.y + (h.y - p.y) / tau;
+                        s[0] += d.x * dg0;
+                        s[0] += d.y * dg1;
+                        s[1] += dg0 * dg0;
+                        s[1] += dg1 * dg1;
+                    }
+                }
+            }
+            up = c[TV_UNROLL - 1];
+        }
+    }
+    if (BB >= 1) {
+        double* const out[3] = {BB >= 2 ? scal + FB200_S_DX_DG : nullptr,
+                                BB >= 2 ? scal + FB200_S_DG_SQ : nullptr, scal + FB200_S_G1_SQ};
+        grid_sum<3>(s, red, counter, out);
+    }
+}
+
+static int tv_grid(int64_t n0, int64_t n1, dim3* grid, int* strip) {
+    const int64_t gx = (n1 + TV_THREADS - 1) / TV_THREADS;
+    int64_t st = TV_STRIP;
+    while (gx * ((n0 + st - 1) / st) > MAX_RED_BLOCKS) st *= 2;
+    const int64_t gy = (n0 + st - 1) / st;
+    if (gx > MAX_RED_BLOCKS || gy > 65535) {
+        set_error("tv: image %lld x %lld too large for the stencil grid", (long long)n0, (long long)n1);
+        return 1;
+    }
+    *grid  = dim3(unsigned(gx), unsigned(gy));
+    *strip = int(st);
+    return 0;
+}
+
+}  // namespace fb200
+
+using namespace fb200;
+
+extern "C" int fb200_tv_div_loss(const double* Y, int64_t n0, int64_t n1, int loss, const double* b, double* z,
+                                 double* r, double* scal, void* ws, void* stream) {
+    Workspace w(ws);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid;
+    int strip = TV_STRIP;
+    if (n0 < 1 || n1 < 1) { set_error("tv_div_loss: bad shape"); return 1; }
+    if (tv_grid(n0, n1, &grid, &strip)) return 1;
+    switch (loss) {
+        case FB200_LOSS_NONE:
+            tv_div_loss_kernel<FB200_LOSS_NONE><<<grid, TV_THREADS, 0, st>>>((const double2*)Y, n0, n1, b, z, r, strip, scal, w.red, w.counter);
+            break;
+        case FB200_LOSS_LEAST_SQUARES:
+            tv_div_loss_kernel<FB200_LOSS_LEAST_SQUARES><<<grid, TV_THREADS, 0, st>>>((const double2*)Y, n0, n1, b, z, r, strip, scal, w.red, w.counter);
+            break;
+        case FB200_LOSS_LOGISTIC:
+            tv_div_loss_kernel<FB200_LOSS_LOGISTIC><<<grid, TV_THREADS, 0, st>>>((const double2*)Y, n0, n1, b, z, r, strip, scal, w.red, w.counter);
+            break;
+        default: set_error("unknown loss tag %d", loss); return 1;
+    }
+    return check_launch("tv_div_loss");
+}
+
+extern "C" int fb200_tv_grad_bb(const double* R, int64_t n0, int64_t n1, double* g, int bb, const double* x0,
+                                const double* xhat, const double* dx, double tau, double* scal, void* ws,
+                                void* stream) {
+    Workspace w(ws);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid;
+    int strip = TV_STRIP;
+    if (n0 < 1 || n1 < 1) { set_error("tv_grad_bb: bad shape"); return 1; }
+    if (tv_grid(n0, n1, &grid, &strip)) return 1;
+    switch (bb) {
+        case 0: tv_grad_bb_kernel<0><<<grid, TV_THREADS, 0, st>>>(R, n0, n1, (double2*)g, (const double2*)x0, (const double2*)xhat, (const double2*)dx, tau, strip, scal, w.red, w.counter); break;
+        case 1: tv_grad_bb_kernel<1><<<grid, TV_THREADS, 0, st>>>(R, n0, n1, (double2*)g, (const double2*)x0, (const double2*)xhat, (const double2*)dx, tau, strip, scal, w.red, w.counter); break;
+        case 2: tv_grad_bb_kernel<2><<<grid, TV_THREADS, 0, st>>>(R, n0, n1, (double2*)g, (const double2*)x0, (const double2*)xhat, (const double2*)dx, tau, strip, scal, w.red, w.counter); break;
+        default: set_error("unknown bb mode %d", bb); return 1;
+    }
+    return check_launch("tv_grad_bb");
+}

@@ -1,0 +1,486 @@
+// N-/M-vector kernels of the FBS loop: forward step + prox + reductions (K1-K3), FISTA
+// extrapolation (K9), loss evaluation (K5), Barzilai-Borwein reductions (K8), the l1-ball
+// threshold search, and small reduction helpers.  All HBM-bound streaming kernels with fused
+// warp-shuffle/block reductions; compiled with -fmad=false so that every elementwise expression
+// rounds once per numpy operation of the reference line it replaces.
+#include "common.cuh"
+
+namespace fb200 {
+
+// =================================================================================================
+// K1-K3  xhat = x0 - tau*g0 ; x1 = prox(xhat) ; dx = x1 - x0       reference __init__.py:181-186
+// =================================================================================================
+template <int PROX, bool RESTART>
+__global__ void __launch_bounds__(VEC_THREADS)
+fbs_step_kernel(const double* __restrict__ x0, const double* __restrict__ g0, double tau, double p0,
+                double p1, const double* __restrict__ xa_prev, int64_t n, double* __restrict__ xhat,
+                double* __restrict__ x1, double* __restrict__ dx, double* scal, double* red,
+                unsigned* counter) {
+    if (PROX == FB200_PROX_L1BALL) p0 = scal[FB200_S_THETA];
+    double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double a  = x0[i];
+        const double gr = g0[i];
+        const double h  = a - tau * gr;
+        const double y  = prox_elem<PROX>(h, p0, p1);
+        const double d  = y - a;
+        xhat[i]         = h;
+        x1[i]           = y;
+        dx[i]           = d;
+        s[0] += d * gr;
+        s[1] += d * d;
+        const double e = y - h;
+        s[2] += e * e;
+        s[3] += fabs(y);
+        if (RESTART) s[4] += (a - y) * (y - xa_prev[i]);
+    }
+    double* const out[5] = {scal + FB200_S_DX_G0, scal + FB200_S_DX_SQ, scal + FB200_S_XMXH_SQ,
+                            scal + FB200_S_PEN, RESTART ? scal + FB200_S_RESTART : nullptr};
+    grid_sum<5>(s, red, counter, out);
+}
+
+// TV dual-ball prox works on interleaved pairs (y0, y1) / max(|y|_2, 1)   tv_denoising.py:89-96
+template <bool RESTART>
+__global__ void __launch_bounds__(VEC_THREADS)
+fbs_step_pairs_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, double tau,
+                      const double2* __restrict__ xa_prev, int64_t npairs, double2* __restrict__ xhat,
+                      double2* __restrict__ x1, double2* __restrict__ dx, double* scal, double* red,
+                      unsigned* counter) {
+    double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < npairs; i += stride) {
+        const double2 a  = x0[i];
+        const double2 gr = g0[i];
+        double2 h, y, d;
+        h.x = a.x - tau * gr.x;
+        h.y = a.y - tau * gr.y;
+        // la.norm(Y, axis=-1): sqrt(y0^2 + y1^2); then maximum(., 1); then Y / norms
+        const double nrm = fmax(sqrt(h.x * h.x + h.y * h.y), 1.0);
+        y.x = h.x / nrm;
+        y.y = h.y / nrm;
+        d.x = y.x - a.x;
+        d.y = y.y - a.y;
+        xhat[i] = h;
+        x1[i]   = y;
+        dx[i]   = d;
+        s[0] += d.x * gr.x;
+        s[0] += d.y * gr.y;
+        s[1] += d.x * d.x;
+        s[1] += d.y * d.y;
+        const double e0 = y.x - h.x, e1 = y.y - h.y;
+        s[2] += e0 * e0;
+        s[2] += e1 * e1;
+        if (RESTART) {
+            const double2 q = xa_prev[i];
+            s[4] += (a.x - y.x) * (y.x - q.x);
+            s[4] += (a.y - y.y) * (y.y - q.y);
+        }
+    }
+    double* const out[5] = {scal + FB200_S_DX_G0, scal + FB200_S_DX_SQ, scal + FB200_S_XMXH_SQ,
+                            scal + FB200_S_PEN, RESTART ? scal + FB200_S_RESTART : nullptr};
+    grid_sum<5>(s, red, counter, out);
+}
+
+template <int PROX>
+static int launch_fbs(const double* x0, const double* g0, double tau, double p0, double p1,
+                      const double* xa_prev, int64_t n, double* xhat, double* x1, double* dx,
+                      double* scal, Workspace& w, cudaStream_t st) {
+    const int grid = vec_grid(n);
+    if (xa_prev)
+        fbs_step_kernel<PROX, true><<<grid, VEC_THREADS, 0, st>>>(x0, g0, tau, p0, p1, xa_prev, n, xhat,
+                                                                  x1, dx, scal, w.red, w.counter);
+    else
+        fbs_step_kernel<PROX, false><<<grid, VEC_THREADS, 0, st>>>(x0, g0, tau, p0, p1, nullptr, n, xhat,
+                                                                   x1, dx, scal, w.red, w.counter);
+    return check_launch("fbs_step");
+}
+
+// generic-path pieces: forward step alone, reductions alone, prox alone
+__global__ void __launch_bounds__(VEC_THREADS)
+forward_step_kernel(const double* __restrict__ x0, const double* __restrict__ g0, double tau, int64_t n,
+                    double* __restrict__ xhat) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        xhat[i] = x0[i] - tau * g0[i];
+}
+
+template <bool RESTART>
+__global__ void __launch_bounds__(VEC_THREADS)
+step_reduce_kernel(const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ xhat,
+                   const double* __restrict__ g0, const double* __restrict__ xa_prev, int64_t n,
+                   double* __restrict__ dx, double* scal, double* red, unsigned* counter) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double a = x0[i], y = x1[i];
+        const double d = y - a;
+        dx[i]          = d;
+        s[0] += d * g0[i];
+        s[1] += d * d;
+        const double e = y - xhat[i];
+        s[2] += e * e;
+        if (RESTART) s[3] += (a - y) * (y - xa_prev[i]);
+    }
+    double* const out[4] = {scal + FB200_S_DX_G0, scal + FB200_S_DX_SQ, scal + FB200_S_XMXH_SQ,
+                            RESTART ? scal + FB200_S_RESTART : nullptr};
+    grid_sum<4>(s, red, counter, out);
+}
+
+template <int PROX>
+__global__ void __launch_bounds__(VEC_THREADS)
+prox_apply_kernel(const double* __restrict__ x, double p0, double p1, int64_t n, double* __restrict__ out,
+                  const double* __restrict__ scal) {
+    if (PROX == FB200_PROX_L1BALL) p0 = scal[FB200_S_THETA];
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    if (PROX == FB200_PROX_TV_BALL) {
+        const double2* xp = reinterpret_cast<const double2*>(x);
+        double2* op       = reinterpret_cast<double2*>(out);
+        for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n / 2; i += stride) {
+            const double2 h  = xp[i];
+            const double nrm = fmax(sqrt(h.x * h.x + h.y * h.y), 1.0);
+            op[i]            = make_double2(h.x / nrm, h.y / nrm);
+        }
+    } else {
+        for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+            out[i] = prox_elem<PROX>(x[i], p0, p1);
+    }
+}
+
+// =================================================================================================
+// l1-ball threshold (Michelot's fixed point; exact active set in finitely many passes)
+//   theta solves sum_i max(|v_i| - theta, 0) = radius; equals the reference's
+//   alpha = max_k (cumsum_k(sorted |v|) - t)/k                     proximal.py:22-26
+// One CTA; each pass is a fixed-order block reduction, so the result is bit-reproducible.
+// =================================================================================================
+constexpr int L1B_THREADS = 1024;
+
+__global__ void __launch_bounds__(L1B_THREADS)
+l1ball_threshold_kernel(const double* __restrict__ v, int64_t n, double radius, double* scal) {
+    __shared__ double sm[2 * 32];
+    __shared__ double sh_theta;
+    __shared__ double sh_count;
+    double theta = -1.0;    // first pass: every element is active (|v| > -1)
+    double prev_count = -1.0;
+    for (int pass = 0; pass < 256; ++pass) {
+        double s[2] = {0.0, 0.0};
+        for (int64_t i = threadIdx.x; i < n; i += L1B_THREADS) {
+            const double m = fabs(v[i]);
+            if (m > theta) {
+                s[0] += m;
+                s[1] += 1.0;
+            }
+        }
+        block_sum<2>(s, sm);
+        if (threadIdx.x == 0) {
+            sh_count = s[1];
+            if (pass == 0 && s[0] <= radius) {
+                sh_theta = 0.0;      // already inside the ball: projection is the identity
+                sh_count = -2.0;     // sentinel: stop
+            } else {
+                sh_theta = (s[1] > 0.0) ? (s[0] - radius) / s[1] : theta;
+            }
+        }
+        __syncthreads();
+        const double cnt = sh_count;
+        theta            = sh_theta;
+        if (cnt == -2.0 || cnt == prev_count || cnt <= 0.0) break;
+        prev_count = cnt;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) scal[FB200_S_THETA] = (theta > 0.0) ? theta : 0.0;
+}
+
+// =================================================================================================
+// K9  FISTA extrapolation of x (n) and z (m) + loss at the extrapolated z  __init__.py:242-245
+// =================================================================================================
+template <int LOSS, bool PEN>
+__global__ void __launch_bounds__(VEC_THREADS)
+accel_step_kernel(double c, const double* __restrict__ xa1, const double* __restrict__ xa0,
+                  const double* __restrict__ xhat, int64_t n, double* __restrict__ x1,
+                  const double* __restrict__ za1, const double* __restrict__ za0,
+                  const double* __restrict__ b, int64_t m, double* __restrict__ z1,
+                  double* __restrict__ r, double* scal, double* red, unsigned* counter) {
+    double s[3] = {0.0, 0.0, 0.0};
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    const int64_t t0     = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (int64_t i = t0; i < n; i += stride) {
+        const double p = xa1[i];
+        const double y = p + c * (p - xa0[i]);          // x1 + (alpha0-1)/alpha1 * (xa1 - xa0)
+        x1[i]          = y;
+        const double e = y - xhat[i];
+        s[1] += e * e;
+        if (PEN) s[2] += fabs(y);
+    }
+    for (int64_t i = t0; i < m; i += stride) {
+        const double p = za1[i];
+        const double z = p + c * (p - za0[i]);
+        z1[i]          = z;
+        double ri, fi;
+        loss_elem<LOSS>(z, b ? b[i] : 0.0, ri, fi);
+        if (LOSS != FB200_LOSS_NONE) r[i] = ri;
+        s[0] += fi;
+    }
+    double* const out[3] = {scal + FB200_S_F, scal + FB200_S_XMXH_SQ, scal + FB200_S_PEN};
+    grid_sum<3>(s, red, counter, out);
+}
+
+// =================================================================================================
+// K5  z (optionally the fixed-order sum of S split partials) -> r = gradf(z), raw f(z)
+// =================================================================================================
+template <int LOSS>
+__global__ void __launch_bounds__(VEC_THREADS)
+loss_kernel(const double* __restrict__ zsrc, int nsplit, int64_t ld, const double* __restrict__ b,
+            int64_t m, double* __restrict__ z, double* __restrict__ r, double* scal, double* red,
+            unsigned* counter) {
+    double s[1] = {0.0};
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m; i += stride) {
+        double zi;
+        if (nsplit > 0) {
+            zi = __ldcg(&zsrc[i]);
+            for (int k = 1; k < nsplit; ++k) zi += __ldcg(&zsrc[int64_t(k) * ld + i]);
+            z[i] = zi;
+        } else {
+            zi = zsrc[i];
+        }
+        if (LOSS != FB200_LOSS_NONE) {
+            double ri, fi;
+            loss_elem<LOSS>(zi, b[i], ri, fi);
+            r[i] = ri;
+            s[0] += fi;
+        }
+    }
+    if (LOSS != FB200_LOSS_NONE) {
+        double* const out[1] = {scal + FB200_S_F};
+        grid_sum<1>(s, red, counter, out);
+    }
+}
+
+int launch_loss(int loss, const double* zsrc, int nsplit, int64_t ld, const double* b, int64_t m,
+                double* z, double* r, double* scal, Workspace& w, cudaStream_t st) {
+    const int grid = vec_grid(m);
+    switch (loss) {
+        case FB200_LOSS_NONE:
+            if (nsplit == 0) return 0;
+            loss_kernel<FB200_LOSS_NONE><<<grid, VEC_THREADS, 0, st>>>(zsrc, nsplit, ld, b, m, z, r, scal, w.red, w.counter);
+            break;
+        case FB200_LOSS_LEAST_SQUARES:
+            loss_kernel<FB200_LOSS_LEAST_SQUARES><<<grid, VEC_THREADS, 0, st>>>(zsrc, nsplit, ld, b, m, z, r, scal, w.red, w.counter);
+            break;
+        case FB200_LOSS_LOGISTIC:
+            loss_kernel<FB200_LOSS_LOGISTIC><<<grid, VEC_THREADS, 0, st>>>(zsrc, nsplit, ld, b, m, z, r, scal, w.red, w.counter);
+            break;
+        default:
+            set_error("unknown loss tag %d", loss);
+            return 1;
+    }
+    return check_launch("loss_kernel");
+}
+
+// =================================================================================================
+// K8  g1 (optionally summed from S split partials) ; dg = g1 + (xhat - x0)/tau ; reductions
+// =================================================================================================
+template <int BB>
+__global__ void __launch_bounds__(VEC_THREADS)
+bb_kernel(const double* __restrict__ gsrc, int nsplit, int64_t ld, int64_t n, double* __restrict__ g,
+          const double* __restrict__ x0, const double* __restrict__ xhat, const double* __restrict__ dx,
+          double tau, double* scal, double* red, unsigned* counter) {
+    double s[3] = {0.0, 0.0, 0.0};
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double gi;
+        if (nsplit > 0) {
+            gi = __ldcg(&gsrc[i]);
+            for (int k = 1; k < nsplit; ++k) gi += __ldcg(&gsrc[int64_t(k) * ld + i]);
+            g[i] = gi;
+        } else {
+            gi = gsrc[i];
+        }
+        if (BB >= 1) s[2] += gi * gi;
+        if (BB >= 2) {
+            const double dg = gi + (xhat[i] - x0[i]) / tau;     // __init__.py:254
+            s[0] += dx[i] * dg;                                  // :255
+            s[1] += dg * dg;                                     // :260
+        }
+    }
+    if (BB >= 1) {
+        double* const out[3] = {BB >= 2 ? scal + FB200_S_DX_DG : nullptr,
+                                BB >= 2 ? scal + FB200_S_DG_SQ : nullptr, scal + FB200_S_G1_SQ};
+        grid_sum<3>(s, red, counter, out);
+    }
+}
+
+int launch_bb(int bb, const double* gsrc, int nsplit, int64_t ld, int64_t n, double* g, const double* x0,
+              const double* xhat, const double* dx, double tau, double* scal, Workspace& w,
+              cudaStream_t st) {
+    const int grid = vec_grid(n);
+    switch (bb) {
+        case 0:
+            if (nsplit == 0) return 0;
+            bb_kernel<0><<<grid, VEC_THREADS, 0, st>>>(gsrc, nsplit, ld, n, g, x0, xhat, dx, tau, scal, w.red, w.counter);
+            break;
+        case 1:
+            bb_kernel<1><<<grid, VEC_THREADS, 0, st>>>(gsrc, nsplit, ld, n, g, x0, xhat, dx, tau, scal, w.red, w.counter);
+            break;
+        case 2:
+            bb_kernel<2><<<grid, VEC_THREADS, 0, st>>>(gsrc, nsplit, ld, n, g, x0, xhat, dx, tau, scal, w.red, w.counter);
+            break;
+        default:
+            set_error("unknown bb mode %d", bb);
+            return 1;
+    }
+    return check_launch("bb_kernel");
+}
+
+// =================================================================================================
+// small reductions
+// =================================================================================================
+template <int OP>   // 0: <a,b>   1: |a-b|^2   2: sum |a|
+__global__ void __launch_bounds__(VEC_THREADS)
+reduce_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* out,
+              double* red, unsigned* counter) {
+    double s[1] = {0.0};
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (OP == 0) {
+            s[0] += a[i] * b[i];
+        } else if (OP == 1) {
+            const double d = a[i] - b[i];
+            s[0] += d * d;
+        } else {
+            s[0] += fabs(a[i]);
+        }
+    }
+    double* const o[1] = {out};
+    grid_sum<1>(s, red, counter, o);
+}
+
+}  // namespace fb200
+
+using namespace fb200;
+
+extern "C" int fb200_fbs_step(const double* x0, const double* g0, double tau, int prox, double p0, double p1,
+                              const double* xa_prev, int64_t n, double* xhat, double* x1, double* dx,
+                              double* scal, void* ws, void* stream) {
+    Workspace w(ws);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n <= 0) { set_error("fbs_step: n must be positive"); return 1; }
+    switch (prox) {
+        case FB200_PROX_IDENTITY: return launch_fbs<FB200_PROX_IDENTITY>(x0, g0, tau, p0, p1, xa_prev, n, xhat, x1, dx, scal, w, st);
+        case FB200_PROX_SHRINK:   return launch_fbs<FB200_PROX_SHRINK>(x0, g0, tau, p0, p1, xa_prev, n, xhat, x1, dx, scal, w, st);
+        case FB200_PROX_NONNEG:   return launch_fbs<FB200_PROX_NONNEG>(x0, g0, tau, p0, p1, xa_prev, n, xhat, x1, dx, scal, w, st);
+        case FB200_PROX_BOX:      return launch_fbs<FB200_PROX_BOX>(x0, g0, tau, p0, p1, xa_prev, n, xhat, x1, dx, scal, w, st);
+        case FB200_PROX_L1BALL:   return launch_fbs<FB200_PROX_L1BALL>(x0, g0, tau, p0, p1, xa_prev, n, xhat, x1, dx, scal, w, st);
+        case FB200_PROX_TV_BALL: {
+            if (n % 2) { set_error("fbs_step: TV ball prox needs an even element count"); return 1; }
+            const int grid = vec_grid(n / 2, 1);
+            if (xa_prev)
+                fbs_step_pairs_kernel<true><<<grid, VEC_THREADS, 0, st>>>(
+                    (const double2*)x0, (const double2*)g0, tau, (const double2*)xa_prev, n / 2, (double2*)xhat,
+                    (double2*)x1, (double2*)dx, scal, w.red, w.counter);
+            else
+                fbs_step_pairs_kernel<false><<<grid, VEC_THREADS, 0, st>>>(
+                    (const double2*)x0, (const double2*)g0, tau, nullptr, n / 2, (double2*)xhat, (double2*)x1,
+                    (double2*)dx, scal, w.red, w.counter);
+            return check_launch("fbs_step_pairs");
+        }
+        default: set_error("unknown prox tag %d", prox); return 1;
+    }
+}
+
+extern "C" int fb200_forward_step(const double* x0, const double* g0, double tau, int64_t n, double* xhat,
+                                  void* stream) {
+    forward_step_kernel<<<vec_grid(n), VEC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x0, g0, tau, n, xhat);
+    return check_launch("forward_step");
+}
+
+extern "C" int fb200_step_reduce(const double* x0, const double* x1, const double* xhat, const double* g0,
+                                 const double* xa_prev, int64_t n, double* dx, double* scal, void* ws,
+                                 void* stream) {
+    Workspace w(ws);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (xa_prev)
+        step_reduce_kernel<true><<<vec_grid(n), VEC_THREADS, 0, st>>>(x0, x1, xhat, g0, xa_prev, n, dx, scal, w.red, w.counter);
+    else
+        step_reduce_kernel<false><<<vec_grid(n), VEC_THREADS, 0, st>>>(x0, x1, xhat, g0, nullptr, n, dx, scal, w.red, w.counter);
+    return check_launch("step_reduce");
+}
+
+extern "C" int fb200_prox_apply(const double* x, int prox, double p0, double p1, int64_t n, double* out,
+                                const double* scal, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid  = vec_grid(n);
+    switch (prox) {
+        case FB200_PROX_IDENTITY: prox_apply_kernel<FB200_PROX_IDENTITY><<<grid, VEC_THREADS, 0, st>>>(x, p0, p1, n, out, scal); break;
+        case FB200_PROX_SHRINK:   prox_apply_kernel<FB200_PROX_SHRINK><<<grid, VEC_THREADS, 0, st>>>(x, p0, p1, n, out, scal); break;
+        case FB200_PROX_NONNEG:   prox_apply_kernel<FB200_PROX_NONNEG><<<grid, VEC_THREADS, 0, st>>>(x, p0, p1, n, out, scal); break;
+        case FB200_PROX_BOX:      prox_apply_kernel<FB200_PROX_BOX><<<grid, VEC_THREADS, 0, st>>>(x, p0, p1, n, out, scal); break;
+        case FB200_PROX_L1BALL:   prox_apply_kernel<FB200_PROX_L1BALL><<<grid, VEC_THREADS, 0, st>>>(x, p0, p1, n, out, scal); break;
+        case FB200_PROX_TV_BALL:
+            if (n % 2) { set_error("prox_apply: TV ball prox needs an even element count"); return 1; }
+            prox_apply_kernel<FB200_PROX_TV_BALL><<<grid, VEC_THREADS, 0, st>>>(x, p0, p1, n, out, scal);
+            break;
+        default: set_error("unknown prox tag %d", prox); return 1;
+    }
+    return check_launch("prox_apply");
+}
+
+extern "C" int fb200_l1ball_threshold(const double* v, int64_t n, double radius, double* scal, void* ws,
+                                      void* stream) {
+    (void)ws;
+    l1ball_threshold_kernel<<<1, L1B_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(v, n, radius, scal);
+    return check_launch("l1ball_threshold");
+}
+
+extern "C" int fb200_accel_step(double c, const double* xa1, const double* xa0, const double* xhat, int64_t n,
+                                double* x1, const double* za1, const double* za0, const double* b, int64_t m,
+                                int loss, int prox, double* z1, double* r, double* scal, void* ws, void* stream) {
+    Workspace w(ws);
+    cudaStream_t st  = static_cast<cudaStream_t>(stream);
+    const int grid   = vec_grid(n > m ? n : m);
+    const bool pen   = (prox == FB200_PROX_SHRINK);
+#define FB200_ACCEL(LOSS)                                                                                        \
+    if (pen) accel_step_kernel<LOSS, true><<<grid, VEC_THREADS, 0, st>>>(c, xa1, xa0, xhat, n, x1, za1, za0, b, m, z1, r, scal, w.red, w.counter); \
+    else     accel_step_kernel<LOSS, false><<<grid, VEC_THREADS, 0, st>>>(c, xa1, xa0, xhat, n, x1, za1, za0, b, m, z1, r, scal, w.red, w.counter);
+    switch (loss) {
+        case FB200_LOSS_NONE:          FB200_ACCEL(FB200_LOSS_NONE) break;
+        case FB200_LOSS_LEAST_SQUARES: FB200_ACCEL(FB200_LOSS_LEAST_SQUARES) break;
+        case FB200_LOSS_LOGISTIC:      FB200_ACCEL(FB200_LOSS_LOGISTIC) break;
+        default: set_error("unknown loss tag %d", loss); return 1;
+    }
+#undef FB200_ACCEL
+    return check_launch("accel_step");
+}
+
+extern "C" int fb200_loss_eval(int loss, const double* z, const double* b, int64_t m, double* r, double* scal,
+                               void* ws, void* stream) {
+    Workspace w(ws);
+    return launch_loss(loss, z, 0, 0, b, m, nullptr, r, scal, w, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fb200_bb_reduce(const double* g1, const double* x0, const double* xhat, const double* dx,
+                               double tau, int64_t n, int adaptive, double* scal, void* ws, void* stream) {
+    Workspace w(ws);
+    return launch_bb(adaptive ? 2 : 1, g1, 0, 0, n, nullptr, x0, xhat, dx, tau, scal, w,
+                     static_cast<cudaStream_t>(stream));
+}
+
+template <int OP>
+static int launch_reduce(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream,
+                         const char* name) {
+    Workspace w(ws);
+    reduce_kernel<OP><<<vec_grid(n), VEC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, out, w.red,
+                                                                                         w.counter);
+    return check_launch(name);
+}
+
+extern "C" int fb200_dot(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream) {
+    return launch_reduce<0>(a, b, n, out, ws, stream, "dot");
+}
+extern "C" int fb200_diff_nrm2sq(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream) {
+    return launch_reduce<1>(a, b, n, out, ws, stream, "diff_nrm2sq");
+}
+extern "C" int fb200_asum(const double* a, int64_t n, double* out, void* ws, void* stream) {
+    return launch_reduce<2>(a, nullptr, n, out, ws, stream, "asum");
+}

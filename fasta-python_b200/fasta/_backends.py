@@ -1,0 +1,417 @@
+"""Device back-ends of the FBS loop (see ``_loop.py`` for the protocol).
+
+``FusedBackend``   tagged operator + tagged loss + tagged penalty: an iteration is
+                   fbs_step -> (A x + loss epilogue) -> sync -> (A^H r + BB epilogue) -> sync,
+                   all hand-written sm_100a kernels behind the C ABI (include/fasta_b200.h).
+``GenericBackend`` arbitrary user callables (f, gradf, g, proxg, A) that accept torch CUDA
+                   tensors; the library's own pieces (forward step, reductions, extrapolation,
+                   dense contractions) still run as the same kernels.
+Operator drivers:  ``DenseDriver`` (TMA streaming GEMV / GEMV-T), ``TVDriver`` (stencils),
+                   ``ShardedDriver`` (row-partitioned A over torch.distributed ranks).
+There is no CPU implementation anywhere in this module.
+"""
+
+import numpy as np
+
+from . import _cabi, _device
+from ._loop import Scalars
+
+S = _cabi
+
+
+# =================================================================================================
+# operator drivers: z = A x (+ loss epilogue) and g = A^H r (+ BB epilogue) on raw device tensors
+# =================================================================================================
+class DenseDriver:
+    """Dense row-major M x N matrix in HBM (reference linalg.py:37-41)."""
+
+    def __init__(self, matrix, lda=None):
+        self.A = matrix
+        self.M, self.N = int(matrix.shape[0]), int(matrix.shape[1])
+        self.lda = int(lda if lda is not None else matrix.stride(0))
+        self.xshape, self.zshape = (self.N,), (self.M,)
+        self.lib = _cabi.load()
+        self.launches = 0
+
+    def workspace_dims(self):
+        return self.M, self.N
+
+    def forward(self, x, loss_tag, b, z, r, ws):
+        _cabi.check(self.lib.fb200_gemv_loss(self.A.data_ptr(), self.lda, self.M, self.N, x.data_ptr(), loss_tag,
+                                             _device.ptr(b), z.data_ptr(), _device.ptr(r), ws.scal.data_ptr(),
+                                             ws.buf.data_ptr(), ws.nbytes, _device.stream_ptr()), "fb200_gemv_loss")
+        self.launches += 2
+
+    def adjoint(self, r, g, bb, x0, xhat, dx, tau, ws):
+        _cabi.check(self.lib.fb200_gemvT_bb(self.A.data_ptr(), self.lda, self.M, self.N, r.data_ptr(), g.data_ptr(),
+                                            bb, _device.ptr(x0), _device.ptr(xhat), _device.ptr(dx), float(tau),
+                                            ws.scal.data_ptr(), ws.buf.data_ptr(), ws.nbytes, _device.stream_ptr()),
+                    "fb200_gemvT_bb")
+        self.launches += 2
+
+    def bb_reduce(self, g, x0, xhat, dx, tau, adaptive, ws):
+        _cabi.check(self.lib.fb200_bb_reduce(g.data_ptr(), _device.ptr(x0), _device.ptr(xhat), _device.ptr(dx),
+                                             float(tau), g.numel(), 1 if adaptive else 0, ws.scal.data_ptr(),
+                                             ws.buf.data_ptr(), _device.stream_ptr()), "fb200_bb_reduce")
+        self.launches += 1
+
+    def sync_point(self, v1, v2):
+        pass
+
+
+class TVDriver:
+    """A = div, A^H = grad on an n0 x n1 image (reference tv_denoising.py:26-63,99)."""
+
+    def __init__(self, n0, n1):
+        self.n0, self.n1 = int(n0), int(n1)
+        self.xshape, self.zshape = (self.n0, self.n1, 2), (self.n0, self.n1)
+        self.lib = _cabi.load()
+        self.launches = 0
+
+    def workspace_dims(self):
+        return 1, 1
+
+    def forward(self, x, loss_tag, b, z, r, ws):
+        _cabi.check(self.lib.fb200_tv_div_loss(x.data_ptr(), self.n0, self.n1, loss_tag, _device.ptr(b), z.data_ptr(),
+                                               _device.ptr(r), ws.scal.data_ptr(), ws.buf.data_ptr(),
+                                               _device.stream_ptr()), "fb200_tv_div_loss")
+        self.launches += 1
+
+    def adjoint(self, r, g, bb, x0, xhat, dx, tau, ws):
+        _cabi.check(self.lib.fb200_tv_grad_bb(r.data_ptr(), self.n0, self.n1, g.data_ptr(), bb, _device.ptr(x0),
+                                              _device.ptr(xhat), _device.ptr(dx), float(tau), ws.scal.data_ptr(),
+                                              ws.buf.data_ptr(), _device.stream_ptr()), "fb200_tv_grad_bb")
+        self.launches += 1
+
+    def sync_point(self, v1, v2):
+        pass
+
+
+class ShardedDriver:
+    """Row-partitioned map: this rank holds a row block of A (and of b) in ``local``.
+
+    A x is local; the loss partial sum and the A^H r partial vector are combined with
+    ``torch.distributed.all_reduce`` (NCCL over NVLink on GPUs; gloo in the CPU tests of the
+    host logic).  x, the gradient, the step size and all histories are replicated, so every rank
+    runs the identical scalar control flow.
+    """
+
+    def __init__(self, local, group=None):
+        import torch.distributed as dist
+        self.local = local
+        self.dist = dist
+        self.group = group
+        self.xshape, self.zshape = local.xshape, local.zshape
+        self.collectives = 0
+
+    @property
+    def launches(self):
+        return self.local.launches
+
+    def workspace_dims(self):
+        return self.local.workspace_dims()
+
+    def _root(self):
+        return self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
+
+    def forward(self, x, loss_tag, b, z, r, ws):
+        self.local.forward(x, loss_tag, b, z, r, ws)
+        if loss_tag != S.LOSS_NONE:
+            self.reduce_loss(ws)
+
+    def adjoint(self, r, g, bb, x0, xhat, dx, tau, ws):
+        self.local.adjoint(r, g, 0, None, None, None, 0.0, ws)
+        self.dist.all_reduce(g, group=self.group)
+        self.collectives += 1
+        if bb:
+            self.local.bb_reduce(g, x0, xhat, dx, tau, bb >= 2, ws)
+
+    def reduce_loss(self, ws):
+        self.dist.all_reduce(ws.scal[S.S_F:S.S_F + 1], group=self.group)
+        self.collectives += 1
+
+    def sync_point(self, v1, v2):
+        # every rank must use the same two random probes for the Lipschitz estimate
+        self.dist.broadcast(v1, src=self._root(), group=self.group)
+        self.dist.broadcast(v2, src=self._root(), group=self.group)
+
+
+# =================================================================================================
+# fused back-end
+# =================================================================================================
+class FusedBackend:
+    def __init__(self, driver, loss, penalty, x0, accelerate):
+        t = _device.torch()
+        self.t = t
+        self.lib = _cabi.load()
+        self.drv = driver
+        self.loss = loss
+        self.pen = penalty
+        self.accelerate = bool(accelerate)
+        self.x0_in = x0
+        self.shape = tuple(x0.shape)
+        assert self.shape == tuple(driver.xshape), f"x0 shape {self.shape} != operator domain {driver.xshape}"
+        assert tuple(loss.b.shape) == tuple(driver.zshape), "loss data does not match the operator range"
+        dev = loss.b.device
+        self.n = int(np.prod(driver.xshape))
+        self.m = int(np.prod(driver.zshape))
+        self.ws = _device.Workspace(*driver.workspace_dims(), device=dev)
+        new = lambda k: t.empty(k, dtype=t.float64, device=dev)
+        self.X = [new(self.n), new(self.n)]
+        self.G = [new(self.n), new(self.n)]
+        self.XH, self.DX, self.BEST = new(self.n), new(self.n), new(self.n)
+        self.Z, self.R = new(self.m), new(self.m)
+        if self.accelerate:
+            self.XA = [new(self.n), new(self.n)]
+            self.ZA = [new(self.m), new(self.m)]
+        self.ic = self.ip = 0      # X[ic] current iterate, X[ip] previous
+        self.gc = self.gp = 0      # G[gc] current gradient, G[gp] previous
+        self.ac = self.ap = 0      # XA/ZA[ac] current prox point, [ap] previous
+        self.launches = 0          # kernels launched by this backend (vector kernels; + driver.launches)
+
+    # -- helpers --------------------------------------------------------------------------------
+    def _st(self):
+        return _device.stream_ptr()
+
+    def total_launches(self):
+        return self.launches + self.drv.launches
+
+    # -- protocol -------------------------------------------------------------------------------
+    def load(self):
+        x0d = _device.to_device(self.x0_in, self.X[0].device).reshape(-1)
+        self.X[self.ic].copy_(x0d)
+        self.BEST.copy_(x0d)
+        if self.accelerate:
+            self.XA[self.ac].copy_(x0d)
+
+    def lipschitz(self, v1, v2):
+        t = self.t
+        a = self.XH
+        b = self.DX
+        a.copy_(t.from_numpy(np.ascontiguousarray(v1.reshape(-1))), non_blocking=False)
+        b.copy_(t.from_numpy(np.ascontiguousarray(v2.reshape(-1))), non_blocking=False)
+        self.drv.sync_point(a, b)
+        d1, d2 = self.G[0], self.G[1]
+        for v, d in ((a, d1), (b, d2)):
+            self.drv.forward(v, self.loss.tag, self.loss.b, self.Z, self.R, self.ws)
+            self.drv.adjoint(self.R, d, 0, None, None, None, 0.0, self.ws)
+        sc = self.ws.scal
+        _cabi.check(self.lib.fb200_diff_nrm2sq(d1.data_ptr(), d2.data_ptr(), self.n, sc[S.S_AUX0:].data_ptr(),
+                                               self.ws.buf.data_ptr(), self._st()), "fb200_diff_nrm2sq")
+        _cabi.check(self.lib.fb200_diff_nrm2sq(a.data_ptr(), b.data_ptr(), self.n, sc[S.S_AUX1:].data_ptr(),
+                                               self.ws.buf.data_ptr(), self._st()), "fb200_diff_nrm2sq")
+        self.launches += 2
+        s = self.ws.fetch()
+        return np.sqrt(s[S.S_AUX0]), np.sqrt(s[S.S_AUX1])
+
+    def _penalty_of(self, x):
+        """raw penalty reduction of a vector (only the l1 norm needs one)."""
+        if self.pen.tag == S.PROX_SHRINK:
+            _cabi.check(self.lib.fb200_asum(x.data_ptr(), self.n, self.ws.scal[S.S_PEN:].data_ptr(),
+                                            self.ws.buf.data_ptr(), self._st()), "fb200_asum")
+            self.launches += 1
+
+    def start(self):
+        z = self.ZA[self.ac] if self.accelerate else self.Z
+        self.drv.forward(self.X[self.ic], self.loss.tag, self.loss.b, z, self.R, self.ws)
+        self.drv.adjoint(self.R, self.G[self.gc], 1, None, None, None, 0.0, self.ws)
+        self._penalty_of(self.X[self.ic])
+        s = self.ws.fetch()
+        return Scalars(f=self.loss.finalize(s[S.S_F]), pen=self.pen.value(s[S.S_PEN]), g_sq=s[S.S_G1_SQ])
+
+    def advance(self):
+        self.ip, self.ic = self.ic, 1 - self.ic
+        self.gp, self.gc = self.gc, 1 - self.gc
+        if self.accelerate:
+            self.ap, self.ac = self.ac, 1 - self.ac
+
+    def trial(self, tau):
+        x0, g0 = self.X[self.ip], self.G[self.gp]
+        x1 = self.XA[self.ac] if self.accelerate else self.X[self.ic]
+        z1 = self.ZA[self.ac] if self.accelerate else self.Z
+        xa_prev = self.XA[self.ap] if self.accelerate else None
+        p0, p1 = self.pen.params(tau)
+        st = self._st()
+        if self.pen.tag == S.PROX_L1BALL:
+            _cabi.check(self.lib.fb200_forward_step(x0.data_ptr(), g0.data_ptr(), float(tau), self.n,
+                                                    self.XH.data_ptr(), st), "fb200_forward_step")
+            _cabi.check(self.lib.fb200_l1ball_threshold(self.XH.data_ptr(), self.n, float(self.pen.radius),
+                                                        self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
+                        "fb200_l1ball_threshold")
+            self.launches += 2
+        _cabi.check(self.lib.fb200_fbs_step(x0.data_ptr(), g0.data_ptr(), float(tau), self.pen.tag, float(p0), float(p1),
+                                            _device.ptr(xa_prev), self.n, self.XH.data_ptr(), x1.data_ptr(),
+                                            self.DX.data_ptr(), self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
+                    "fb200_fbs_step")
+        self.launches += 1
+        self.drv.forward(x1, self.loss.tag, self.loss.b, z1, self.R, self.ws)
+        s = self.ws.fetch()
+        return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
+                       xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART])
+
+    def extrapolate(self, c):
+        _cabi.check(self.lib.fb200_accel_step(float(c), self.XA[self.ac].data_ptr(), self.XA[self.ap].data_ptr(),
+                                              self.XH.data_ptr(), self.n, self.X[self.ic].data_ptr(),
+                                              self.ZA[self.ac].data_ptr(), self.ZA[self.ap].data_ptr(),
+                                              self.loss.b.data_ptr(), self.m, self.loss.tag, self.pen.tag,
+                                              self.Z.data_ptr(), self.R.data_ptr(), self.ws.scal.data_ptr(),
+                                              self.ws.buf.data_ptr(), self._st()), "fb200_accel_step")
+        self.launches += 1
+        if hasattr(self.drv, "reduce_loss"):
+            self.drv.reduce_loss(self.ws)
+        s = self.ws.fetch()
+        return Scalars(f=self.loss.finalize(s[S.S_F]), xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]))
+
+    def gradient(self, tau, adaptive):
+        self.drv.adjoint(self.R, self.G[self.gc], 2 if adaptive else 1, self.X[self.ip], self.XH, self.DX, tau, self.ws)
+        s = self.ws.fetch()
+        return Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
+
+    def keep_best(self):
+        self.BEST.copy_(self.X[self.ic])
+
+    def iterate(self):
+        return _device.like_input(self.X[self.ic].view(self.shape), self.x0_in)
+
+    def solution(self):
+        return _device.like_input(self.BEST.clone().view(self.shape), self.x0_in)
+
+
+# =================================================================================================
+# generic back-end: user callables on torch CUDA tensors
+# =================================================================================================
+def _scalar(v):
+    if hasattr(v, "item"):
+        v = v.item()
+    return np.float64(v)
+
+
+class GenericBackend:
+    def __init__(self, A, f, gradf, g, proxg, x0, accelerate, need_objective):
+        t = _device.torch()
+        self.t = t
+        self.lib = _cabi.load()
+        self.A, self.f, self.gradf, self.g, self.proxg = A, f, gradf, g, proxg
+        self.accelerate = bool(accelerate)
+        self.need_objective = bool(need_objective)
+        self.x0_in = x0
+        self.shape = tuple(x0.shape)
+        self.n = int(np.prod(self.shape))
+        self.ws = _device.Workspace(1, 1)
+        self.launches = 0
+        self.x1 = self.x0 = self.g1 = self.g0 = self.z1 = None
+        self.xhat = self.dx = self.best = None
+        self.xa1 = self.xa0 = self.za1 = self.za0 = None
+
+    def total_launches(self):
+        return self.launches
+
+    def _dev(self, a):
+        return _device.to_device(a)
+
+    def _flat(self, a):
+        return a.contiguous().view(-1)
+
+    def load(self):
+        self.x1 = self._dev(self.x0_in).clone()
+        self.best = self.x1
+        if self.accelerate:
+            self.xa1 = self.x1
+
+    def lipschitz(self, v1, v2):
+        a, b = self._dev(v1), self._dev(v2)
+        d1 = self._dev(self.A.H(self.gradf(self.A(a))))
+        d2 = self._dev(self.A.H(self.gradf(self.A(b))))
+        sc = self.ws.scal
+        st = _device.stream_ptr()
+        _cabi.check(self.lib.fb200_diff_nrm2sq(self._flat(d1).data_ptr(), self._flat(d2).data_ptr(), self.n,
+                                               sc[S.S_AUX0:].data_ptr(), self.ws.buf.data_ptr(), st), "fb200_diff_nrm2sq")
+        _cabi.check(self.lib.fb200_diff_nrm2sq(self._flat(a).data_ptr(), self._flat(b).data_ptr(), self.n,
+                                               sc[S.S_AUX1:].data_ptr(), self.ws.buf.data_ptr(), st), "fb200_diff_nrm2sq")
+        self.launches += 2
+        s = self.ws.fetch()
+        return np.sqrt(s[S.S_AUX0]), np.sqrt(s[S.S_AUX1])
+
+    def _grad(self):
+        self.g1 = self._dev(self.A.H(self.gradf(self.z1)))
+
+    def start(self):
+        self.z1 = self._dev(self.A(self.x1))
+        if self.accelerate:
+            self.za1 = self.z1
+        f1 = _scalar(self.f(self.z1))
+        self._grad()
+        g = self._flat(self.g1)
+        _cabi.check(self.lib.fb200_dot(g.data_ptr(), g.data_ptr(), self.n, self.ws.scal[S.S_G1_SQ:].data_ptr(),
+                                       self.ws.buf.data_ptr(), _device.stream_ptr()), "fb200_dot")
+        self.launches += 1
+        s = self.ws.fetch()
+        pen = _scalar(self.g(self.x1)) if self.need_objective else 0
+        return Scalars(f=f1, pen=pen, g_sq=s[S.S_G1_SQ])
+
+    def advance(self):
+        self.x0, self.g0 = self.x1, self.g1
+        if self.accelerate:
+            self.xa0, self.za0 = self.xa1, self.za1
+
+    def trial(self, tau):
+        t = self.t
+        st = _device.stream_ptr()
+        x0f, g0f = self._flat(self.x0), self._flat(self.g0)
+        self.xhat = t.empty_like(self.x0)
+        _cabi.check(self.lib.fb200_forward_step(x0f.data_ptr(), g0f.data_ptr(), float(tau), self.n,
+                                                self.xhat.data_ptr(), st), "fb200_forward_step")
+        x1 = self._dev(self.proxg(self.xhat, tau))
+        if x1.data_ptr() == self.xhat.data_ptr():       # identity prox returns its argument
+            x1 = x1.clone()
+        self.dx = t.empty_like(self.x0)
+        xa_prev = self._flat(self.xa0) if self.accelerate else None
+        _cabi.check(self.lib.fb200_step_reduce(x0f.data_ptr(), self._flat(x1).data_ptr(), self.xhat.data_ptr(),
+                                               g0f.data_ptr(), _device.ptr(xa_prev), self.n, self.dx.data_ptr(),
+                                               self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st), "fb200_step_reduce")
+        self.launches += 2
+        self.x1 = x1
+        self.z1 = self._dev(self.A(x1))
+        if self.accelerate:
+            self.xa1, self.za1 = self.x1, self.z1
+        f1 = _scalar(self.f(self.z1))
+        s = self.ws.fetch()
+        pen = _scalar(self.g(self.x1)) if (self.need_objective and not self.accelerate) else 0
+        return Scalars(f=f1, dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ], xmxh_sq=s[S.S_XMXH_SQ], pen=pen,
+                       restart=s[S.S_RESTART])
+
+    def extrapolate(self, c):
+        t = self.t
+        x1 = t.empty_like(self.xa1)
+        z1 = t.empty_like(self.za1)
+        m = z1.numel()
+        _cabi.check(self.lib.fb200_accel_step(float(c), self._flat(self.xa1).data_ptr(), self._flat(self.xa0).data_ptr(),
+                                              self.xhat.data_ptr(), self.n, x1.data_ptr(),
+                                              self._flat(self.za1).data_ptr(), self._flat(self.za0).data_ptr(), 0, m,
+                                              S.LOSS_NONE, S.PROX_IDENTITY, z1.data_ptr(), 0, self.ws.scal.data_ptr(),
+                                              self.ws.buf.data_ptr(), _device.stream_ptr()), "fb200_accel_step")
+        self.launches += 1
+        self.x1, self.z1 = x1, z1
+        f1 = _scalar(self.f(self.z1))
+        s = self.ws.fetch()
+        pen = _scalar(self.g(self.x1)) if self.need_objective else 0
+        return Scalars(f=f1, xmxh_sq=s[S.S_XMXH_SQ], pen=pen)
+
+    def gradient(self, tau, adaptive):
+        self._grad()
+        _cabi.check(self.lib.fb200_bb_reduce(self._flat(self.g1).data_ptr(), self._flat(self.x0).data_ptr(),
+                                             self.xhat.data_ptr(), self.dx.data_ptr(), float(tau), self.n,
+                                             1 if adaptive else 0, self.ws.scal.data_ptr(), self.ws.buf.data_ptr(),
+                                             _device.stream_ptr()), "fb200_bb_reduce")
+        self.launches += 1
+        s = self.ws.fetch()
+        return Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
+
+    def keep_best(self):
+        self.best = self.x1
+
+    def iterate(self):
+        return _device.like_input(self.x1, self.x0_in)
+
+    def solution(self):
+        return _device.like_input(self.best.clone(), self.x0_in)

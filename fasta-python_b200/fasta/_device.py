@@ -1,0 +1,92 @@
+"""Device-buffer plumbing: torch tensors are the buffer type, ctypes pointers cross the C ABI."""
+
+import numpy as np
+
+from . import _cabi
+
+
+def torch():
+    return _cabi.require_cuda()
+
+
+def is_array(x) -> bool:
+    if isinstance(x, np.ndarray):
+        return True
+    try:
+        import torch as _t
+        return isinstance(x, _t.Tensor)
+    except Exception:       # pragma: no cover
+        return False
+
+
+def is_numpy(x) -> bool:
+    return isinstance(x, np.ndarray)
+
+
+def to_device(x, device=None):
+    """fp64, contiguous, CUDA copy/borrow of a numpy array or torch tensor."""
+    t = torch()
+    device = device or t.device("cuda", t.cuda.current_device())
+    if isinstance(x, np.ndarray):
+        return t.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(device)
+    if isinstance(x, t.Tensor):
+        return x.to(device=device, dtype=t.float64).contiguous()
+    return t.as_tensor(np.asarray(x, dtype=np.float64), device=device)
+
+
+def like_input(dev_tensor, template):
+    """Hand a result back in the caller's array type (numpy in -> numpy out)."""
+    if isinstance(template, np.ndarray) or not is_array(template):
+        return dev_tensor.detach().cpu().numpy()
+    return dev_tensor
+
+
+def ptr(tensor):
+    return 0 if tensor is None else tensor.data_ptr()
+
+
+def stream_ptr():
+    return torch().cuda.current_stream().cuda_stream
+
+
+class Workspace:
+    """Zero-initialised device workspace + scalar block + pinned host mirror for one solve."""
+
+    def __init__(self, M, N, device=None):
+        t = torch()
+        self.lib = _cabi.load()
+        self.device = device or t.device("cuda", t.cuda.current_device())
+        self.nbytes = int(self.lib.fb200_workspace_bytes(int(M), int(N)))
+        self.buf = t.zeros(self.nbytes, dtype=t.uint8, device=self.device)
+        self.scal = t.zeros(_cabi.NSCAL, dtype=t.float64, device=self.device)
+        self.host = t.zeros(_cabi.NSCAL, dtype=t.float64).pin_memory()
+        self._np = self.host.numpy()
+
+    def grow(self, M, N):
+        need = int(self.lib.fb200_workspace_bytes(int(M), int(N)))
+        if need > self.nbytes:
+            t = torch()
+            self.buf = t.zeros(need, dtype=t.uint8, device=self.device)
+            self.nbytes = need
+
+    def fetch(self):
+        """One D2H copy of the scalar block + one stream sync: the per-decision-point sync."""
+        t = torch()
+        self.host.copy_(self.scal, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        return self._np      # np.float64 elements
+
+
+_shared_ws = {}
+
+
+def shared_workspace(M=1, N=1):
+    """Per-device workspace for stand-alone operator / prox calls outside a solve."""
+    t = torch()
+    dev = t.cuda.current_device()
+    ws = _shared_ws.get(dev)
+    if ws is None:
+        ws = _shared_ws[dev] = Workspace(M, N)
+    else:
+        ws.grow(M, N)
+    return ws

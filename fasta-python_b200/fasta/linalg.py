@@ -1,0 +1,177 @@
+"""Linear-map objects for fasta(): drop-in for the reference ``fasta/linalg.py``.
+
+``LinearMap`` keeps the reference's surface (constructor, ``from_matrix``, ``identity``,
+``__call__``, ``.H``, ``@ * - + **``, ``is_operator``, ``eigs``; reference linalg.py:13-160) and its
+bare-``assert`` shape checks.  What differs is where the arithmetic runs: ``from_matrix`` returns a
+``DenseMap`` whose two contractions are the hand-written sm_100a streaming kernels behind
+``fb200_gemv_loss`` / ``fb200_gemvT_bb`` (csrc/dense_stream.cu), and which the solver recognises
+so that it can fuse the loss / step / prox epilogues around them.
+
+Array types: maps accept numpy arrays or torch tensors and answer in the same type; all compute
+is on the current CUDA device (numpy inputs are uploaded, results downloaded).
+"""
+
+from functools import reduce
+from operator import mul
+from typing import Callable, Tuple
+
+import numpy as np
+
+from . import _cabi, _device
+
+Matrix = np.ndarray
+Vector = np.ndarray
+
+__all__ = ["LinearMap", "LinearOperator", "DenseMap", "Matrix", "Vector"]
+
+
+class LinearMap:
+    """A linear map V -> W on n-dimensional arrays with an adjoint (reference linalg.py:13-35)."""
+
+    def __init__(self, map_func: Callable, adj_func: Callable, Vshape: Tuple[int, ...], Wshape: Tuple[int, ...] = None):
+        # 3-argument legacy form LinearOperator(map, adj, shape) (democratic_representation.py:80-82)
+        if Wshape is None:
+            Wshape = Vshape
+        self.map_func = map_func
+        self.adj_func = adj_func
+        self.Vshape = tuple(Vshape)
+        self.Wshape = tuple(Wshape)
+
+    # -- constructors ---------------------------------------------------------------------------
+    @staticmethod
+    def from_matrix(A) -> "DenseMap":
+        """Linear map of a 2-D array, x -> A @ x with adjoint y -> A.T @ y (reference linalg.py:37-41)."""
+        assert A.ndim == 2
+        return DenseMap(A)
+
+    @staticmethod
+    def identity(shape: Tuple[int, ...]) -> "LinearMap":
+        """The identity on arrays of ``shape``; returns its argument object itself (reference linalg.py:43-50)."""
+        return LinearMap(lambda x: x, lambda x: x, shape, shape)
+
+    # -- application ----------------------------------------------------------------------------
+    def __call__(self, v):
+        assert tuple(v.shape) == self.Vshape
+        w = self.map_func(v)
+        assert tuple(w.shape) == self.Wshape
+        return w
+
+    @property
+    def H(self) -> "LinearMap":
+        """The adjoint map; a fresh object per access (reference linalg.py:63-69)."""
+        return LinearMap(self.adj_func, self.map_func, self.Wshape, self.Vshape)
+
+    # -- algebra (reference linalg.py:71-139, including its labelling of compositions) ------------
+    def __matmul__(self, B: "LinearMap") -> "LinearMap":
+        assert isinstance(B, LinearMap) and self.Wshape == B.Vshape
+        return LinearMap(lambda x: self(B(x)), lambda x: B.H(self.H(x)), self.Vshape, B.Wshape)
+
+    def __rmul__(self, k) -> "LinearMap":
+        assert np.isscalar(k)
+        return LinearMap(lambda x: k * self(x), lambda x: k * self.H(x), self.Vshape, self.Wshape)
+
+    def __mul__(self, k) -> "LinearMap":
+        return k * self
+
+    def __neg__(self) -> "LinearMap":
+        return (-1) * self
+
+    def __add__(self, B: "LinearMap") -> "LinearMap":
+        assert isinstance(B, LinearMap) and self.Vshape == B.Vshape and self.Wshape == B.Wshape
+        return LinearMap(lambda x: self(x) + B(x), lambda x: self.H(x) + B.H(x), self.Vshape, self.Wshape)
+
+    def __sub__(self, B: "LinearMap") -> "LinearMap":
+        return self + (-B)
+
+    @property
+    def is_operator(self) -> bool:
+        return self.Vshape == self.Wshape
+
+    def __pow__(self, n: int, modulo=None) -> "LinearMap":
+        assert self.is_operator
+        out = LinearMap.identity(self.Vshape)
+        for _ in range(n):
+            out @= self
+        return out
+
+    # -- scipy bridge (reference linalg.py:141-160); off the hot path -----------------------------
+    @property
+    def _scipy(self):
+        from scipy.sparse import linalg as sla
+        m = reduce(mul, self.Vshape, 1)
+        n = reduce(mul, self.Wshape, 1)
+        return sla.LinearOperator((m, n), matvec=lambda x: np.ravel(self(x)), rmatvec=lambda x: np.ravel(self.H(x)))
+
+    def eigs(self, k: int = 1):
+        assert self.is_operator
+        from scipy.sparse import linalg as sla
+        values, vectors = sla.eigs(self._scipy, k)
+        return values, np.reshape(vectors, (k,) + self.Wshape)
+
+
+class DenseMap(LinearMap):
+    """x -> A @ x for a dense row-major fp64 matrix resident in HBM (what ``from_matrix`` returns).
+
+    The matrix is uploaded once (numpy input) or borrowed (CUDA tensor with unit column stride);
+    ``.H`` shares the same buffer -- like the reference's ``A.T`` view, both contractions stream
+    the one row-major copy.  ``_fb200_dense`` is the tag the solver looks for.
+    """
+
+    def __init__(self, A, _transposed=False, _dev=None):
+        if _dev is None:
+            t = _device.torch()
+            if isinstance(A, t.Tensor) and A.is_cuda and A.dtype == t.float64 and A.stride(1) == 1 and A.stride(0) >= A.shape[1]:
+                _dev = A                       # borrow: may be a row-slice view of a larger matrix
+            else:
+                _dev = _device.to_device(A)
+        self.matrix = _dev
+        self.transposed = bool(_transposed)
+        M, N = self.matrix.shape
+        self.M, self.N, self.lda = int(M), int(N), int(self.matrix.stride(0))
+        V, W = ((N,), (M,)) if not self.transposed else ((M,), (N,))
+        super().__init__(self._apply, self._apply_adjoint, V, W)
+
+    _fb200_dense = True
+
+    @property
+    def H(self) -> "DenseMap":
+        return DenseMap(None, _transposed=not self.transposed, _dev=self.matrix)
+
+    @property
+    def uses_tma(self) -> bool:
+        lib = _cabi.load()
+        return bool(lib.fb200_dense_uses_tma(self.matrix.data_ptr(), self.lda, self.M, self.N))
+
+    # raw device contractions (used by the solver back-ends too)
+    def gemv_into(self, x_dev, z_dev, ws):
+        lib = _cabi.load()
+        _cabi.check(lib.fb200_gemv_loss(self.matrix.data_ptr(), self.lda, self.M, self.N, x_dev.data_ptr(),
+                                        _cabi.LOSS_NONE, 0, z_dev.data_ptr(), 0, ws.scal.data_ptr(),
+                                        ws.buf.data_ptr(), ws.nbytes, _device.stream_ptr()), "fb200_gemv_loss")
+
+    def gemvT_into(self, r_dev, g_dev, ws):
+        lib = _cabi.load()
+        _cabi.check(lib.fb200_gemvT_bb(self.matrix.data_ptr(), self.lda, self.M, self.N, r_dev.data_ptr(),
+                                       g_dev.data_ptr(), 0, 0, 0, 0, 0.0, ws.scal.data_ptr(), ws.buf.data_ptr(),
+                                       ws.nbytes, _device.stream_ptr()), "fb200_gemvT_bb")
+
+    def _run(self, v, transposed):
+        t = _device.torch()
+        ws = _device.shared_workspace(self.M, self.N)
+        x = _device.to_device(v, self.matrix.device).reshape(-1)
+        out = t.empty(self.N if transposed else self.M, dtype=t.float64, device=self.matrix.device)
+        if transposed:
+            self.gemvT_into(x, out, ws)
+        else:
+            self.gemv_into(x, out, ws)
+        return _device.like_input(out, v)
+
+    def _apply(self, v):
+        return self._run(v, self.transposed)
+
+    def _apply_adjoint(self, v):
+        return self._run(v, not self.transposed)
+
+
+# legacy name used by every reference example (``from fasta.linalg import LinearOperator``)
+LinearOperator = LinearMap

@@ -1,0 +1,149 @@
+/*
+ * fasta_b200.h -- C ABI of libfasta_b200.so: the sm_100a kernels under FASTA's
+ * forward-backward-splitting loop.
+ *
+ * The reference (phasepack/fasta-python) has no FFI: its "operator interface" is the Python
+ * callable protocol of fasta.fasta() (reference fasta/__init__.py:38-53).  Each entry point below
+ * replaces the numpy expression(s) cited next to it; INTEGRATION.md shows the ctypes stubs a
+ * maintainer of the reference would add to route those expressions here.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure (fb200_last_error() has text);
+ *     nothing throws across the boundary;
+ *   - all pointers are BORROWED device pointers (fp64, densely packed unless an lda is given);
+ *     the library allocates nothing persistent;
+ *   - `ws` is a caller-owned, zero-initialised device workspace of at least
+ *     fb200_workspace_bytes(M, N) bytes, reused by consecutive calls on one stream;
+ *   - `scal` is a caller-owned device array of FB200_NSCAL doubles that receives the reduction
+ *     results (slot indices FB200_S_*); the caller copies it to the host once per decision point;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they never synchronise;
+ *   - reductions are atomics-free and fixed-order: results are bit-reproducible run to run.
+ */
+#ifndef FASTA_B200_H
+#define FASTA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_ABI_VERSION 1
+#define FB200_NSCAL 32
+
+/* slots of the device scalar block */
+enum {
+    FB200_S_F        = 0,  /* raw loss reduction: sum (z-b)^2 (least squares) or the logistic sum */
+    FB200_S_DX_G0    = 1,  /* <Dx, gradf0>                      __init__.py:200 */
+    FB200_S_DX_SQ    = 2,  /* <Dx, Dx>                          __init__.py:200,258,272 */
+    FB200_S_XMXH_SQ  = 3,  /* <x1 - x1hat, x1 - x1hat>          __init__.py:274 */
+    FB200_S_PEN      = 4,  /* raw penalty reduction: sum |x1|   sparse_least_squares.py:43 */
+    FB200_S_RESTART  = 5,  /* <x0 - x1, x1 - x_accel0>          __init__.py:231 */
+    FB200_S_DX_DG    = 6,  /* <Dx, Dg>                          __init__.py:255 */
+    FB200_S_DG_SQ    = 7,  /* <Dg, Dg>                          __init__.py:260 */
+    FB200_S_G1_SQ    = 8,  /* <gradf1, gradf1> (next iteration's |gradf0|)  __init__.py:274 */
+    FB200_S_THETA    = 9,  /* l1-ball projection threshold      proximal.py:26 */
+    FB200_S_AUX0     = 10, /* dot / norm helpers write here by default */
+    FB200_S_AUX1     = 11,
+    FB200_S_AUX2     = 12,
+    FB200_S_AUX3     = 13
+};
+
+/* loss tags: f and gradf evaluated on z = A x */
+enum {
+    FB200_LOSS_NONE          = 0,  /* no loss: only z is produced */
+    FB200_LOSS_LEAST_SQUARES = 1,  /* f=.5|z-b|^2, gradf=z-b        sparse_least_squares.py:41-42 */
+    FB200_LOSS_LOGISTIC      = 2   /* f=sum log(1+e^z)-(b==1)z, gradf=-b/(1+e^{bz})  sparse_logistic.py:47-48 */
+};
+
+/* prox tags: x1 = prox(x1hat, t) */
+enum {
+    FB200_PROX_IDENTITY = 0,  /* g is None                          __init__.py:88-90 */
+    FB200_PROX_SHRINK   = 1,  /* sign(x)*max(|x|-p0,0)              proximal.py:67 */
+    FB200_PROX_NONNEG   = 2,  /* max(x,0)                           nn_least_squares.py:42 */
+    FB200_PROX_BOX      = 3,  /* min(max(x,p0),p1)                  svm.py:71 */
+    FB200_PROX_L1BALL   = 4,  /* shrink by scal[FB200_S_THETA]      proximal.py:34-41 (after fb200_l1ball_threshold) */
+    FB200_PROX_TV_BALL  = 5   /* pairs (y0,y1) / max(|y|_2, 1)      tv_denoising.py:89-96 */
+};
+
+int         fb200_abi_version(void);
+const char* fb200_last_error(void);
+/* bytes of zero-initialised workspace needed for an M x N dense map (or vectors up to max(M,N)) */
+size_t      fb200_workspace_bytes(int64_t M, int64_t N);
+/* 1 if the TMA (cp.async.bulk.tensor) streaming path will be used for this matrix, else 0 */
+int         fb200_dense_uses_tma(const double* A, int64_t lda, int64_t M, int64_t N);
+
+/* ---- K1-K3: forward step, backward (prox) step and their reductions -------------------------
+ * xhat = x0 - tau*g0 ; x1 = prox(xhat) ; dx = x1 - x0            __init__.py:181,184,186 (redo :207-211)
+ * scal[S_DX_G0, S_DX_SQ, S_XMXH_SQ, S_PEN] and, when xa_prev != NULL, scal[S_RESTART].       */
+int fb200_fbs_step(const double* x0, const double* g0, double tau, int prox, double p0, double p1,
+                   const double* xa_prev, int64_t n, double* xhat, double* x1, double* dx,
+                   double* scal, void* ws, void* stream);
+
+/* generic-path pieces of the same step, for untagged (user-callable) prox operators:
+ *   forward_step: xhat = x0 - tau*g0                              __init__.py:181
+ *   step_reduce : dx = x1 - x0 and the reductions of fbs_step     __init__.py:186,200,231,274
+ *   prox_apply  : out = prox(x) for a tagged prox (stand-alone use of fasta.proximal.*)       */
+int fb200_forward_step(const double* x0, const double* g0, double tau, int64_t n, double* xhat,
+                       void* stream);
+int fb200_step_reduce(const double* x0, const double* x1, const double* xhat, const double* g0,
+                      const double* xa_prev, int64_t n, double* dx, double* scal, void* ws,
+                      void* stream);
+int fb200_prox_apply(const double* x, int prox, double p0, double p1, int64_t n, double* out,
+                     const double* scal, void* stream);
+
+/* threshold of the Euclidean projection of v onto {|x|_1 <= radius} -> scal[S_THETA]
+ * (0 when v is already inside)                                    proximal.py:12-41            */
+int fb200_l1ball_threshold(const double* v, int64_t n, double radius, double* scal, void* ws,
+                           void* stream);
+
+/* ---- K9: FISTA extrapolation                                     __init__.py:242-245,274,285
+ * x1 = xa1 + c*(xa1 - xa0) ; z1 = za1 + c*(za1 - za0) ; r = gradf(z1)
+ * scal[S_F] (loss at z1), scal[S_XMXH_SQ] (|x1 - xhat|^2), scal[S_PEN] (penalty of x1)        */
+int fb200_accel_step(double c, const double* xa1, const double* xa0, const double* xhat, int64_t n,
+                     double* x1, const double* za1, const double* za0, const double* b, int64_t m,
+                     int loss, int prox, double* z1, double* r, double* scal, void* ws, void* stream);
+
+/* ---- K5 stand-alone: r = gradf(z), scal[S_F] = raw f(z)          sparse_least_squares.py:41-42 */
+int fb200_loss_eval(int loss, const double* z, const double* b, int64_t m, double* r, double* scal,
+                    void* ws, void* stream);
+
+/* ---- K8: Barzilai-Borwein reductions                             __init__.py:254-260,274
+ * dg = g1 + (xhat - x0)/tau ; scal[S_DX_DG, S_DG_SQ] (if adaptive) and scal[S_G1_SQ]         */
+int fb200_bb_reduce(const double* g1, const double* x0, const double* xhat, const double* dx,
+                    double tau, int64_t n, int adaptive, double* scal, void* ws, void* stream);
+
+/* ---- K4+K5: z = A x fused with the loss epilogue                 linalg.py:41 (A @ x), __init__.py:187-188
+ * A is M x N row-major with leading dimension lda (elements).  z, r are length M.
+ * loss == FB200_LOSS_NONE: only z is written (r, b may be NULL).                              */
+int fb200_gemv_loss(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss,
+                    const double* b, double* z, double* r, double* scal, void* ws, size_t ws_bytes,
+                    void* stream);
+
+/* ---- K7+K8: g = A^T r fused with the Barzilai-Borwein epilogue   linalg.py:41 (A.T @ x), __init__.py:248-260
+ * bb: 0 = only g; 1 = g and scal[S_G1_SQ]; 2 = also scal[S_DX_DG, S_DG_SQ] (needs x0,xhat,dx,tau) */
+int fb200_gemvT_bb(const double* A, int64_t lda, int64_t M, int64_t N, const double* r, double* g,
+                   int bb, const double* x0, const double* xhat, const double* dx, double tau,
+                   double* scal, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K11/K12: total-variation stencils (periodic)               tv_denoising.py:26-63
+ * Y is n0 x n1 x 2 (last axis interleaved), Z is n0 x n1.
+ * div:  Z = sum_d roll(Y[...,d],-1,d) - Y[...,d], fused with the loss epilogue like gemv_loss.
+ * grad: G[...,d] = roll(R,+1,d) - R, fused with the BB epilogue like gemvT_bb.               */
+int fb200_tv_div_loss(const double* Y, int64_t n0, int64_t n1, int loss, const double* b, double* z,
+                      double* r, double* scal, void* ws, void* stream);
+int fb200_tv_grad_bb(const double* R, int64_t n0, int64_t n1, double* g, int bb, const double* x0,
+                     const double* xhat, const double* dx, double tau, double* scal, void* ws,
+                     void* stream);
+
+/* ---- small reductions used by the prologue and the generic (untagged-callable) path ---------
+ * out (device) receives: dot = <a,b>; diff_nrm2sq = |a-b|^2; asum = sum |a|                   */
+int fb200_dot(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream);
+int fb200_diff_nrm2sq(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream);
+int fb200_asum(const double* a, int64_t n, double* out, void* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTA_B200_H */

@@ -1,0 +1,248 @@
+"""TEST DOUBLE (test infrastructure, never shipped): a CPU implementation of the back-end protocol
+of ``fasta._loop`` so that the HOST logic -- the FBS control flow in ``fasta/_loop.py`` and the
+collective choreography of ``fasta._backends.ShardedDriver`` -- can be exercised without a GPU
+(``-m "not gpu"`` tests; gloo world_size-2 tests).  The product never imports this module and
+``fasta.fasta()`` cannot select it.
+
+Buffers are torch CPU tensors (so ``torch.distributed`` works on them); the arithmetic restates
+the same reference expressions the CUDA kernels implement.
+"""
+
+import numpy as np
+import torch
+
+from fasta import _cabi as S
+from fasta._loop import Scalars
+
+
+class CpuWorkspace:
+    def __init__(self):
+        self.scal = torch.zeros(S.NSCAL, dtype=torch.float64)
+
+    def fetch(self):
+        return self.scal.numpy().copy()
+
+
+def _loss(tag, z, b):
+    if tag == S.LOSS_LEAST_SQUARES:
+        r = z - b
+        return r, torch.dot(r, r)
+    if tag == S.LOSS_LOGISTIC:
+        f = torch.sum(torch.log(1 + torch.exp(z)) - (b == 1).double() * z)
+        return -b / (1 + torch.exp(b * z)), f
+    return None, torch.tensor(0.0, dtype=torch.float64)
+
+
+class CpuDenseDriver:
+    """Same interface as fasta._backends.DenseDriver, torch CPU arithmetic."""
+
+    def __init__(self, matrix):
+        self.A = torch.as_tensor(matrix, dtype=torch.float64)
+        self.M, self.N = self.A.shape
+        self.xshape, self.zshape = (self.N,), (self.M,)
+        self.launches = 0
+
+    def workspace_dims(self):
+        return self.M, self.N
+
+    def forward(self, x, loss_tag, b, z, r, ws):
+        z.copy_(self.A @ x)
+        rr, f = _loss(loss_tag, z, b)
+        if rr is not None:
+            r.copy_(rr)
+            ws.scal[S.S_F] = f
+        self.launches += 2
+
+    def adjoint(self, r, g, bb, x0, xhat, dx, tau, ws):
+        g.copy_(self.A.T @ r)
+        if bb:
+            self.bb_reduce(g, x0, xhat, dx, tau, bb >= 2, ws)
+        self.launches += 2
+
+    def bb_reduce(self, g, x0, xhat, dx, tau, adaptive, ws):
+        ws.scal[S.S_G1_SQ] = torch.dot(g, g)
+        if adaptive:
+            dg = g + (xhat - x0) / tau
+            ws.scal[S.S_DX_DG] = torch.dot(dx, dg)
+            ws.scal[S.S_DG_SQ] = torch.dot(dg, dg)
+
+    def sync_point(self, v1, v2):
+        pass
+
+
+class CpuTVDriver:
+    def __init__(self, n0, n1):
+        self.n0, self.n1 = n0, n1
+        self.xshape, self.zshape = (n0, n1, 2), (n0, n1)
+        self.launches = 0
+
+    def workspace_dims(self):
+        return 1, 1
+
+    def forward(self, x, loss_tag, b, z, r, ws):
+        Y = x.view(self.n0, self.n1, 2)
+        out = torch.zeros(self.n0, self.n1, dtype=torch.float64)
+        for d in range(2):
+            out += torch.roll(Y[..., d], -1, dims=d) - Y[..., d]
+        z.copy_(out.reshape(-1))
+        rr, f = _loss(loss_tag, z, b.reshape(-1) if b is not None else None)
+        if rr is not None:
+            r.copy_(rr)
+            ws.scal[S.S_F] = f
+
+    def adjoint(self, r, g, bb, x0, xhat, dx, tau, ws):
+        R = r.view(self.n0, self.n1)
+        G = torch.stack([torch.roll(R, 1, dims=0) - R, torch.roll(R, 1, dims=1) - R], dim=-1)
+        g.copy_(G.reshape(-1))
+        if bb:
+            CpuDenseDriver.bb_reduce(self, g, x0, xhat, dx, tau, bb >= 2, ws)
+
+    def sync_point(self, v1, v2):
+        pass
+
+
+def _prox(tag, h, p0, p1, radius=None):
+    if tag == S.PROX_SHRINK:
+        return torch.sign(h) * torch.clamp(torch.abs(h) - p0, min=0)
+    if tag == S.PROX_NONNEG:
+        return torch.clamp(h, min=0)
+    if tag == S.PROX_BOX:
+        return torch.clamp(h, min=p0, max=p1)
+    if tag == S.PROX_TV_BALL:
+        Y = h.view(-1, 2)
+        nrm = torch.clamp(torch.linalg.norm(Y, dim=1), min=1)
+        return (Y / nrm[:, None]).reshape(-1)
+    if tag == S.PROX_L1BALL:
+        x = h.numpy()
+        mag = np.abs(x)
+        if mag.sum() <= radius:
+            return h.clone()
+        desc = np.sort(mag)[::-1]
+        theta = np.max((np.cumsum(desc) - radius) / np.arange(1, len(x) + 1))
+        return torch.from_numpy(np.sign(x) * np.maximum(mag - theta, 0))
+    return h.clone()
+
+
+class CpuFusedBackend:
+    """Mirror of fasta._backends.FusedBackend on torch CPU tensors."""
+
+    def __init__(self, driver, loss_tag, b, penalty, x0, accelerate):
+        self.drv = driver
+        self.loss_tag = loss_tag
+        self.b = torch.as_tensor(np.asarray(b, dtype=np.float64)).reshape(-1)
+        self.pen = penalty
+        self.accelerate = accelerate
+        self.shape = tuple(x0.shape)
+        self.x0_in = x0
+        self.n = int(np.prod(driver.xshape))
+        self.m = int(np.prod(driver.zshape))
+        self.ws = CpuWorkspace()
+        new = lambda k: torch.zeros(k, dtype=torch.float64)
+        self.x1, self.g1 = new(self.n), new(self.n)
+        self.z, self.r = new(self.m), new(self.m)
+
+    def _finalize_f(self, raw):
+        return .5 * np.sqrt(raw) ** 2 if self.loss_tag == S.LOSS_LEAST_SQUARES else raw
+
+    def total_launches(self):
+        return 0
+
+    def load(self):
+        self.x1 = torch.from_numpy(np.array(self.x0_in, dtype=np.float64).reshape(-1))
+        self.best = self.x1.clone()
+        self.xa1 = self.x1.clone()
+
+    def lipschitz(self, v1, v2):
+        a = torch.from_numpy(np.ascontiguousarray(v1.reshape(-1)))
+        b = torch.from_numpy(np.ascontiguousarray(v2.reshape(-1)))
+        self.drv.sync_point(a, b)
+        ds = []
+        for v in (a, b):
+            d = torch.zeros(self.n, dtype=torch.float64)
+            self.drv.forward(v, self.loss_tag, self.b, self.z, self.r, self.ws)
+            self.drv.adjoint(self.r, d, 0, None, None, None, 0.0, self.ws)
+            ds.append(d)
+        return np.float64(torch.linalg.norm(ds[0] - ds[1])), np.float64(torch.linalg.norm(a - b))
+
+    def start(self):
+        z = torch.zeros(self.m, dtype=torch.float64)
+        self.drv.forward(self.x1, self.loss_tag, self.b, z, self.r, self.ws)
+        self.za1 = z.clone()
+        self.g1 = torch.zeros(self.n, dtype=torch.float64)
+        self.drv.adjoint(self.r, self.g1, 1, None, None, None, 0.0, self.ws)
+        s = self.ws.fetch()
+        return Scalars(f=self._finalize_f(s[S.S_F]), pen=self.pen.value(np.float64(self.x1.abs().sum())),
+                       g_sq=s[S.S_G1_SQ])
+
+    def advance(self):
+        self.x0, self.g0 = self.x1, self.g1
+        self.xa0, self.za0 = self.xa1, self.za1
+
+    def trial(self, tau):
+        tau = float(tau)
+        self.xhat = self.x0 - tau * self.g0
+        p0, p1 = self.pen.params(np.float64(tau))
+        x1 = _prox(self.pen.tag, self.xhat, float(p0), float(p1), getattr(self.pen, "radius", None))
+        self.dx = x1 - self.x0
+        z = torch.zeros(self.m, dtype=torch.float64)
+        self.drv.forward(x1, self.loss_tag, self.b, z, self.r, self.ws)
+        s = self.ws.fetch()
+        restart = np.float64(torch.dot(self.x0 - x1, x1 - self.xa0))
+        self.x1, self.xa1, self.za1 = x1, x1, z
+        return Scalars(f=self._finalize_f(s[S.S_F]), dx_g0=np.float64(torch.dot(self.dx, self.g0)),
+                       dx_sq=np.float64(torch.dot(self.dx, self.dx)),
+                       xmxh_sq=np.float64(torch.dot(x1 - self.xhat, x1 - self.xhat)),
+                       pen=self.pen.value(np.float64(x1.abs().sum())), restart=restart)
+
+    def extrapolate(self, c):
+        c = float(c)
+        self.x1 = self.xa1 + c * (self.xa1 - self.xa0)
+        z = self.za1 + c * (self.za1 - self.za0)
+        rr, f = _loss(self.loss_tag, z, self.b)
+        self.r = rr
+        self.ws.scal[S.S_F] = f
+        if hasattr(self.drv, "reduce_loss"):
+            self.drv.reduce_loss(self.ws)
+        s = self.ws.fetch()
+        e = self.x1 - self.xhat
+        return Scalars(f=self._finalize_f(s[S.S_F]), xmxh_sq=np.float64(torch.dot(e, e)),
+                       pen=self.pen.value(np.float64(self.x1.abs().sum())))
+
+    def gradient(self, tau, adaptive):
+        self.g1 = torch.zeros(self.n, dtype=torch.float64)
+        self.drv.adjoint(self.r, self.g1, 2 if adaptive else 1, self.x0, self.xhat, self.dx, float(tau), self.ws)
+        s = self.ws.fetch()
+        return Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
+
+    def keep_best(self):
+        self.best = self.x1.clone()
+
+    def iterate(self):
+        return self.x1.numpy().reshape(self.shape)
+
+    def solution(self):
+        return self.best.numpy().reshape(self.shape).copy()
+
+
+class HostPenalty:
+    """params()/value() of fasta.proximal penalties without touching the GPU."""
+
+    def __init__(self, kind, mu):
+        self.kind, self.mu = kind, mu
+        self.tag = {"l1": S.PROX_SHRINK, "l1ball": S.PROX_L1BALL, "nonneg": S.PROX_NONNEG,
+                    "tv_ball": S.PROX_TV_BALL, "none": S.PROX_IDENTITY}[kind]
+        self.radius = mu
+
+    def params(self, t):
+        return (t * self.mu, 0.0) if self.kind == "l1" else (0.0, 0.0)
+
+    def value(self, raw):
+        return self.mu * raw if self.kind == "l1" else 0
+
+
+def backend_for(problem, accelerate, driver=None):
+    """CPU test-double back-end for an oracle.problems.Problem."""
+    tag = S.LOSS_LEAST_SQUARES if problem.loss == "least_squares" else S.LOSS_LOGISTIC
+    if driver is None:
+        driver = CpuDenseDriver(problem.A) if problem.kind == "dense" else CpuTVDriver(*problem.x0.shape[:2])
+    return CpuFusedBackend(driver, tag, problem.b, HostPenalty(problem.penalty, problem.mu), problem.x0, accelerate)

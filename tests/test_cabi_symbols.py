@@ -1,0 +1,50 @@
+"""CPU: the C-ABI library builds, loads without a GPU, and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "fasta_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fb200_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    import __graft_entry__
+    __graft_entry__.build()
+    from fasta import _cabi
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 19
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/fasta_b200.h but not exported"
+        assert name in _cabi.SIGNATURES, f"{name} has no ctypes signature in fasta/_cabi.py"
+    assert sorted(_cabi.SIGNATURES) == names
+    loaded = _cabi.load()
+    assert loaded.fb200_abi_version() == _cabi.ABI_VERSION
+    assert loaded.fb200_workspace_bytes(40000, 100000) > 32 * 100096 * 8
+
+
+def test_no_cpu_fallback_without_gpu():
+    import numpy as np
+    import pytest
+    import torch
+    import fasta
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(fasta._cabi.Fb200Error):
+        fasta.fasta(fasta.linalg.LinearMap.identity((3,)), lambda z: 0, lambda z: z, None, None, np.zeros(3),
+                    verbose=False)
+    with pytest.raises(fasta._cabi.Fb200Error):
+        fasta.proximal.shrink(np.ones(4), 0.5)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "fasta-python_b200", "fasta")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), f"{fn} mentions the oracle"

@@ -1,0 +1,189 @@
+"""GPU: every C-ABI kernel against its numpy expression (through the public toolkits / ctypes)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _t():
+    import torch
+    return torch
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+# M, N pairs: tile multiples, ragged edges, tiny, single row/col, tall, wide
+SHAPES = [(200, 1000), (16, 256), (333, 1414), (1, 2), (5, 4098), (4099, 6), (1000, 2000), (2048, 4096),
+          (17, 258), (640, 5120)]
+
+
+@pytest.mark.parametrize("M,N", SHAPES)
+def test_dense_map_tma_path(M, N):
+    import fasta
+    rng = np.random.RandomState(M * 7 + N)
+    A = rng.randn(M, N)
+    x, r = rng.randn(N), rng.randn(M)
+    op = fasta.linalg.LinearMap.from_matrix(A)
+    assert op.uses_tma
+    assert op.Vshape == (N,) and op.Wshape == (M,)
+    z = op(x)
+    g = op.H(r)
+    assert isinstance(z, np.ndarray) and z.shape == (M,) and g.shape == (N,)
+    assert _rel(z, A @ x) < 1e-14
+    assert _rel(g, A.T @ r) < 1e-14
+    # bit-reproducible run to run (fixed-order, atomics-free reductions)
+    assert np.array_equal(z, op(x)) and np.array_equal(g, op.H(r))
+    with pytest.raises(AssertionError):
+        op(np.zeros(N + 1))
+
+
+@pytest.mark.parametrize("M,N", [(200, 1001), (33, 77), (1, 1), (513, 2049)])
+def test_dense_map_plain_path_odd_leading_dimension(M, N):
+    import fasta
+    rng = np.random.RandomState(M + N)
+    A = rng.randn(M, N)
+    x, r = rng.randn(N), rng.randn(M)
+    op = fasta.linalg.LinearMap.from_matrix(A)
+    assert not op.uses_tma            # odd lda: TMA needs 16-byte row pitch
+    assert _rel(op(x), A @ x) < 1e-14
+    assert _rel(op.H(r), A.T @ r) < 1e-14
+
+
+def test_dense_map_borrows_cuda_tensor_and_row_slices():
+    import fasta
+    torch = _t()
+    rng = np.random.RandomState(3)
+    A = rng.randn(300, 512)
+    Ad = torch.from_numpy(A).cuda()
+    op = fasta.linalg.LinearMap.from_matrix(Ad)
+    assert op.matrix.data_ptr() == Ad.data_ptr()
+    x = torch.from_numpy(rng.randn(512)).cuda()
+    z = op(x)
+    assert isinstance(z, torch.Tensor) and z.is_cuda
+    assert _rel(z.cpu().numpy(), A @ x.cpu().numpy()) < 1e-14
+    sl = fasta.linalg.LinearMap.from_matrix(Ad[100:260])          # view: rows 100..259
+    assert sl.matrix.data_ptr() == Ad[100:260].data_ptr()
+    assert _rel(sl(x).cpu().numpy(), A[100:260] @ x.cpu().numpy()) < 1e-14
+    r = rng.randn(160)
+    assert _rel(sl.H(r), A[100:260].T @ r) < 1e-14
+
+
+def test_adjoint_identity_large():
+    """<A x, r> == <x, A^T r> at a size where both kernels run many tiles per CTA."""
+    import fasta
+    torch = _t()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, N = 6000, 20000
+    A = torch.randn(M, N, dtype=torch.float64, device="cuda", generator=g)
+    x = torch.randn(N, dtype=torch.float64, device="cuda", generator=g)
+    r = torch.randn(M, dtype=torch.float64, device="cuda", generator=g)
+    op = fasta.linalg.LinearMap.from_matrix(A)
+    z, gr = op(x), op.H(r)
+    assert _rel(z.cpu().numpy(), (A @ x).cpu().numpy()) < 1e-13
+    assert _rel(gr.cpu().numpy(), (A.T @ r).cpu().numpy()) < 1e-13
+    lhs, rhs = float(torch.dot(z, r)), float(torch.dot(x, gr))
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+
+
+def test_prox_known_answers(golden_dir):
+    import fasta
+    with np.load(f"{golden_dir}/kat_prox.npz") as z:
+        for i in range(int(z["count"])):
+            x, t = z[f"x{i}"], float(z[f"t{i}"])
+            got = fasta.proximal.shrink(x, t)
+            assert np.array_equal(got, z[f"shrink{i}"])                       # bit exact, incl. -0.0
+            assert np.array_equal(np.signbit(got), np.signbit(z[f"shrink{i}"]))
+            want = z[f"l1ball{i}"]
+            got = fasta.proximal.project_L1_ball(x, t)
+            assert np.max(np.abs(got - want)) <= 4e-16 * max(1.0, np.max(np.abs(x)))
+            assert np.max(np.abs(fasta.proximal.project_Linf_ball(x, t) - z[f"tinf{i}"])) <= 4e-16 * max(1.0, np.max(np.abs(x)))
+        assert _rel(fasta.proximal.project_Lnuc_ball(z["X"], float(z["Xt"])), z["nuc"]) < 1e-12
+    assert np.array_equal(fasta.proximal.shrink(np.ones((3, 5)) * -2, 0.5), -1.5 * np.ones((3, 5)))  # any shape
+    assert np.array_equal(fasta.proximal.shrink(np.array([1.0, -1.0]), -1.0), np.array([2.0, -2.0]))  # negative t expands
+    x = np.array([0.1, -0.2, 0.05])
+    assert np.array_equal(fasta.proximal.project_L1_ball(x, 1.0), x)           # inside the ball: unchanged
+
+
+def test_l1_ball_projection_large_and_penalties():
+    import fasta
+    from oracle import fasta_oracle
+    rng = np.random.RandomState(11)
+    x = rng.randn(100003) * 3
+    for radius in (1.0, 50.0, 5000.0, 1e9):
+        got = fasta.proximal.project_L1_ball(x, radius)
+        want = fasta_oracle.project_l1_ball(x, radius)
+        assert np.max(np.abs(got - want)) < 1e-13
+        assert np.abs(got).sum() <= radius * (1 + 1e-12) or radius >= np.abs(x).sum()
+    pen = fasta.proximal.L1Norm(0.3)
+    assert abs(pen.g(x) - 0.3 * np.abs(x).sum()) < 1e-9
+    assert np.array_equal(pen.prox(x, 0.5), fasta_oracle.shrink(x, 0.5 * 0.3))
+    assert np.array_equal(fasta.proximal.NonNegative().prox(x, 1.0), np.maximum(x, 0))
+    assert np.array_equal(fasta.proximal.Box(-1.0, 0.5).prox(x, 1.0), np.clip(x, -1.0, 0.5))
+    Y = rng.randn(37, 41, 2) * 2
+    nrm = np.maximum(np.linalg.norm(Y, axis=2), 1)
+    assert np.array_equal(fasta.proximal.TVBall().prox(Y, 0.1), Y / nrm[..., None])
+
+
+def test_losses():
+    import fasta
+    rng = np.random.RandomState(5)
+    z, b = rng.randn(7777) * 3, rng.randn(7777)
+    ls = fasta.losses.LeastSquares(b)
+    assert abs(ls.f(z) - .5 * np.linalg.norm(z - b) ** 2) <= 1e-12 * ls.f(z)
+    assert np.array_equal(ls.gradf(z), z - b)
+    lab = np.sign(rng.randn(7777))
+    lg = fasta.losses.Logistic(lab)
+    want = np.sum(np.log(1 + np.exp(z)) - (lab == 1) * z)
+    assert abs(lg.f(z) - want) <= 1e-12 * abs(want)
+    assert np.max(np.abs(lg.gradf(z) - (-lab / (1 + np.exp(lab * z))))) <= 1e-15
+
+
+@pytest.mark.parametrize("n0,n1", [(64, 64), (128, 96), (33, 130), (1, 7), (5, 1), (300, 257)])
+def test_tv_stencils(n0, n1):
+    import fasta
+    from oracle import problems
+    rng = np.random.RandomState(n0 + n1)
+    X, Y = rng.randn(n0, n1), rng.randn(n0, n1, 2)
+    assert np.array_equal(fasta.tv.grad(X), problems.tv_grad(X))        # elementwise: bit exact
+    assert np.array_equal(fasta.tv.div(Y), problems.tv_div(Y))
+    lhs = np.sum(fasta.tv.div(Y) * X)
+    rhs = np.sum(Y * fasta.tv.grad(X))
+    assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), 1.0)                  # adjointness
+
+
+def test_step_kernels_through_ctypes():
+    """fbs_step / bb_reduce / accel_step scalars against numpy on ragged sizes."""
+    import fasta
+    from fasta import _cabi, _device
+    torch = _t()
+    lib = _cabi.load()
+    rng = np.random.RandomState(9)
+    for n in (1, 31, 1000, 100003):
+        x0, g0, xa = rng.randn(n), rng.randn(n), rng.randn(n)
+        tau, thr = 0.37, 0.21
+        d = {k: torch.from_numpy(v).cuda() for k, v in dict(x0=x0, g0=g0, xa=xa).items()}
+        xhat, x1, dx = (torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3))
+        ws = _device.Workspace(1, 1)
+        _cabi.check(lib.fb200_fbs_step(d["x0"].data_ptr(), d["g0"].data_ptr(), tau, _cabi.PROX_SHRINK, thr, 0.0,
+                                       d["xa"].data_ptr(), n, xhat.data_ptr(), x1.data_ptr(), dx.data_ptr(),
+                                       ws.scal.data_ptr(), ws.buf.data_ptr(), _device.stream_ptr()))
+        s = ws.fetch().copy()
+        h = x0 - tau * g0
+        y = np.sign(h) * np.maximum(np.abs(h) - thr, 0)
+        assert np.array_equal(xhat.cpu().numpy(), h) and np.array_equal(x1.cpu().numpy(), y)
+        assert np.array_equal(dx.cpu().numpy(), y - x0)
+        for slot, want in ((_cabi.S_DX_G0, (y - x0) @ g0), (_cabi.S_DX_SQ, (y - x0) @ (y - x0)),
+                           (_cabi.S_XMXH_SQ, (y - h) @ (y - h)), (_cabi.S_PEN, np.abs(y).sum()),
+                           (_cabi.S_RESTART, (x0 - y) @ (y - xa))):
+            assert abs(s[slot] - want) <= 1e-12 * max(abs(want), 1e-3), (n, slot)
+        g1 = torch.from_numpy(rng.randn(n)).cuda()
+        _cabi.check(lib.fb200_bb_reduce(g1.data_ptr(), d["x0"].data_ptr(), xhat.data_ptr(), dx.data_ptr(), tau, n, 1,
+                                        ws.scal.data_ptr(), ws.buf.data_ptr(), _device.stream_ptr()))
+        s = ws.fetch().copy()
+        g1n = g1.cpu().numpy()
+        dg = g1n + (h - x0) / tau
+        for slot, want in ((_cabi.S_DX_DG, (y - x0) @ dg), (_cabi.S_DG_SQ, dg @ dg), (_cabi.S_G1_SQ, g1n @ g1n)):
+            assert abs(s[slot] - want) <= 1e-12 * max(abs(want), 1e-3), (n, slot)

@@ -1,0 +1,136 @@
+"""GPU: trajectory parity of the CUDA path (public fasta.fasta API -> C ABI) with the reference.
+
+The bar (BASELINE.json north_star): identical iteration and backtrack counts, final iterate within
+1e-9 relative, objective history within 1e-10 relative -- against the committed live-reference
+golden trajectories AND against the numpy oracle run on the same seeded inputs.
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_trajectory, golden_cases, load_golden
+from oracle import fasta_oracle, problems
+
+pytestmark = pytest.mark.gpu
+
+
+def tagged(p, sharded=False):
+    import fasta
+    if p.kind == "dense":
+        A = fasta.linalg.LinearMap.from_matrix(p.A)
+    else:
+        A = fasta.tv.divergence_map(p.x0.shape[:2])
+    loss = {"least_squares": fasta.losses.LeastSquares, "logistic": fasta.losses.Logistic}[p.loss](p.b)
+    pen = {"l1": lambda: fasta.proximal.L1Norm(p.mu), "l1ball": lambda: fasta.proximal.L1Ball(p.mu),
+           "nonneg": fasta.proximal.NonNegative, "tv_ball": fasta.proximal.TVBall}[p.penalty]()
+    return A, loss, pen
+
+
+@pytest.mark.parametrize("case,mode", golden_cases())
+def test_fused_path_matches_golden(case, mode):
+    import fasta
+    gold = load_golden(case, mode)
+    p = problems.build(case, int(gold["seed"]))
+    A, loss, pen = tagged(p)
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert res.backend == "FusedBackend" and res.kernel_launches > 0
+    assert isinstance(res.solution, np.ndarray)
+    assert_trajectory(res, gold, label=f"{case}/{mode}")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("mode", list(problems.MODES))
+def test_fused_path_matches_oracle_other_seeds(seed, mode):
+    """Fresh seeded inputs (not in the fixtures): CUDA path vs the numpy oracle run side by side."""
+    import fasta
+    opts = dict(problems.HARNESS_OPTS, **problems.MODES[mode])
+    for case in ("lasso_200x1000_k50", "logistic_1000x2000", "l1ball_200x1000"):
+        p = problems.build(case, seed)
+        state = np.random.get_state()
+        ref = fasta_oracle.solve_problem(p, **opts)
+        np.random.set_state(state)          # the CUDA run must see the same tau0 draws
+        A, loss, pen = tagged(p)
+        res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **opts)
+        n = ref.iteration_count
+        gold = dict(iteration_count=n, backtracks=ref.backtracks, solution=ref.solution,
+                    objectives=ref.objectives[:n + 1], residuals=ref.residuals[:n],
+                    stepsizes=ref.stepsizes[:n], norm_residuals=ref.norm_residuals[:n])
+        assert_trajectory(res, gold, label=f"{case}/{mode}/seed{seed}")
+
+
+def test_legacy_seven_argument_form_with_arrays():
+    """fasta(A, At, f, gradf, g, proxg, x0) with ndarrays (sparse_least_squares.py:46,76)."""
+    import fasta
+    gold = load_golden("lasso_200x1000_k10", "adaptive")
+    p = problems.build("lasso_200x1000_k10", 0)
+    loss, pen = fasta.losses.LeastSquares(p.b), fasta.proximal.L1Norm(p.mu)
+    res = fasta.fasta(p.A, p.A.T, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert res.backend == "FusedBackend"
+    assert_trajectory(res, gold, label="legacy/arrays")
+
+
+def test_legacy_form_with_tv_callables():
+    """fasta(div, grad, ...) as tv_denoising.py:99 calls it."""
+    import fasta
+    gold = load_golden("tv_64", "accelerated")
+    p = problems.build("tv_64", 0)
+    loss, pen = fasta.losses.LeastSquares(p.b), fasta.proximal.TVBall()
+    res = fasta.fasta(fasta.tv.div, fasta.tv.grad, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert res.backend == "FusedBackend"
+    assert_trajectory(res, gold, label="legacy/tv")
+
+
+@pytest.mark.parametrize("mode", list(problems.MODES))
+def test_generic_path_with_user_callables(mode):
+    """Untagged torch lambdas (the reference's own formulas) run through GenericBackend on the GPU."""
+    import fasta
+    import torch
+    gold = load_golden("lasso_200x1000_k50", mode)
+    p = problems.build("lasso_200x1000_k50", 0)
+    b = torch.from_numpy(p.b).cuda()
+    mu = p.mu
+    f = lambda z: .5 * torch.linalg.norm((z - b).ravel()) ** 2
+    gradf = lambda z: z - b
+    g = lambda x: mu * torch.linalg.norm(x.ravel(), 1)
+    proxg = lambda x, t: fasta.proximal.shrink(x, t * mu)
+    A = fasta.linalg.LinearMap.from_matrix(p.A)
+    res = fasta.fasta(A, f, gradf, g, proxg, torch.from_numpy(p.x0).cuda(), **gold["opts"])
+    assert res.backend == "GenericBackend"
+    assert isinstance(res.solution, torch.Tensor) and res.solution.is_cuda
+    res.solution = res.solution.cpu().numpy()
+    assert_trajectory(res, gold, label=f"generic/{mode}")
+
+
+def test_gradient_descent_when_g_is_none_and_hooks():
+    import fasta
+    p = problems.build("lasso_200x1000_k10", 0)
+    f, gradf, _, _ = problems.numpy_callables(p)
+    op, adj, _, _ = problems.numpy_operator(p)
+    opts = dict(verbose=False, max_iters=25, evaluate_objective=True, record_iterates=True)
+    np.random.seed(3)
+    ref = fasta_oracle.solve(op, adj, f, gradf, None, None, p.x0, func=lambda x: np.abs(x).max(), **opts)
+    np.random.seed(3)
+    loss = fasta.losses.LeastSquares(p.b)
+    res = fasta.fasta(fasta.linalg.LinearMap.from_matrix(p.A), loss.f, loss.gradf, None, None, p.x0,
+                      func=lambda x: np.abs(x).max(), **opts)
+    assert res.backend == "FusedBackend"
+    assert res.iteration_count == ref.iteration_count and res.backtracks == ref.backtracks
+    n = ref.iteration_count
+    np.testing.assert_allclose(res.objectives[:n + 1], ref.objectives[:n + 1], rtol=1e-10)
+    np.testing.assert_allclose(res.iterates[:n + 1], ref.iterates[:n + 1], rtol=0, atol=1e-9 * np.abs(ref.iterates).max())
+    np.testing.assert_allclose(res.function_hist[:n + 1], ref.function_hist[:n + 1], rtol=1e-9)
+    assert np.array_equal(res.iterates[0], p.x0)
+
+
+def test_x0_not_mutated_and_torch_in_torch_out():
+    import fasta
+    import torch
+    p = problems.build("nnls_200x1000", 0)
+    x0 = torch.from_numpy(p.x0.copy()).cuda() + 0.25
+    keep = x0.clone()
+    A = fasta.linalg.LinearMap.from_matrix(torch.from_numpy(p.A).cuda())
+    loss = fasta.losses.LeastSquares(torch.from_numpy(p.b).cuda())
+    pen = fasta.proximal.NonNegative()
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, x0, verbose=False, max_iters=5)
+    assert torch.equal(x0, keep)
+    assert isinstance(res.solution, torch.Tensor) and res.solution.is_cuda and res.solution.shape == x0.shape
+    assert res.solution.data_ptr() != x0.data_ptr()
