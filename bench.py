@@ -93,7 +93,7 @@ def clocks_sampler():
     """nvidia-smi clocks line of the profiling recipe, sampled every 200 ms in the background."""
     try:
         f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
@@ -103,7 +103,16 @@ def clocks_sampler():
         return None, None
 
 
-def clocks_summary(proc, f, device_index):
+def _stamp(text):
+    from datetime import datetime
+    try:
+        return datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+    except ValueError:
+        return None
+
+
+def clocks_summary(proc, f, device_index, t_begin, t_end):
+    """Median SM clock / throttle reasons over the samples taken INSIDE [t_begin, t_end]."""
     out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
     if proc is None:
         return out
@@ -114,20 +123,22 @@ def clocks_summary(proc, f, device_index):
         proc.kill()
     f.flush()
     f.seek(0)
-    sm, smmax, reasons = [], [], set()
+    sm, smmax, power, reasons = [], [], [], set()
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     for line in f.read().splitlines():
         parts = [p.strip() for p in line.split(",")]
-        if len(parts) < 9:
+        if len(parts) < 10:
             continue
+        ts = _stamp(parts[0])
         try:
-            if int(parts[0]) != device_index:
+            if int(parts[1]) != device_index or ts is None or ts < t_begin - 0.2 or ts > t_end + 0.2:
                 continue
-            sm.append(float(parts[1]))
-            smmax.append(float(parts[2]))
+            sm.append(float(parts[2]))
+            smmax.append(float(parts[3]))
+            power.append(float(parts[4]))
         except ValueError:
             continue
-        for name, val in zip(names, parts[5:9]):
+        for name, val in zip(names, parts[6:10]):
             if val.lower().startswith("active"):
                 reasons.add(name)
     f.close()
@@ -140,6 +151,7 @@ def clocks_summary(proc, f, device_index):
         out["sm_mhz"] = float(np.median(sm))
         out["sm_max_mhz"] = float(max(smmax))
         out["samples"] = len(sm)
+        out["power_w_max"] = float(max(power))
     out["reasons"] = sorted(reasons)
     return out
 
@@ -298,14 +310,16 @@ def main():
         return outs, float(ms.item()), wall
 
     # ---- warm-up, then the resident-input measurement ---------------------------------------------
+    sampler, sfile = clocks_sampler() if rank == 0 else (None, None)
     for _ in range(max(args.warmup, 3)):
         res = solve(x0)
-    sampler, sfile = clocks_sampler() if rank == 0 else (None, None)
     record["on"] = True
+    t_begin = time.time()
     outs, ms_total, wall = timed_region(lambda: solve(x0), args.steps)
+    t_end = time.time()
     record["on"] = False
     torch.cuda.synchronize()
-    clocks = clocks_summary(sampler, sfile, local) if rank == 0 else None
+    clocks = clocks_summary(sampler, sfile, local, t_begin, t_end) if rank == 0 else None
 
     iters = sum(r.iteration_count for r in outs)
     backtracks = sum(r.backtracks for r in outs)
