@@ -26,6 +26,7 @@ UNITS = [
     ("vector_kernels.cu", ["-fmad=false"]),
     ("tv_stencil.cu", ["-fmad=false"]),
     ("dense_stream.cu", []),
+    ("dense_sweep.cu", []),
 ]
 
 

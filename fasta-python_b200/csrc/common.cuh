@@ -13,12 +13,14 @@ namespace fb200 {
 // ------------------------------------------------------------------------------------------------
 // workspace layout (bytes from the start of `ws`; the caller zero-initialises it once)
 //   [0, 256)                       ticket counters for the "last block finalises" reductions
-//   [256, 256 + RED_BYTES)         per-block reduction partials  [MAX_RED_BLOCKS][MAX_RED_K]
+//   [256, 2048)                    per-cluster loss partials of the single-pass sweep (FPART_MAX doubles)
+//   [2048, 2048 + RED_BYTES)       per-block reduction partials  [MAX_RED_BLOCKS][MAX_RED_K]
 //   [DENSE_OFF, ...)               split partials of the dense maps: zp[S][ldz] then gp[S][ldg]
 // ------------------------------------------------------------------------------------------------
 constexpr int    MAX_RED_BLOCKS = 8192;
 constexpr int    MAX_RED_K      = 8;
-constexpr size_t CTR_BYTES      = 256;
+constexpr size_t CTR_BYTES      = 2048;
+constexpr int    FPART_MAX      = 160;
 constexpr size_t RED_BYTES      = size_t(MAX_RED_BLOCKS) * MAX_RED_K * sizeof(double);
 constexpr size_t DENSE_OFF      = CTR_BYTES + RED_BYTES;
 constexpr int    MAX_SPLIT      = 32;
@@ -29,10 +31,12 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 struct Workspace {
     unsigned* counter;
+    double*   fpart;
     double*   red;
     double*   dense;
     __host__ explicit Workspace(void* ws)
         : counter(reinterpret_cast<unsigned*>(ws)),
+          fpart(reinterpret_cast<double*>(static_cast<char*>(ws) + 256)),
           red(reinterpret_cast<double*>(static_cast<char*>(ws) + CTR_BYTES)),
           dense(reinterpret_cast<double*>(static_cast<char*>(ws) + DENSE_OFF)) {}
 };

@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace fb200 {
 
@@ -39,52 +40,6 @@ constexpr int V_TILE_BYTES = TC * 8;                 // 2048 reserved per stage 
 constexpr int STAGE_BYTES  = A_TILE_BYTES + V_TILE_BYTES;
 constexpr int RED_SMEM     = NCONS * TC * 8;         // 16384, A^T r cross-warp reduction
 constexpr int SMEM_BYTES   = NSTAGE * STAGE_BYTES + RED_SMEM + 2 * NSTAGE * 8 + 128;
-
-// ---- PTX wrappers --------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const CUtensorMap* map, int c0, uint64_t* bar, uint64_t pol) {
-    asm volatile(
-        "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%2}], [%3], %4;" ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(smem_u32(bar)), "l"(pol)
-        : "memory");
-}
 
 struct StreamPlan {
     int nrb;      // row blocks   = ceil(M / TR)
@@ -115,7 +70,7 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], NCONS);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
 
@@ -346,7 +301,11 @@ static int ensure_smem_attr() {
 }
 
 size_t dense_partial_elems(int64_t M, int64_t N) {
-    return size_t(MAX_SPLIT) * size_t(round_up(M, TR) > round_up(N, TC) ? round_up(M, TR) : round_up(N, TC));
+    // two-pass split partials: MAX_SPLIT x max(ldz, ldg); single-pass sweep: <= 160 cluster partials of
+    // ldg doubles with (#clusters x ldg) bounded by ~148 x 6656 (dense_sweep.cu)
+    const size_t two_pass = size_t(MAX_SPLIT) * size_t(round_up(M, TR) > round_up(N, TC) ? round_up(M, TR) : round_up(N, TC));
+    const size_t sweep    = std::min<size_t>(size_t(160) * size_t(round_up(N, TC)), size_t(1200000));
+    return two_pass > sweep ? two_pass : sweep;
 }
 
 // z-partials: returns nsplit / ld through the plan

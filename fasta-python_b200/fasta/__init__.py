@@ -160,5 +160,6 @@ def fasta(*args, **kwargs) -> Convergence:
     be.load()
     result = _run(be, tuple(x0.shape), **opts)
     result.backend = type(be).__name__
+    result.single_pass = bool(getattr(be, "use_sweep", False))
     result.kernel_launches = be.total_launches()
     return result

@@ -11,6 +11,8 @@ Operator drivers:  ``DenseDriver`` (TMA streaming GEMV / GEMV-T), ``TVDriver`` (
 There is no CPU implementation anywhere in this module.
 """
 
+import os
+
 import numpy as np
 
 from . import _cabi, _device
@@ -32,9 +34,21 @@ class DenseDriver:
         self.xshape, self.zshape = (self.N,), (self.M,)
         self.lib = _cabi.load()
         self.launches = 0
+        # single-pass sweep (csrc/dense_sweep.cu): cluster size it would use, 0 = not eligible
+        self.sweep_cluster = int(self.lib.fb200_sweep_supported(self.A.data_ptr(), self.lda, self.M, self.N))
+        self.sweep_ok = self.sweep_cluster > 0 and os.environ.get("FASTA_B200_SWEEP", "1") != "0"
 
     def workspace_dims(self):
         return self.M, self.N
+
+    def sweep(self, x, loss_tag, b, z, r, g, bb, x0, xhat, dx, tau, ws):
+        """z = A x, r = gradf(z), S_F and g = A^T r (+BB epilogue) in ONE pass over A."""
+        _cabi.check(self.lib.fb200_dense_sweep(self.A.data_ptr(), self.lda, self.M, self.N, x.data_ptr(), loss_tag,
+                                               _device.ptr(b), z.data_ptr(), _device.ptr(r), _device.ptr(g), bb,
+                                               _device.ptr(x0), _device.ptr(xhat), _device.ptr(dx), float(tau),
+                                               ws.scal.data_ptr(), ws.buf.data_ptr(), ws.nbytes,
+                                               _device.stream_ptr()), "fb200_dense_sweep")
+        self.launches += 3
 
     def forward(self, x, loss_tag, b, z, r, ws):
         _cabi.check(self.lib.fb200_gemv_loss(self.A.data_ptr(), self.lda, self.M, self.N, x.data_ptr(), loss_tag,
@@ -108,8 +122,21 @@ class ShardedDriver:
     def launches(self):
         return self.local.launches
 
+    @property
+    def sweep_ok(self):
+        return getattr(self.local, "sweep_ok", False)
+
     def workspace_dims(self):
         return self.local.workspace_dims()
+
+    def sweep(self, x, loss_tag, b, z, r, g, bb, x0, xhat, dx, tau, ws):
+        self.local.sweep(x, loss_tag, b, z, r, g, 0, None, None, None, 0.0, ws)
+        self.dist.all_reduce(g, group=self.group)
+        self.collectives += 1
+        if loss_tag != S.LOSS_NONE:
+            self.reduce_loss(ws)
+        if bb:
+            self.local.bb_reduce(g, x0, xhat, dx, tau, bb >= 2, ws)
 
     def _root(self):
         return self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
@@ -168,6 +195,11 @@ class FusedBackend:
         self.gc = self.gp = 0      # G[gc] current gradient, G[gp] previous
         self.ac = self.ap = 0      # XA/ZA[ac] current prox point, [ap] previous
         self.launches = 0          # kernels launched by this backend (vector kernels; + driver.launches)
+        # Single-pass mode: every trial also produces g = A^T gradf(A x1) speculatively in the same
+        # pass over A (the line search accepts the first trial in the vast majority of iterations;
+        # a rejected trial costs exactly what the two-pass path would have paid for it).
+        self.use_sweep = (not self.accelerate) and bool(getattr(driver, "sweep_ok", False))
+        self._spec = None
 
     # -- helpers --------------------------------------------------------------------------------
     def _st(self):
@@ -193,8 +225,11 @@ class FusedBackend:
         self.drv.sync_point(a, b)
         d1, d2 = self.G[0], self.G[1]
         for v, d in ((a, d1), (b, d2)):
-            self.drv.forward(v, self.loss.tag, self.loss.b, self.Z, self.R, self.ws)
-            self.drv.adjoint(self.R, d, 0, None, None, None, 0.0, self.ws)
+            if self.use_sweep:
+                self.drv.sweep(v, self.loss.tag, self.loss.b, self.Z, self.R, d, 0, None, None, None, 0.0, self.ws)
+            else:
+                self.drv.forward(v, self.loss.tag, self.loss.b, self.Z, self.R, self.ws)
+                self.drv.adjoint(self.R, d, 0, None, None, None, 0.0, self.ws)
         sc = self.ws.scal
         _cabi.check(self.lib.fb200_diff_nrm2sq(d1.data_ptr(), d2.data_ptr(), self.n, sc[S.S_AUX0:].data_ptr(),
                                                self.ws.buf.data_ptr(), self._st()), "fb200_diff_nrm2sq")
@@ -213,8 +248,12 @@ class FusedBackend:
 
     def start(self):
         z = self.ZA[self.ac] if self.accelerate else self.Z
-        self.drv.forward(self.X[self.ic], self.loss.tag, self.loss.b, z, self.R, self.ws)
-        self.drv.adjoint(self.R, self.G[self.gc], 1, None, None, None, 0.0, self.ws)
+        if self.use_sweep:
+            self.drv.sweep(self.X[self.ic], self.loss.tag, self.loss.b, z, self.R, self.G[self.gc], 1, None, None, None,
+                           0.0, self.ws)
+        else:
+            self.drv.forward(self.X[self.ic], self.loss.tag, self.loss.b, z, self.R, self.ws)
+            self.drv.adjoint(self.R, self.G[self.gc], 1, None, None, None, 0.0, self.ws)
         self._penalty_of(self.X[self.ic])
         s = self.ws.fetch()
         return Scalars(f=self.loss.finalize(s[S.S_F]), pen=self.pen.value(s[S.S_PEN]), g_sq=s[S.S_G1_SQ])
@@ -244,8 +283,14 @@ class FusedBackend:
                                             self.DX.data_ptr(), self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
                     "fb200_fbs_step")
         self.launches += 1
-        self.drv.forward(x1, self.loss.tag, self.loss.b, z1, self.R, self.ws)
-        s = self.ws.fetch()
+        if self.use_sweep:
+            self.drv.sweep(x1, self.loss.tag, self.loss.b, z1, self.R, self.G[self.gc], 2, x0, self.XH, self.DX, tau,
+                           self.ws)
+            s = self.ws.fetch()
+            self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
+        else:
+            self.drv.forward(x1, self.loss.tag, self.loss.b, z1, self.R, self.ws)
+            s = self.ws.fetch()
         return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
                        xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART])
 
@@ -263,6 +308,9 @@ class FusedBackend:
         return Scalars(f=self.loss.finalize(s[S.S_F]), xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]))
 
     def gradient(self, tau, adaptive):
+        if self.use_sweep and self._spec is not None:
+            spec, self._spec = self._spec, None      # produced by the accepted trial's sweep: no device work
+            return spec
         self.drv.adjoint(self.R, self.G[self.gc], 2 if adaptive else 1, self.X[self.ip], self.XH, self.DX, tau, self.ws)
         s = self.ws.fetch()
         return Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])

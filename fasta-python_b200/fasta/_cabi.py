@@ -41,6 +41,8 @@ SIGNATURES = {
     "fb200_bb_reduce": (_int, [_p, _p, _p, _p, _dbl, _i64, _int, _p, _p, _p]),
     "fb200_gemv_loss": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _p, _sz, _p]),
     "fb200_gemvT_bb": (_int, [_p, _i64, _i64, _i64, _p, _p, _int, _p, _p, _p, _dbl, _p, _p, _sz, _p]),
+    "fb200_sweep_supported": (_int, [_p, _i64, _i64, _i64]),
+    "fb200_dense_sweep": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _int, _p, _p, _p, _dbl, _p, _p, _sz, _p]),
     "fb200_tv_div_loss": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_tv_grad_bb": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),
     "fb200_dot": (_int, [_p, _p, _i64, _p, _p, _p]),

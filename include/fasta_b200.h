@@ -127,6 +127,19 @@ int fb200_gemvT_bb(const double* A, int64_t lda, int64_t M, int64_t N, const dou
                    int bb, const double* x0, const double* xhat, const double* dx, double tau,
                    double* scal, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- K4+K5+K7+K8 in ONE pass over A (single-pass sweep; csrc/dense_sweep.cu) ---------------------
+ * z = A x, r = gradf(z), scal[S_F], and g = A^T r with the BB epilogue (as gemv_loss followed by
+ * gemvT_bb, reference __init__.py:187-188 and :248-260) while streaming A from HBM once: a row of A
+ * stays resident in the distributed shared memory of a thread-block cluster between the two uses.
+ * g == NULL leaves only the per-cluster partials (multi-GPU callers all-reduce first).
+ * fb200_sweep_supported returns the cluster size that will be used, or 0 if the matrix is not
+ * eligible (then use the two-pass entry points).                                               */
+int fb200_sweep_supported(const double* A, int64_t lda, int64_t M, int64_t N);
+int fb200_dense_sweep(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss,
+                      const double* b, double* z, double* r, double* g, int bb, const double* x0,
+                      const double* xhat, const double* dx, double tau, double* scal, void* ws,
+                      size_t ws_bytes, void* stream);
+
 /* ---- K11/K12: total-variation stencils (periodic)               tv_denoising.py:26-63
  * Y is n0 x n1 x 2 (last axis interleaved), Z is n0 x n1.
  * div:  Z = sum_d roll(Y[...,d],-1,d) - Y[...,d], fused with the loss epilogue like gemv_loss.

@@ -187,3 +187,56 @@ def test_step_kernels_through_ctypes():
         dg = g1n + (h - x0) / tau
         for slot, want in ((_cabi.S_DX_DG, (y - x0) @ dg), (_cabi.S_DG_SQ, dg @ dg), (_cabi.S_G1_SQ, g1n @ g1n)):
             assert abs(s[slot] - want) <= 1e-12 * max(abs(want), 1e-3), (n, slot)
+
+
+SWEEP_SHAPES = [(200, 1000), (37, 6656), (333, 1414), (1000, 20000), (64, 26624), (500, 53248), (257, 100000),
+                (3, 2), (1, 106496), (40, 13314)]
+
+
+@pytest.mark.parametrize("loss", ["least_squares", "logistic", "none"])
+@pytest.mark.parametrize("M,N", SWEEP_SHAPES)
+def test_single_pass_sweep(M, N, loss):
+    """fb200_dense_sweep: z, r, f and g = A^T r from ONE pass over A, for every cluster size."""
+    import fasta
+    from fasta import _backends, _cabi, _device
+    torch = _t()
+    rng = np.random.RandomState(M + N)
+    A = rng.randn(M, N) / np.sqrt(N)
+    x = rng.randn(N)
+    b = np.sign(rng.randn(M)) if loss == "logistic" else rng.randn(M)
+    tag = {"least_squares": _cabi.LOSS_LEAST_SQUARES, "logistic": _cabi.LOSS_LOGISTIC, "none": _cabi.LOSS_NONE}[loss]
+    Ad, xd, bd = (torch.from_numpy(v).cuda() for v in (A, x, b))
+    drv = _backends.DenseDriver(Ad)
+    assert drv.sweep_cluster in (1, 2, 4, 8, 16)
+    ws = _device.Workspace(M, N)
+    z, r = torch.zeros(M, dtype=torch.float64, device="cuda"), torch.zeros(M, dtype=torch.float64, device="cuda")
+    g = torch.zeros(N, dtype=torch.float64, device="cuda")
+    drv.sweep(xd, tag, bd, z, r, g, 1, None, None, None, 0.0, ws)
+    s = ws.fetch().copy()
+    zr = A @ x
+    if loss == "least_squares":
+        rr, fr = zr - b, np.sum((zr - b) ** 2)
+    elif loss == "logistic":
+        rr, fr = -b / (1 + np.exp(b * zr)), np.sum(np.log(1 + np.exp(zr)) - (b == 1) * zr)
+    else:
+        rr, fr = zr, None
+    gr = A.T @ rr
+    assert _rel(z.cpu().numpy(), zr) < 1e-14
+    if loss != "none":
+        assert _rel(r.cpu().numpy(), rr) < 1e-13
+        assert abs(s[_cabi.S_F] - fr) <= 1e-13 * abs(fr)
+    assert _rel(g.cpu().numpy(), gr) < 1e-13
+    assert abs(s[_cabi.S_G1_SQ] - gr @ gr) <= 1e-12 * (gr @ gr)
+    # bit-reproducible
+    z2, g2 = torch.zeros_like(z), torch.zeros_like(g)
+    drv.sweep(xd, tag, bd, z2, r, g2, 1, None, None, None, 0.0, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(z, z2) and torch.equal(g, g2)
+
+
+def test_sweep_not_eligible_for_odd_shapes():
+    import fasta
+    from fasta import _backends
+    torch = _t()
+    assert _backends.DenseDriver(torch.zeros(10, 1001, dtype=torch.float64, device="cuda")).sweep_cluster == 0
+    assert _backends.DenseDriver(torch.zeros(4, 106498, dtype=torch.float64, device="cuda")).sweep_cluster == 0

@@ -37,6 +37,29 @@ def test_fused_path_matches_golden(case, mode):
     assert_trajectory(res, gold, label=f"{case}/{mode}")
 
 
+@pytest.mark.parametrize("case,mode", golden_cases(prefixes=("lasso_200x1000_k50", "logistic", "lasso_333", "l1ball")))
+def test_two_pass_path_matches_golden(case, mode, monkeypatch):
+    """Same parity bar with the single-pass sweep disabled (separate A x and A^T r kernels)."""
+    import fasta
+    monkeypatch.setenv("FASTA_B200_SWEEP", "0")
+    gold = load_golden(case, mode)
+    p = problems.build(case, int(gold["seed"]))
+    A, loss, pen = tagged(p)
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert res.backend == "FusedBackend" and not res.single_pass
+    assert_trajectory(res, gold, label=f"two-pass/{case}/{mode}")
+
+
+def test_single_pass_is_default_for_dense_non_accelerated():
+    import fasta
+    p = problems.build("lasso_200x1000_k10", 0)
+    A, loss, pen = tagged(p)
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3)
+    assert res.single_pass
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3, accelerate=True)
+    assert not res.single_pass
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3])
 @pytest.mark.parametrize("mode", list(problems.MODES))
 def test_fused_path_matches_oracle_other_seeds(seed, mode):

@@ -43,6 +43,12 @@ def main():
         rec = dict(M=M, N=N, gemv_ms=t_min, gemv_avg_ms=t_avg, gemv_GBs=nbytes / t_min / 1e6)
         t_min, t_avg = time_op(lambda: drv.adjoint(r, g, 1, None, None, None, 0.0, ws))
         rec.update(gemvT_ms=t_min, gemvT_avg_ms=t_avg, gemvT_GBs=nbytes / t_min / 1e6)
+        if drv.sweep_ok:
+            t_min, t_avg = time_op(lambda: drv.sweep(x, _cabi.LOSS_LEAST_SQUARES, b, z, r, g, 1, None, None, None, 0.0, ws))
+            rec.update(sweep_ms=t_min, sweep_avg_ms=t_avg, sweep_dram_GBs=nbytes / t_min / 1e6,
+                       sweep_algorithmic_GBs=2 * nbytes / t_min / 1e6, sweep_cluster=drv.sweep_cluster)
+            g2 = torch.mv(A.T, torch.mv(A, x) - b)
+            rec.update(sweep_g_relerr=float((g - g2).norm() / g2.norm()))
         t_min, _ = time_op(lambda: torch.mv(A, x))
         rec.update(torch_mv_ms=t_min, torch_mv_GBs=nbytes / t_min / 1e6)
         t_min, _ = time_op(lambda: torch.mv(A.T, b))
