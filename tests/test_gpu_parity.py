@@ -138,7 +138,9 @@ def test_gradient_descent_when_g_is_none_and_hooks():
     assert res.backend == "FusedBackend"
     assert res.iteration_count == ref.iteration_count and res.backtracks == ref.backtracks
     n = ref.iteration_count
-    np.testing.assert_allclose(res.objectives[:n + 1], ref.objectives[:n + 1], rtol=1e-10)
+    # the unregularised objective decays towards 0: compare on the scale of the initial objective
+    scale = np.maximum(np.abs(ref.objectives[:n + 1]), 1e-3 * abs(ref.objectives[0]))
+    assert np.max(np.abs(res.objectives[:n + 1] - ref.objectives[:n + 1]) / scale) <= 1e-10
     np.testing.assert_allclose(res.iterates[:n + 1], ref.iterates[:n + 1], rtol=0, atol=1e-9 * np.abs(ref.iterates).max())
     np.testing.assert_allclose(res.function_hist[:n + 1], ref.function_hist[:n + 1], rtol=1e-9)
     assert np.array_equal(res.iterates[0], p.x0)
