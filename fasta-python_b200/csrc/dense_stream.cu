@@ -19,6 +19,7 @@
 // A matrix whose base or leading dimension is not 16-byte aligned cannot be described by a TMA
 // tensor map; it takes the plain-load kernels at the bottom (same partial layout).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -270,7 +271,8 @@ static StreamPlan make_plan(int mode, int64_t M, int64_t N) {
     p.nct = int((N + TC - 1) / TC);
     const int outer = mode == 0 ? p.nrb : p.nct;
     const int inner = mode == 0 ? p.nct : p.nrb;
-    const int G     = sm_count();
+    int G = sm_count();
+    if (const char* e = getenv("FB200_STREAM_GRID")) { int v = atoi(e); if (v > 0 && v < G) G = v; }   // experiments only
     int best_s = 1;
     double best_eff = -1.0;
     for (int s = 1; s <= MAX_SPLIT; ++s) {

@@ -27,6 +27,7 @@
 // is bounded by its own stage ring, which its B-group frees only after receiving everybody's
 // partials), so NSLOT = 16 >= 2*NST receive slots never alias.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -82,7 +83,8 @@ dense_sweep_kernel(const double* __restrict__ A, int64_t lda, int M, int N, int 
     const uint32_t slab_bytes = uint32_t(ncols) * 8u;
 
     // zero the stage ring once: the tail beyond `ncols` is never written by the bulk copies
-    for (int i = tid; i < nstage * STAGE_BYTES / 16; i += SW_THREADS)
+    // ... and the receive table: entries of ranks >= csize are never written and must add as zeros
+    for (int i = tid; i < (nstage * STAGE_BYTES + SW_NSLOT * SW_MAXCS * 8) / 16; i += SW_THREADS)
         reinterpret_cast<double2*>(smem)[i] = make_double2(0.0, 0.0);
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) {
@@ -147,8 +149,9 @@ dense_sweep_kernel(const double* __restrict__ A, int64_t lda, int M, int N, int 
             if (lane == 0) redA[par * 8 + warp] = p;
             asm volatile("bar.sync 1, %0;" ::"n"(SW_GROUP) : "memory");
             if (warp == 0) {
-                double v = (lane < SW_GROUP / 32) ? redA[par * 8 + lane] : 0.0;
-                v = warp_sum(v);                                   // fixed butterfly order
+                double v = redA[par * 8 + (lane & 7)];
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // the 8 warp partials, fixed order
                 if (lane < int(csize)) {
                     const int slot = (row - row_lo) & (SW_NSLOT - 1);
                     st_async_f64(peer_recv + uint32_t(slot) * SW_MAXCS * 8u, v, peer_bar + uint32_t(slot) * 8u);
@@ -174,9 +177,18 @@ dense_sweep_kernel(const double* __restrict__ A, int64_t lda, int M, int N, int 
             if (t == 0) mbar_expect_tx(&rbar[slot], csize * 8u);
             const double bi = bnext;
             if (row + 1 < row_hi && b) bnext = __ldg(b + row + 1);
-            mbar_wait_cluster(&rbar[slot], rpar);
-            double zi = recv[slot * SW_MAXCS];
-            for (uint32_t q = 1; q < csize; ++q) zi += recv[slot * SW_MAXCS + q];      // rank order: same bits on every CTA
+            // st.async data is visible to whoever observes the phase completion of the barrier it signals
+            // (a cluster-scope acquire here would make ptxas emit an L1 invalidate, CCTL.IVALL, per row)
+            mbar_wait(&rbar[slot], rpar);
+            const double2* rv = reinterpret_cast<const double2*>(recv + slot * SW_MAXCS);
+            double zi;      // fixed binary tree over ranks: same bits on every CTA (missing ranks hold zeros)
+            {
+                const double2 e0 = rv[0], e1 = rv[1], e2 = rv[2], e3 = rv[3];
+                const double s0 = (e0.x + e0.y) + (e1.x + e1.y), s1 = (e2.x + e2.y) + (e3.x + e3.y);
+                const double2 e4 = rv[4], e5 = rv[5], e6 = rv[6], e7 = rv[7];
+                const double s2 = (e4.x + e4.y) + (e5.x + e5.y), s3 = (e6.x + e6.y) + (e7.x + e7.y);
+                zi = (s0 + s1) + (s2 + s3);
+            }
             double ri, fi;
             loss_strict<LOSS>(zi, bi, ri, fi);
             if (slab_bytes > 0) {
@@ -313,6 +325,14 @@ int sweep_max_clusters() { return 160; }
 
 using namespace fb200;
 
+// plan[0..4] = cluster size, clusters co-resident, stages, columns per CTA, double2 per thread
+extern "C" int fb200_sweep_plan(int64_t M, int64_t N, int* plan) {
+    SweepPlan p = make_sweep_plan(FB200_LOSS_LEAST_SQUARES, M, N);
+    if (!p.ok) return 1;
+    plan[0] = p.cs; plan[1] = p.ncl; plan[2] = p.nstage; plan[3] = p.nc; plan[4] = p.cpt;
+    return 0;
+}
+
 extern "C" int fb200_sweep_supported(const double* A, int64_t lda, int64_t M, int64_t N) {
     if (!sweep_eligible(A, lda, M, N)) return 0;
     SweepPlan p = make_sweep_plan(FB200_LOSS_LEAST_SQUARES, M, N);
@@ -334,6 +354,7 @@ extern "C" int fb200_dense_sweep(const double* A, int64_t lda, int64_t M, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t ldg = round_up(N, 256);
     int ncl = p.ncl;
+    if (const char* e = getenv("FB200_SWEEP_NCL")) { int v = atoi(e); if (v > 0 && v < ncl) ncl = v; }   // experiments only
     if (ncl > M) ncl = int(M);
     const int64_t cap = int64_t(fb200_workspace_bytes(M, N) - DENSE_OFF) / 8 / ldg;
     if (ncl > cap) ncl = int(cap);

@@ -42,6 +42,7 @@ SIGNATURES = {
     "fb200_gemv_loss": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _p, _sz, _p]),
     "fb200_gemvT_bb": (_int, [_p, _i64, _i64, _i64, _p, _p, _int, _p, _p, _p, _dbl, _p, _p, _sz, _p]),
     "fb200_sweep_supported": (_int, [_p, _i64, _i64, _i64]),
+    "fb200_sweep_plan": (_int, [_i64, _i64, ctypes.POINTER(ctypes.c_int)]),
     "fb200_dense_sweep": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _int, _p, _p, _p, _dbl, _p, _p, _sz, _p]),
     "fb200_tv_div_loss": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_tv_grad_bb": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),

@@ -135,6 +135,8 @@ int fb200_gemvT_bb(const double* A, int64_t lda, int64_t M, int64_t N, const dou
  * fb200_sweep_supported returns the cluster size that will be used, or 0 if the matrix is not
  * eligible (then use the two-pass entry points).                                               */
 int fb200_sweep_supported(const double* A, int64_t lda, int64_t M, int64_t N);
+/* plan[0..4] = cluster size, co-resident clusters, pipeline stages, columns per CTA, double2 per thread */
+int fb200_sweep_plan(int64_t M, int64_t N, int* plan);
 int fb200_dense_sweep(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss,
                       const double* b, double* z, double* r, double* g, int bb, const double* x0,
                       const double* xhat, const double* dx, double tau, double* scal, void* ws,

@@ -47,6 +47,10 @@ def main():
             t_min, t_avg = time_op(lambda: drv.sweep(x, _cabi.LOSS_LEAST_SQUARES, b, z, r, g, 1, None, None, None, 0.0, ws))
             rec.update(sweep_ms=t_min, sweep_avg_ms=t_avg, sweep_dram_GBs=nbytes / t_min / 1e6,
                        sweep_algorithmic_GBs=2 * nbytes / t_min / 1e6, sweep_cluster=drv.sweep_cluster)
+            import ctypes
+            plan = (ctypes.c_int * 5)()
+            _cabi.load().fb200_sweep_plan(M, N, plan)
+            rec.update(sweep_plan=dict(cs=plan[0], clusters=plan[1], stages=plan[2], nc=plan[3], cpt=plan[4]))
             g2 = torch.mv(A.T, torch.mv(A, x) - b)
             rec.update(sweep_g_relerr=float((g - g2).norm() / g2.norm()))
         t_min, _ = time_op(lambda: torch.mv(A, x))
