@@ -157,8 +157,12 @@ def fasta(*args, **kwargs) -> Convergence:
     _cabi.load()
     be = _make_backend(A, f, gradf, g, proxg, x0, opts.get("accelerate", False),
                        opts.get("evaluate_objective", False))
-    be.load()
-    result = _run(be, tuple(x0.shape), **opts)
+    try:
+        be.load()
+        result = _run(be, tuple(x0.shape), **opts)
+    finally:
+        if hasattr(be, "close"):
+            be.close()
     result.backend = type(be).__name__
     result.single_pass = bool(getattr(be, "use_sweep", False))
     result.kernel_launches = be.total_launches()

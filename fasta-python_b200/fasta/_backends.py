@@ -131,10 +131,20 @@ class ShardedDriver:
 
     def sweep(self, x, loss_tag, b, z, r, g, bb, x0, xhat, dx, tau, ws):
         self.local.sweep(x, loss_tag, b, z, r, g, 0, None, None, None, 0.0, ws)
-        self.dist.all_reduce(g, group=self.group)
-        self.collectives += 1
-        if loss_tag != S.LOSS_NONE:
-            self.reduce_loss(ws)
+        n = g.numel()
+        base = getattr(g, "_base", None)
+        packed = None
+        if loss_tag != S.LOSS_NONE and base is not None and base.numel() > n and base.data_ptr() == g.data_ptr():
+            packed = base[:n + 1]                       # [g ; raw loss partial] in one message
+            packed[n:n + 1].copy_(ws.scal[S.S_F:S.S_F + 1])
+            self.dist.all_reduce(packed, group=self.group)
+            ws.scal[S.S_F:S.S_F + 1].copy_(packed[n:n + 1])
+            self.collectives += 1
+        else:
+            self.dist.all_reduce(g, group=self.group)
+            self.collectives += 1
+            if loss_tag != S.LOSS_NONE:
+                self.reduce_loss(ws)
         if bb:
             self.local.bb_reduce(g, x0, xhat, dx, tau, bb >= 2, ws)
 
@@ -182,10 +192,13 @@ class FusedBackend:
         dev = loss.b.device
         self.n = int(np.prod(driver.xshape))
         self.m = int(np.prod(driver.zshape))
-        self.ws = _device.Workspace(*driver.workspace_dims(), device=dev)
+        self.ws = _device.acquire_workspace(*driver.workspace_dims(), device=dev)
         new = lambda k: t.empty(k, dtype=t.float64, device=dev)
         self.X = [new(self.n), new(self.n)]
-        self.G = [new(self.n), new(self.n)]
+        # gradient buffers carry 8 spare doubles: a sharded driver packs the loss partial behind the
+        # gradient so that ONE all-reduce per iteration moves both
+        self._Gbuf = [new(self.n + 8), new(self.n + 8)]
+        self.G = [g[:self.n] for g in self._Gbuf]
         self.XH, self.DX, self.BEST = new(self.n), new(self.n), new(self.n)
         self.Z, self.R = new(self.m), new(self.m)
         if self.accelerate:
@@ -207,6 +220,10 @@ class FusedBackend:
 
     def total_launches(self):
         return self.launches + self.drv.launches
+
+    def close(self):
+        _device.release_workspace(self.ws)
+        self.ws = None
 
     # -- protocol -------------------------------------------------------------------------------
     def load(self):
@@ -345,7 +362,7 @@ class GenericBackend:
         self.x0_in = x0
         self.shape = tuple(x0.shape)
         self.n = int(np.prod(self.shape))
-        self.ws = _device.Workspace(1, 1)
+        self.ws = _device.acquire_workspace(1, 1)
         self.launches = 0
         self.x1 = self.x0 = self.g1 = self.g0 = self.z1 = None
         self.xhat = self.dx = self.best = None
@@ -353,6 +370,10 @@ class GenericBackend:
 
     def total_launches(self):
         return self.launches
+
+    def close(self):
+        _device.release_workspace(self.ws)
+        self.ws = None
 
     def _dev(self, a):
         return _device.to_device(a)

@@ -77,6 +77,32 @@ class Workspace:
         return self._np      # np.float64 elements
 
 
+# ---- per-device pool: a solve borrows a workspace (device scratch + pinned scalar mirror) and gives
+# it back, so back-to-back solves pay no cudaHostAlloc / memset (kernels re-arm their own counters)
+_pool = {}
+
+
+def acquire_workspace(M, N, device=None):
+    t = torch()
+    device = device or t.device("cuda", t.cuda.current_device())
+    key = (device.index if device.index is not None else t.cuda.current_device())
+    free = _pool.setdefault(key, [])
+    need = int(_cabi.load().fb200_workspace_bytes(int(M), int(N)))
+    for i, ws in enumerate(free):
+        if ws.nbytes >= need:
+            return free.pop(i)
+    return Workspace(M, N, device=device)
+
+
+def release_workspace(ws):
+    if ws is None:
+        return
+    key = ws.device.index if ws.device.index is not None else torch().cuda.current_device()
+    free = _pool.setdefault(key, [])
+    if len(free) < 4:
+        free.append(ws)
+
+
 _shared_ws = {}
 
 
