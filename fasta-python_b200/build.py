@@ -27,6 +27,8 @@ UNITS = [
     ("tv_stencil.cu", ["-fmad=false"]),
     ("dense_stream.cu", []),
     ("dense_sweep.cu", []),
+    ("batched_gemm.cu", []),
+    ("batched_vector.cu", ["-fmad=false"]),
 ]
 
 

@@ -39,9 +39,9 @@ def __getattr__(name):
     if name == "plots":            # matplotlib is optional and never needed by the solver
         import importlib
         return importlib.import_module(".plots", __name__)
-    if name == "distributed":
+    if name in ("distributed", "batched"):
         import importlib
-        return importlib.import_module(".distributed", __name__)
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)
 
 

@@ -44,6 +44,13 @@ SIGNATURES = {
     "fb200_sweep_supported": (_int, [_p, _i64, _i64, _i64]),
     "fb200_sweep_plan": (_int, [_i64, _i64, ctypes.POINTER(ctypes.c_int)]),
     "fb200_dense_sweep": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _int, _p, _p, _p, _dbl, _p, _p, _sz, _p]),
+    "fb200_gemm_f64": (_int, [_int, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _int, _i64, _p]),
+    "fb200_gemm_splits": (_int, [_i64, _i64, _i64]),
+    "fb200_batched_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "fb200_batched_fbs_step": (_int, [_p, _p, _p, _int, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "fb200_batched_loss": (_int, [_int, _p, _int, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p]),
+    "fb200_batched_bb": (_int, [_p, _int, _i64, _p, _p, _p, _p, _p, _int, _i64, _i64, _p, _p, _p, _p]),
+    "fb200_batched_select": (_int, [_p, _p, _p, _i64, _i64, _p]),
     "fb200_tv_div_loss": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_tv_grad_bb": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),
     "fb200_dot": (_int, [_p, _p, _i64, _p, _p, _p]),

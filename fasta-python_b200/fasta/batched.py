@@ -1,0 +1,290 @@
+"""Batched FASTA: B independent forward-backward-splitting solves that share the operator A
+(a regularisation path over B penalty weights, or B right-hand sides) run in lock-step, so that
+the two contractions per iteration become fp64 GEMMs (BASELINE config 5).
+
+    results = fasta.batched.lasso_path(A, b, mus, tolerance=1e-5)           # list of Convergence, one per mu
+    results = fasta.batched.fasta_batched(A, loss, penalty, X0, **options)  # general form
+
+Every column is exactly one reference run (reference ``fasta/__init__.py:38-320``): it has its own
+step size, its own non-monotone line search (columns that fail the test are re-tried alone, the
+others keep their accepted point), its own Barzilai-Borwein update, its own best iterate and its own
+stopping time; the scalar algebra is the vectorised ``np.float64`` transcription of ``_loop.run``.
+A column's trajectory therefore matches ``fasta.fasta`` on that column (same counts; values to
+reduction-order rounding).  The randomised Lipschitz estimate (reference ``:100-113``) is drawn once:
+all columns share A, and for the least-squares / logistic losses the estimate does not depend on the
+column (the data term cancels in ``gradf1 - gradf2`` up to rounding), so each column sees what a single
+run seeded identically would see.
+
+Device work per iteration: one batched step/prox kernel, the forward GEMM, one loss kernel, the
+adjoint GEMM, one BB kernel (csrc/batched_vector.cu, csrc/batched_gemm.cu), plus masked column copies.
+Accelerated (FISTA) mode is not available in the batched loop yet.
+"""
+
+from time import time
+
+import numpy as np
+
+from . import _cabi, _device, linalg, losses, proximal, stopping
+from ._loop import Convergence, EPSILON
+
+__all__ = ["fasta_batched", "lasso_path"]
+
+
+class _Batch:
+    """Device state of a batch (all matrices row-major, batch index fastest)."""
+
+    def __init__(self, A, loss, pen, X0, B):
+        t = _device.torch()
+        self.t, self.lib = t, _cabi.load()
+        self.A = A.matrix
+        self.M, self.N, self.lda = A.M, A.N, A.lda
+        self.B = B
+        dev = self.A.device
+        self.loss, self.pen = loss, pen
+        b = loss.b
+        assert b.shape[0] == self.M and (b.ndim == 1 or b.shape[1] == B)
+        self.b, self.b_ld = (b.contiguous(), 0 if b.ndim == 1 else B)
+        new = lambda r: t.empty((r, B), dtype=t.float64, device=dev)
+        self.X0, self.X1, self.XH, self.DX, self.G0, self.G1, self.BEST = (new(self.N) for _ in range(7))
+        self.Z, self.R = new(self.M), new(self.M)
+        self.sf = int(self.lib.fb200_gemm_splits(self.M, B, self.N))       # forward: (M x B) over K = N
+        self.sa = int(self.lib.fb200_gemm_splits(self.N, B, self.M))       # adjoint: (N x B) over K = M
+        self.ZP = t.empty((self.sf, self.M, B), dtype=t.float64, device=dev)
+        self.GP = t.empty((self.sa, self.N, B), dtype=t.float64, device=dev)
+        self.ws = t.empty(int(self.lib.fb200_batched_workspace_bytes(self.M, self.N, B)), dtype=t.uint8, device=dev)
+        self.out = t.zeros(5 * B, dtype=t.float64, device=dev)
+        self.launches = 0
+        x0 = _device.to_device(X0, dev)
+        if x0.ndim == 1:
+            x0 = x0[:, None].expand(self.N, B)
+        assert tuple(x0.shape) == (self.N, B)
+        self.X1.copy_(x0)
+        self.BEST.copy_(x0)
+
+    def _st(self):
+        return _device.stream_ptr()
+
+    def _vec(self, a, dtype):
+        return self.t.as_tensor(np.ascontiguousarray(a, dtype=dtype), device=self.A.device)
+
+    def forward(self, act):
+        """Z = A X1 (all columns), then z, r = gradf(z), f for the active columns -> f (B,)"""
+        lib = self.lib
+        _cabi.check(lib.fb200_gemm_f64(0, self.A.data_ptr(), self.lda, self.X1.data_ptr(), self.B, self.ZP.data_ptr(), self.B,
+                                       self.M, self.B, self.N, self.sf, self.M * self.B, self._st()), "fb200_gemm_f64")
+        a = self._vec(act, np.int32)
+        _cabi.check(lib.fb200_batched_loss(self.loss.tag, self.ZP.data_ptr(), self.sf, self.M * self.B, self.b.data_ptr(), self.b_ld,
+                                           a.data_ptr(), self.M, self.B, self.Z.data_ptr(), self.R.data_ptr(), self.out.data_ptr(),
+                                           self.ws.data_ptr(), self._st()), "fb200_batched_loss")
+        self.launches += 3
+        return self.out[:self.B].cpu().numpy()
+
+    def adjoint(self, act, tau, bb):
+        """G1 = A^T R, per-column BB sums for the active columns -> (dx_dg, dg_sq, g_sq) each (B,)"""
+        lib = self.lib
+        _cabi.check(lib.fb200_gemm_f64(1, self.A.data_ptr(), self.lda, self.R.data_ptr(), self.B, self.GP.data_ptr(), self.B,
+                                       self.N, self.B, self.M, self.sa, self.N * self.B, self._st()), "fb200_gemm_f64")
+        a = self._vec(act, np.int32)
+        tv = self._vec(tau, np.float64)
+        _cabi.check(lib.fb200_batched_bb(self.GP.data_ptr(), self.sa, self.N * self.B, self.X0.data_ptr(), self.XH.data_ptr(),
+                                         self.DX.data_ptr(), tv.data_ptr(), a.data_ptr(), bb, self.N, self.B, self.G1.data_ptr(),
+                                         self.out.data_ptr(), self.ws.data_ptr(), self._st()), "fb200_batched_bb")
+        self.launches += 3
+        o = self.out[:3 * self.B].cpu().numpy().reshape(3, self.B)
+        return o[0], o[1], o[2]
+
+    def step(self, act, tau):
+        """xhat, x1 = prox, dx for the active columns -> (dx_g0, dx_sq, xmxh_sq, pen_raw) each (B,)"""
+        p0, p1 = self.pen.params(np.asarray(tau, dtype=np.float64))
+        p0 = np.broadcast_to(np.asarray(p0, dtype=np.float64), (self.B,))
+        p1 = np.broadcast_to(np.asarray(p1, dtype=np.float64), (self.B,))
+        a, tv = self._vec(act, np.int32), self._vec(tau, np.float64)
+        p0d, p1d = self._vec(p0, np.float64), self._vec(p1, np.float64)
+        _cabi.check(self.lib.fb200_batched_fbs_step(self.X0.data_ptr(), self.G0.data_ptr(), tv.data_ptr(), self.pen.tag,
+                                                    p0d.data_ptr(), p1d.data_ptr(), a.data_ptr(), self.N, self.B,
+                                                    self.XH.data_ptr(), self.X1.data_ptr(), self.DX.data_ptr(),
+                                                    self.out.data_ptr(), self.ws.data_ptr(), self._st()), "fb200_batched_fbs_step")
+        self.launches += 2
+        o = self.out[:4 * self.B].cpu().numpy().reshape(4, self.B)
+        return o[0], o[1], o[2], o[3]
+
+    def select(self, dst, src, mask):
+        if not np.any(mask):
+            return
+        m = self._vec(mask, np.int32)
+        _cabi.check(self.lib.fb200_batched_select(dst.data_ptr(), src.data_ptr(), m.data_ptr(), dst.shape[0], self.B, self._st()),
+                    "fb200_batched_select")
+        self.launches += 1
+
+
+def _lipschitz(A, loss, x_shape_n):
+    """One randomised estimate shared by the batch: L = |A^T A (v1 - v2)| / |v1 - v2| (reference :100-113)."""
+    v1 = np.random.randn(x_shape_n)
+    v2 = np.random.randn(x_shape_n)
+    b0 = loss.b if loss.b.ndim == 1 else loss.b[:, 0].contiguous()
+    single = type(loss)(b0)
+    d1 = A.H(single.gradf(A(_device.to_device(v1))))
+    d2 = A.H(single.gradf(A(_device.to_device(v2))))
+    num = float(_device.torch().linalg.norm(d1 - d2))
+    L = np.float64(num) / np.float64(np.linalg.norm(v1 - v2))
+    return L, (2 / L) / 10
+
+
+def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verbose=False, max_iters=1000,
+                  tolerance=1e-5, stop_rule=stopping.hybrid_residual, L=None, tau0=None, backtrack=True,
+                  stepsize_shrink=None, window=10, max_backtracks=20, evaluate_objective=False):
+    """Solve B problems min_x f_j(A x) + g_j(x) in lock-step; returns a list of B ``Convergence``."""
+    _cabi.require_cuda()
+    if accelerate:
+        raise NotImplementedError("fasta_batched: accelerated mode is not available in the batched loop")
+    if not isinstance(A, linalg.DenseMap):
+        A = linalg.LinearMap.from_matrix(A)
+    if penalty is None:
+        penalty = proximal._Penalty()
+    if isinstance(penalty, proximal.L1Norm):
+        mus = np.atleast_1d(np.asarray(penalty.mu, dtype=np.float64))
+    else:
+        mus = np.zeros(1)
+    x0a = X0 if _device.is_array(X0) else np.asarray(X0)
+    B = x0a.shape[1] if x0a.ndim == 2 else (loss.b.shape[1] if loss.b.ndim == 2 else len(mus))
+    mus = np.broadcast_to(mus, (B,)).copy()
+    if isinstance(penalty, proximal.L1Norm):
+        penalty = proximal.L1Norm(mus)
+    if B % 2:
+        raise ValueError("fasta_batched: the batch width must be even (pad with a duplicate column)")
+    st = _Batch(A, loss, penalty, x0a, B)
+
+    if stepsize_shrink is None and backtrack:
+        stepsize_shrink = 0.2 if adaptive else 0.5
+    if not L or not tau0:
+        L, tau0 = _lipschitz(A, loss, st.N)
+    if not tau0:
+        tau0 = 1 / L
+    if verbose:
+        print(f"Initializing batched FASTA: {B} columns\n")
+
+    ones = np.ones(B, dtype=bool)
+    resid_h = np.zeros((B, max_iters))
+    nresid_h = np.zeros((B, max_iters))
+    tau_h = np.zeros((B, max_iters))
+    f_h = np.zeros((B, max_iters + 1))
+    obj_h = np.zeros((B, max_iters + 1)) if evaluate_objective else None
+    times = np.zeros(max_iters + 1)
+
+    tau1 = np.full(B, tau0, dtype=np.float64)
+    f1 = loss.finalize(st.forward(ones))
+    _, _, g1_sq = st.adjoint(ones, tau1, 1)
+    g1_sq = g1_sq.copy()
+    f_h[:, 0] = f1
+    pen_raw0 = np.zeros(B)
+    if evaluate_objective:
+        pen_raw0 = st.X1.abs().sum(dim=0).cpu().numpy() if isinstance(penalty, proximal.L1Norm) else np.zeros(B)
+        obj_h[:, 0] = f1 + penalty.value(pen_raw0)
+
+    done = np.zeros(B, dtype=bool)
+    iters = np.zeros(B, dtype=np.int64)
+    total_bt = np.zeros(B, dtype=np.int64)
+    max_resid = np.full(B, -np.inf)
+    best_q = np.full(B, np.inf)
+    dx_g0, dx_sq, xmxh_sq, pen_raw = (np.zeros(B) for _ in range(4))
+    f1 = f1.copy()
+
+    i = 0
+    while i < max_iters and not done.all():
+        times[i] = time()
+        act = ~done
+        st.select(st.X0, st.X1, act)                      # x0 <- x1, gradf0 <- gradf1 (reference :176-177)
+        st.select(st.G0, st.G1, act)
+        g0_sq = g1_sq.copy()
+        tau_cur = tau1.copy()
+
+        def trial(mask):
+            a, b_, c, d = st.step(mask, tau_cur)
+            fm = loss.finalize(st.forward(mask))
+            dx_g0[mask], dx_sq[mask], xmxh_sq[mask], pen_raw[mask] = a[mask], b_[mask], c[mask], d[mask]
+            f1[mask] = fm[mask]
+
+        trial(act)
+        bt = np.zeros(B, dtype=np.int64)
+        if backtrack:
+            lo = max(i - window + 1, 0)
+            f_max = np.max(f_h[:, lo:i + 1], axis=1)
+            while True:
+                with np.errstate(all="ignore"):
+                    need = act & (f1 - (f_max + dx_g0 + np.sqrt(dx_sq) ** 2 / (2 * tau_cur)) > EPSILON) & (bt < max_backtracks)
+                if not need.any():
+                    break
+                tau_cur[need] *= stepsize_shrink
+                trial(need)
+                bt[need] += 1
+            total_bt += bt
+
+        dx_dg, dg_sq, gsq = st.adjoint(act, tau_cur, 2 if adaptive else 1)
+        g1_sq[act] = gsq[act]
+        tau1[act] = tau_cur[act]
+        dx_norm = np.sqrt(dx_sq)
+        if adaptive:
+            with np.errstate(all="ignore"):
+                tau_s = dx_norm ** 2 / dx_dg
+                q = dx_dg / np.sqrt(dg_sq) ** 2
+                tau_m = np.where(np.isnan(q), q, np.maximum(q, 0))      # python max(q, 0) keeps a nan first argument
+                new = np.where(2 * tau_m > tau_s, tau_m, tau_s - .5 * tau_m)
+                bad = (new <= 0) | np.isinf(new) | np.isnan(new)
+                new = np.where(bad, tau_cur * 1.5, new)
+            tau1[act] = new[act]
+
+        with np.errstate(all="ignore"):
+            resid = dx_norm / tau_cur
+            normalizer = np.maximum(np.sqrt(g0_sq), np.sqrt(xmxh_sq) / tau_cur) + EPSILON
+            nresid = resid / normalizer
+        resid_h[act, i] = resid[act]
+        tau_h[act, i] = tau_cur[act]
+        nresid_h[act, i] = nresid[act]
+        f_h[act, i + 1] = f1[act]
+        max_resid[act] = np.maximum(max_resid[act], resid[act])
+        if evaluate_objective:
+            obj = f1 + penalty.value(pen_raw)
+            obj_h[act, i + 1] = obj[act]
+            quality = obj
+        else:
+            quality = resid
+        better = act & (quality < best_q)
+        st.select(st.BEST, st.X1, better)
+        best_q[better] = quality[better]
+
+        for j in np.nonzero(act)[0]:
+            with np.errstate(all="ignore"):
+                stop = stop_rule(i, resid_h[j, i], nresid_h[j, i], max_resid[j], tolerance)
+            iters[j] = i + 1
+            if stop:
+                done[j] = True
+        if verbose:
+            print(f"[{i:<6}]\tactive {int(act.sum()):4d}\tmax residual {np.max(resid[act]):e}")
+        i += 1
+    times[i] = time()
+
+    best = st.BEST.t().contiguous()          # (B, N)
+    results = []
+    for j in range(B):
+        n = int(iters[j])
+        tj = np.zeros(max_iters + 1)
+        tj[:n] = times[:n]
+        tj[n] = times[min(n, i)] if n < i else times[i]
+        sol = _device.like_input(best[j].clone(), x0a)
+        c = Convergence(resid_h[j], nresid_h[j], tau_h[j], int(total_bt[j]), tj, n, sol,
+                        obj_h[j] if evaluate_objective else None, None, None)
+        results.append(c)
+    results_meta = dict(kernel_launches=st.launches, gemm_splits=(st.sf, st.sa), iterations_lockstep=i)
+    for c in results:
+        c.batch = results_meta
+    return results
+
+
+def lasso_path(A, b, mus, x0=None, **options):
+    """The regularisation path min mu_j |x|_1 + .5 |A x - b|^2 for every mu_j in ``mus`` (config 5)."""
+    mus = np.asarray(mus, dtype=np.float64)
+    if not isinstance(A, linalg.DenseMap):
+        A = linalg.LinearMap.from_matrix(A)
+    if x0 is None:
+        x0 = np.zeros((A.N, len(mus)))
+    return fasta_batched(A, losses.LeastSquares(b), proximal.L1Norm(mus), x0, **options)

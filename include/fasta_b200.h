@@ -142,6 +142,36 @@ int fb200_dense_sweep(const double* A, int64_t lda, int64_t M, int64_t N, const 
                       const double* xhat, const double* dx, double tau, double* scal, void* ws,
                       size_t ws_bytes, void* stream);
 
+/* ---- K14: batched contractions (B columns, batch index fastest), fp64 DMMA GEMM -----------------
+ * adjoint = 0:  C (Mg x Ng) = A (Mg x K) . B (K x Ng)         the per-column `A @ x`   of linalg.py:41
+ * adjoint = 1:  C (Mg x Ng) = A^T . B with A stored (K x Mg)  the per-column `A.T @ r` of linalg.py:41
+ * all matrices row-major fp64 with even leading dimensions and 16-byte aligned bases.            */
+int fb200_gemm_f64(int adjoint, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                   int64_t ldc, int64_t Mg, int64_t Ng, int64_t K, int splits, int64_t split_stride,
+                   void* stream);
+/* K slices that balance the chip for this shape; with splits > 1 C holds [splits][split_stride]
+ * partial products which the batched epilogues add in index order                                */
+int fb200_gemm_splits(int64_t Mg, int64_t Ng, int64_t K);
+
+/* per-column vector kernels of the batched loop: arrays are (rows x B) row-major, batch fastest;
+ * tau / p0 / p1 are per-column (device, B doubles), act is a per-column int mask (only active
+ * columns are touched); out receives per-column sums as [k][B]:
+ *   fbs_step: k = <Dx,g0>, <Dx,Dx>, |x1-xhat|^2, sum|x1|     (reference __init__.py:181-186,200,274,285)
+ *   loss    : k = raw f                                        (sparse_least_squares.py:41-42)
+ *   bb      : k = <Dx,Dg>, <Dg,Dg>, <g1,g1>                    (__init__.py:254-260,274)
+ * ws: fb200_batched_workspace_bytes(M, N, B) bytes of device scratch.                             */
+size_t fb200_batched_workspace_bytes(int64_t M, int64_t N, int64_t B);
+int fb200_batched_fbs_step(const double* x0, const double* g0, const double* tau, int prox, const double* p0,
+                           const double* p1, const int* act, int64_t n, int64_t B, double* xhat, double* x1,
+                           double* dx, double* out, void* ws, void* stream);
+int fb200_batched_loss(int loss, const double* zsrc, int nsplit, int64_t split_stride, const double* b,
+                       int64_t b_ld, const int* act, int64_t m, int64_t B, double* z, double* r, double* out,
+                       void* ws, void* stream);
+int fb200_batched_bb(const double* gsrc, int nsplit, int64_t split_stride, const double* x0, const double* xhat,
+                     const double* dx, const double* tau, const int* act, int bb, int64_t n, int64_t B,
+                     double* g1, double* out, void* ws, void* stream);
+int fb200_batched_select(double* dst, const double* src, const int* mask, int64_t n, int64_t B, void* stream);
+
 /* ---- K11/K12: total-variation stencils (periodic)               tv_denoising.py:26-63
  * Y is n0 x n1 x 2 (last axis interleaved), Z is n0 x n1.
  * div:  Z = sum_d roll(Y[...,d],-1,d) - Y[...,d], fused with the loss epilogue like gemv_loss.
