@@ -65,31 +65,58 @@ class _Batch:
         return _device.stream_ptr()
 
     def _vec(self, a, dtype):
-        return self.t.as_tensor(np.ascontiguousarray(a, dtype=dtype), device=self.A.device)
+        return self.t.as_tensor(np.array(a, dtype=dtype, copy=True), device=self.A.device)
+
+    def _gemm(self, adjoint, src, part, rows, K, splits, act):
+        """Columns `act` of (A or A^T) . src into `part`; returns the number of split partials the
+        epilogue has to add (1 when the product was computed on a compacted column subset)."""
+        lib, t = self.lib, self.t
+        n_act = int(np.count_nonzero(act))
+        if n_act > 0.75 * self.B or self.B <= 8:
+            _cabi.check(lib.fb200_gemm_f64(adjoint, self.A.data_ptr(), self.lda, src.data_ptr(), self.B, part.data_ptr(),
+                                           self.B, rows, self.B, K, splits, rows * self.B, self._st()), "fb200_gemm_f64")
+            self.launches += 1
+            return splits
+        # few active columns (late iterations, or a handful of columns re-trying a shorter step):
+        # gather them, multiply the narrow matrix, scatter the result columns back
+        cols = np.nonzero(act)[0]
+        if len(cols) % 2:
+            cols = np.append(cols, cols[-1])
+        idx = t.as_tensor(cols, device=src.device)
+        nb = len(cols)
+        sub = src.index_select(1, idx).contiguous()
+        s = int(lib.fb200_gemm_splits(rows, nb, K))
+        out = t.empty((s, rows, nb), dtype=t.float64, device=src.device)
+        _cabi.check(lib.fb200_gemm_f64(adjoint, self.A.data_ptr(), self.lda, sub.data_ptr(), nb, out.data_ptr(), nb, rows, nb, K,
+                                       s, rows * nb, self._st()), "fb200_gemm_f64")
+        self.launches += 1
+        res = out[0]
+        for k in range(1, s):
+            res = res + out[k]                 # fixed order
+        part[0].index_copy_(1, idx, res)
+        return 1
 
     def forward(self, act):
-        """Z = A X1 (all columns), then z, r = gradf(z), f for the active columns -> f (B,)"""
+        """Z = A X1 on the active columns, then z, r = gradf(z), f for them -> f (B,)"""
         lib = self.lib
-        _cabi.check(lib.fb200_gemm_f64(0, self.A.data_ptr(), self.lda, self.X1.data_ptr(), self.B, self.ZP.data_ptr(), self.B,
-                                       self.M, self.B, self.N, self.sf, self.M * self.B, self._st()), "fb200_gemm_f64")
+        ns = self._gemm(0, self.X1, self.ZP, self.M, self.N, self.sf, act)
         a = self._vec(act, np.int32)
-        _cabi.check(lib.fb200_batched_loss(self.loss.tag, self.ZP.data_ptr(), self.sf, self.M * self.B, self.b.data_ptr(), self.b_ld,
+        _cabi.check(lib.fb200_batched_loss(self.loss.tag, self.ZP.data_ptr(), ns, self.M * self.B, self.b.data_ptr(), self.b_ld,
                                            a.data_ptr(), self.M, self.B, self.Z.data_ptr(), self.R.data_ptr(), self.out.data_ptr(),
                                            self.ws.data_ptr(), self._st()), "fb200_batched_loss")
-        self.launches += 3
+        self.launches += 2
         return self.out[:self.B].cpu().numpy()
 
     def adjoint(self, act, tau, bb):
-        """G1 = A^T R, per-column BB sums for the active columns -> (dx_dg, dg_sq, g_sq) each (B,)"""
+        """G1 = A^T R on the active columns, per-column BB sums -> (dx_dg, dg_sq, g_sq) each (B,)"""
         lib = self.lib
-        _cabi.check(lib.fb200_gemm_f64(1, self.A.data_ptr(), self.lda, self.R.data_ptr(), self.B, self.GP.data_ptr(), self.B,
-                                       self.N, self.B, self.M, self.sa, self.N * self.B, self._st()), "fb200_gemm_f64")
+        ns = self._gemm(1, self.R, self.GP, self.N, self.M, self.sa, act)
         a = self._vec(act, np.int32)
         tv = self._vec(tau, np.float64)
-        _cabi.check(lib.fb200_batched_bb(self.GP.data_ptr(), self.sa, self.N * self.B, self.X0.data_ptr(), self.XH.data_ptr(),
+        _cabi.check(lib.fb200_batched_bb(self.GP.data_ptr(), ns, self.N * self.B, self.X0.data_ptr(), self.XH.data_ptr(),
                                          self.DX.data_ptr(), tv.data_ptr(), a.data_ptr(), bb, self.N, self.B, self.G1.data_ptr(),
                                          self.out.data_ptr(), self.ws.data_ptr(), self._st()), "fb200_batched_bb")
-        self.launches += 3
+        self.launches += 2
         o = self.out[:3 * self.B].cpu().numpy().reshape(3, self.B)
         return o[0], o[1], o[2]
 
