@@ -143,6 +143,160 @@ tv_grad_bb_kernel(const double* __restrict__ R, int64_t n0, int64_t n1, double2*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused TV iteration (non-accelerated modes): the forward step, the per-pixel ball projection, the
+// divergence and the loss in ONE pass,
+//     xhat = x0 - tau*g0 ; x1 = xhat / max(|xhat|_2, 1) ; z = div(x1) ; r = z - b ; sums
+// (reference __init__.py:181-188 with tv_denoising.py:43-63,85-96).  xhat, dx and z are never
+// written: the gradient kernel below recomputes xhat and dx from x0, g0, x1 with the same
+// expressions (bit-identical), so an iteration moves 8U + 9U (adaptive) or 8U + 3U (plain) bytes
+// instead of 24U / 18U, U = n0*n1*8.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 tv_prox_point(double2 a, double2 gr, double tau, double2& h) {
+    h.x = a.x - tau * gr.x;
+    h.y = a.y - tau * gr.y;
+    const double nrm = fmax(sqrt(h.x * h.x + h.y * h.y), 1.0);
+    return make_double2(h.x / nrm, h.y / nrm);
+}
+
+template <int LOSS>
+__global__ void __launch_bounds__(TV_THREADS)
+tv_step_div_loss_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, double tau, int64_t n0, int64_t n1,
+                        const double* __restrict__ b, double2* __restrict__ x1, double* __restrict__ r, int strip,
+                        double* scal, double* red, unsigned* counter) {
+    const int lane   = threadIdx.x & 31;
+    const int64_t j  = int64_t(blockIdx.x) * TV_THREADS + threadIdx.x;
+    const int64_t i0 = int64_t(blockIdx.y) * strip;
+    const bool live  = j < n1;
+    const int64_t jc = live ? j : 0;
+    const int64_t jr = (jc + 1 == n1) ? 0 : jc + 1;
+    const bool edge  = (lane == 31) || (jc + 1 == n1);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};      // <dx,g0>, <dx,dx>, |x1-xhat|^2, f
+    if (i0 < n0) {
+        const int64_t i1 = (i0 + strip < n0) ? i0 + strip : n0;
+        // first row of the strip: this thread owns it (store + sums)
+        double2 a = x0[i0 * n1 + jc], gr = g0[i0 * n1 + jc], h;
+        double2 cur = tv_prox_point(a, gr, tau, h);
+        if (live) {
+            x1[i0 * n1 + j] = cur;
+            const double dxx = cur.x - a.x, dxy = cur.y - a.y, ex = cur.x - h.x, ey = cur.y - h.y;
+            s[0] += dxx * gr.x; s[0] += dxy * gr.y;
+            s[1] += dxx * dxx;  s[1] += dxy * dxy;
+            s[2] += ex * ex;    s[2] += ey * ey;
+        }
+        for (int64_t ib = i0; ib < i1; ib += TV_UNROLL) {
+            double2 an[TV_UNROLL], gn[TV_UNROLL], ae[TV_UNROLL], ge[TV_UNROLL];
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {            // loads first: rows ib+1 .. ib+UNROLL (periodic)
+                const int64_t i  = ib + u;
+                const int64_t in = (i + 1 >= n0) ? (i + 1 - n0) : i + 1;
+                const bool ok = i < i1;
+                an[u] = ok ? x0[in * n1 + jc] : make_double2(0.0, 0.0);
+                gn[u] = ok ? g0[in * n1 + jc] : make_double2(0.0, 0.0);
+                ae[u] = (ok && edge) ? x0[i * n1 + jr] : make_double2(0.0, 0.0);
+                ge[u] = (ok && edge) ? g0[i * n1 + jr] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {
+                const int64_t i = ib + u;
+                double2 hn;
+                const double2 nxt = tv_prox_point(an[u], gn[u], tau, hn);      // x1 at (i+1, j)
+                double right = __shfl_down_sync(0xffffffffu, cur.y, 1);        // x1 at (i, j+1), y component
+                if (edge) {
+                    double2 he;
+                    right = tv_prox_point(ae[u], ge[u], tau, he).y;
+                }
+                if (i < i1 && live) {
+                    const double zi = (nxt.x - cur.x) + (right - cur.y);
+                    const int64_t o = i * n1 + j;
+                    double ri, fi;
+                    loss_elem<LOSS>(zi, b[o], ri, fi);
+                    r[o] = ri;
+                    s[3] += fi;
+                    if (i + 1 < i1) {                                          // row i+1 is ours too: store + sums
+                        x1[(i + 1) * n1 + j] = nxt;
+                        const double dxx = nxt.x - an[u].x, dxy = nxt.y - an[u].y, ex = nxt.x - hn.x, ey = nxt.y - hn.y;
+                        s[0] += dxx * gn[u].x; s[0] += dxy * gn[u].y;
+                        s[1] += dxx * dxx;     s[1] += dxy * dxy;
+                        s[2] += ex * ex;       s[2] += ey * ey;
+                    }
+                }
+                cur = nxt;
+            }
+        }
+    }
+    double* const out[4] = {scal + FB200_S_DX_G0, scal + FB200_S_DX_SQ, scal + FB200_S_XMXH_SQ, scal + FB200_S_F};
+    grid_sum<4>(s, red, counter, out);
+}
+
+// G = grad(R) fused with the BB reductions, recomputing xhat = x0 - tau*g0 and dx = x1 - x0
+template <int BB>
+__global__ void __launch_bounds__(TV_THREADS)
+tv_grad_bb_fused_kernel(const double* __restrict__ R, int64_t n0, int64_t n1, double2* __restrict__ g,
+                        const double2* __restrict__ x0, const double2* __restrict__ g0, const double2* __restrict__ x1,
+                        double tau, int strip, double* scal, double* red, unsigned* counter) {
+    const int lane   = threadIdx.x & 31;
+    const int64_t j  = int64_t(blockIdx.x) * TV_THREADS + threadIdx.x;
+    const int64_t i0 = int64_t(blockIdx.y) * strip;
+    const bool live  = j < n1;
+    const int64_t jc = live ? j : 0;
+    const int64_t jl = (jc == 0) ? n1 - 1 : jc - 1;
+    double s[3] = {0.0, 0.0, 0.0};
+    if (i0 < n0) {
+        const int64_t i1 = (i0 + strip < n0) ? i0 + strip : n0;
+        double up = R[((i0 == 0) ? n0 - 1 : i0 - 1) * n1 + jc];
+        for (int64_t ib = i0; ib < i1; ib += TV_UNROLL) {
+            double c[TV_UNROLL], lf[TV_UNROLL];
+            double2 p[TV_UNROLL], q[TV_UNROLL], y[TV_UNROLL];
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {
+                const int64_t i = ib + u;
+                const bool ok = i < i1;
+                c[u] = ok ? R[i * n1 + jc] : 0.0;
+                if (BB >= 2) {
+                    p[u] = ok ? x0[i * n1 + jc] : make_double2(0.0, 0.0);
+                    q[u] = ok ? g0[i * n1 + jc] : make_double2(0.0, 0.0);
+                    y[u] = ok ? x1[i * n1 + jc] : make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {
+                const int64_t i = ib + u;
+                double left = __shfl_up_sync(0xffffffffu, c[u], 1);
+                if ((lane == 0 || jc == 0) && i < i1) left = R[i * n1 + jl];
+                lf[u] = left;
+            }
+#pragma unroll
+            for (int u = 0; u < TV_UNROLL; ++u) {
+                const int64_t i = ib + u;
+                if (i < i1 && live) {
+                    const double a = (u == 0) ? up : c[u - 1];
+                    double2 gi;
+                    gi.x = a - c[u];
+                    gi.y = lf[u] - c[u];
+                    g[i * n1 + j] = gi;
+                    s[2] += gi.x * gi.x;
+                    s[2] += gi.y * gi.y;
+                    if (BB >= 2) {
+                        const double hx = p[u].x - tau * q[u].x, hy = p[u].y - tau * q[u].y;      // xhat, as in the step kernel
+                        const double dxx = y[u].x - p[u].x, dxy = y[u].y - p[u].y;                // dx = x1 - x0
+                        const double dg0 = gi.x + (hx - p[u].x) / tau;
+                        const double dg1 = gi.y + (hy - p[u].y) / tau;
+                        s[0] += dxx * dg0;
+                        s[0] += dxy * dg1;
+                        s[1] += dg0 * dg0;
+                        s[1] += dg1 * dg1;
+                    }
+                }
+            }
+            up = c[TV_UNROLL - 1];
+        }
+    }
+    double* const out[3] = {BB >= 2 ? scal + FB200_S_DX_DG : nullptr, BB >= 2 ? scal + FB200_S_DG_SQ : nullptr,
+                            scal + FB200_S_G1_SQ};
+    grid_sum<3>(s, red, counter, out);
+}
+
 static int tv_grid(int64_t n0, int64_t n1, dim3* grid, int* strip) {
     const int64_t gx = (n1 + TV_THREADS - 1) / TV_THREADS;
     int64_t st = TV_STRIP;
@@ -200,4 +354,40 @@ extern "C" int fb200_tv_grad_bb(const double* R, int64_t n0, int64_t n1, double*
         default: set_error("unknown bb mode %d", bb); return 1;
     }
     return check_launch("tv_grad_bb");
+}
+
+extern "C" int fb200_tv_step_div_loss(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, int loss,
+                                      const double* b, double* x1, double* r, double* scal, void* ws, void* stream) {
+    Workspace w(ws);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid;
+    int strip = TV_STRIP;
+    if (n0 < 1 || n1 < 1) { set_error("tv_step_div_loss: bad shape"); return 1; }
+    if (tv_grid(n0, n1, &grid, &strip)) return 1;
+    switch (loss) {
+        case FB200_LOSS_LEAST_SQUARES:
+            tv_step_div_loss_kernel<FB200_LOSS_LEAST_SQUARES><<<grid, TV_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, n0, n1, b, (double2*)x1, r, strip, scal, w.red, w.counter);
+            break;
+        case FB200_LOSS_LOGISTIC:
+            tv_step_div_loss_kernel<FB200_LOSS_LOGISTIC><<<grid, TV_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, n0, n1, b, (double2*)x1, r, strip, scal, w.red, w.counter);
+            break;
+        default: set_error("tv_step_div_loss: unsupported loss tag %d", loss); return 1;
+    }
+    return check_launch("tv_step_div_loss");
+}
+
+extern "C" int fb200_tv_grad_bb_fused(const double* R, int64_t n0, int64_t n1, double* g, int bb, const double* x0,
+                                      const double* g0, const double* x1, double tau, double* scal, void* ws,
+                                      void* stream) {
+    Workspace w(ws);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid;
+    int strip = TV_STRIP;
+    if (n0 < 1 || n1 < 1) { set_error("tv_grad_bb_fused: bad shape"); return 1; }
+    if (tv_grid(n0, n1, &grid, &strip)) return 1;
+    if (bb >= 2)
+        tv_grad_bb_fused_kernel<2><<<grid, TV_THREADS, 0, st>>>(R, n0, n1, (double2*)g, (const double2*)x0, (const double2*)g0, (const double2*)x1, tau, strip, scal, w.red, w.counter);
+    else
+        tv_grad_bb_fused_kernel<1><<<grid, TV_THREADS, 0, st>>>(R, n0, n1, (double2*)g, (const double2*)x0, (const double2*)g0, (const double2*)x1, tau, strip, scal, w.red, w.counter);
+    return check_launch("tv_grad_bb_fused");
 }

@@ -165,5 +165,6 @@ def fasta(*args, **kwargs) -> Convergence:
             be.close()
     result.backend = type(be).__name__
     result.single_pass = bool(getattr(be, "use_sweep", False))
+    result.tv_fused = bool(getattr(be, "use_tv_fused", False))
     result.kernel_launches = be.total_launches()
     return result

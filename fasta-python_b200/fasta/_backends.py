@@ -97,6 +97,22 @@ class TVDriver:
                                               ws.buf.data_ptr(), _device.stream_ptr()), "fb200_tv_grad_bb")
         self.launches += 1
 
+    # fused iteration (non-accelerated modes): step + ball projection + div + loss in one pass, and
+    # grad + BB with xhat / dx recomputed -- xhat, dx and z are never materialised
+    fused_step_ok = os.environ.get("FASTA_B200_TV_FUSED", "1") != "0"
+
+    def step_forward(self, x0, g0, tau, loss_tag, b, x1, r, ws):
+        _cabi.check(self.lib.fb200_tv_step_div_loss(x0.data_ptr(), g0.data_ptr(), float(tau), self.n0, self.n1, loss_tag,
+                                                    b.data_ptr(), x1.data_ptr(), r.data_ptr(), ws.scal.data_ptr(),
+                                                    ws.buf.data_ptr(), _device.stream_ptr()), "fb200_tv_step_div_loss")
+        self.launches += 1
+
+    def adjoint_fused(self, r, g, bb, x0, g0, x1, tau, ws):
+        _cabi.check(self.lib.fb200_tv_grad_bb_fused(r.data_ptr(), self.n0, self.n1, g.data_ptr(), bb, x0.data_ptr(),
+                                                    g0.data_ptr(), x1.data_ptr(), float(tau), ws.scal.data_ptr(),
+                                                    ws.buf.data_ptr(), _device.stream_ptr()), "fb200_tv_grad_bb_fused")
+        self.launches += 1
+
     def sync_point(self, v1, v2):
         pass
 
@@ -213,6 +229,9 @@ class FusedBackend:
         # a rejected trial costs exactly what the two-pass path would have paid for it).
         self.use_sweep = (not self.accelerate) and bool(getattr(driver, "sweep_ok", False))
         self._spec = None
+        # TV: one fused kernel per half-iteration (see TVDriver.step_forward)
+        self.use_tv_fused = ((not self.accelerate) and isinstance(driver, TVDriver) and driver.fused_step_ok
+                             and penalty.tag == S.PROX_TV_BALL and loss.tag != S.LOSS_NONE)
 
     # -- helpers --------------------------------------------------------------------------------
     def _st(self):
@@ -288,6 +307,11 @@ class FusedBackend:
         xa_prev = self.XA[self.ap] if self.accelerate else None
         p0, p1 = self.pen.params(tau)
         st = self._st()
+        if self.use_tv_fused:
+            self.drv.step_forward(x0, g0, tau, self.loss.tag, self.loss.b, x1, self.R, self.ws)
+            s = self.ws.fetch()
+            return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
+                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0))
         if self.pen.tag == S.PROX_L1BALL:
             _cabi.check(self.lib.fb200_forward_step(x0.data_ptr(), g0.data_ptr(), float(tau), self.n,
                                                     self.XH.data_ptr(), st), "fb200_forward_step")
@@ -328,6 +352,11 @@ class FusedBackend:
         if self.use_sweep and self._spec is not None:
             spec, self._spec = self._spec, None      # produced by the accepted trial's sweep: no device work
             return spec
+        if self.use_tv_fused:
+            self.drv.adjoint_fused(self.R, self.G[self.gc], 2 if adaptive else 1, self.X[self.ip], self.G[self.gp],
+                                   self.X[self.ic], tau, self.ws)
+            s = self.ws.fetch()
+            return Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
         self.drv.adjoint(self.R, self.G[self.gc], 2 if adaptive else 1, self.X[self.ip], self.XH, self.DX, tau, self.ws)
         s = self.ws.fetch()
         return Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])

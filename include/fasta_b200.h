@@ -182,6 +182,16 @@ int fb200_tv_grad_bb(const double* R, int64_t n0, int64_t n1, double* g, int bb,
                      const double* xhat, const double* dx, double tau, double* scal, void* ws,
                      void* stream);
 
+/* fused TV iteration for the non-accelerated modes (K1-K3 + K11 + K5 in one pass, K11 + K8 in one):
+ *   step_div_loss : xhat = x0 - tau*g0, x1 = xhat/max(|xhat|_2,1), r = div(x1) - b;
+ *                   scal[S_DX_G0, S_DX_SQ, S_XMXH_SQ, S_F]   (__init__.py:181-188, tv_denoising.py:43-63,85-96)
+ *   grad_bb_fused : g = grad(r); BB sums with xhat and dx recomputed from x0, g0, x1 (__init__.py:248-260) */
+int fb200_tv_step_div_loss(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, int loss,
+                           const double* b, double* x1, double* r, double* scal, void* ws, void* stream);
+int fb200_tv_grad_bb_fused(const double* R, int64_t n0, int64_t n1, double* g, int bb, const double* x0,
+                           const double* g0, const double* x1, double tau, double* scal, void* ws,
+                           void* stream);
+
 /* ---- small reductions used by the prologue and the generic (untagged-callable) path ---------
  * out (device) receives: dot = <a,b>; diff_nrm2sq = |a-b|^2; asum = sum |a|                   */
 int fb200_dot(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream);

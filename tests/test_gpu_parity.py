@@ -50,6 +50,27 @@ def test_two_pass_path_matches_golden(case, mode, monkeypatch):
     assert_trajectory(res, gold, label=f"two-pass/{case}/{mode}")
 
 
+@pytest.mark.parametrize("case,mode", golden_cases(prefixes=("tv_",)))
+def test_tv_unfused_kernels_match_golden(case, mode, monkeypatch):
+    """TV with the fused iteration kernels disabled (separate step / div / grad kernels)."""
+    import fasta
+    monkeypatch.setattr(fasta._backends.TVDriver, "fused_step_ok", False)
+    gold = load_golden(case, mode)
+    p = problems.build(case, int(gold["seed"]))
+    A, loss, pen = tagged(p)
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert not res.tv_fused
+    assert_trajectory(res, gold, label=f"tv-unfused/{case}/{mode}")
+
+
+def test_tv_fused_is_default_for_non_accelerated():
+    import fasta
+    p = problems.build("tv_64", 0)
+    A, loss, pen = tagged(p)
+    assert fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3).tv_fused
+    assert not fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3, accelerate=True).tv_fused
+
+
 def test_single_pass_is_default_for_dense_non_accelerated():
     import fasta
     p = problems.build("lasso_200x1000_k10", 0)
