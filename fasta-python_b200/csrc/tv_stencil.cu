@@ -159,69 +159,60 @@ __device__ __forceinline__ double2 tv_prox_point(double2 a, double2 gr, double t
     return make_double2(h.x / nrm, h.y / nrm);
 }
 
+// Shared-memory stencil: a block walks 16 x 64-pixel tiles; for every pixel of the tile plus one halo
+// row and one halo column it computes the prox point once into shared memory (so the sqrt / divide
+// chain of a pixel is independent of its neighbours: no serial marching, full occupancy, every load
+// independent), then forms the divergence and the loss from shared memory.
+constexpr int TVS_TH = 16, TVS_TW = 64, TVS_THREADS = 256;
+constexpr int TVS_EXT = (TVS_TH + 1) * (TVS_TW + 1);        // 1105 prox points per tile (8% halo)
+
 template <int LOSS>
-__global__ void __launch_bounds__(TV_THREADS)
+__global__ void __launch_bounds__(TVS_THREADS)
 tv_step_div_loss_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, double tau, int64_t n0, int64_t n1,
-                        const double* __restrict__ b, double2* __restrict__ x1, double* __restrict__ r, int strip,
-                        double* scal, double* red, unsigned* counter) {
-    const int lane   = threadIdx.x & 31;
-    const int64_t j  = int64_t(blockIdx.x) * TV_THREADS + threadIdx.x;
-    const int64_t i0 = int64_t(blockIdx.y) * strip;
-    const bool live  = j < n1;
-    const int64_t jc = live ? j : 0;
-    const int64_t jr = (jc + 1 == n1) ? 0 : jc + 1;
-    const bool edge  = (lane == 31) || (jc + 1 == n1);
+                        const double* __restrict__ b, double2* __restrict__ x1, double* __restrict__ r, int tiles_x,
+                        int ntiles, double* scal, double* red, unsigned* counter) {
+    __shared__ double2 ys[TVS_EXT];
     double s[4] = {0.0, 0.0, 0.0, 0.0};      // <dx,g0>, <dx,dx>, |x1-xhat|^2, f
-    if (i0 < n0) {
-        const int64_t i1 = (i0 + strip < n0) ? i0 + strip : n0;
-        // first row of the strip: this thread owns it (store + sums)
-        double2 a = x0[i0 * n1 + jc], gr = g0[i0 * n1 + jc], h;
-        double2 cur = tv_prox_point(a, gr, tau, h);
-        if (live) {
-            x1[i0 * n1 + j] = cur;
-            const double dxx = cur.x - a.x, dxy = cur.y - a.y, ex = cur.x - h.x, ey = cur.y - h.y;
-            s[0] += dxx * gr.x; s[0] += dxy * gr.y;
-            s[1] += dxx * dxx;  s[1] += dxy * dxy;
-            s[2] += ex * ex;    s[2] += ey * ey;
-        }
-        for (int64_t ib = i0; ib < i1; ib += TV_UNROLL) {
-            double2 an[TV_UNROLL], gn[TV_UNROLL], ae[TV_UNROLL], ge[TV_UNROLL];
-#pragma unroll
-            for (int u = 0; u < TV_UNROLL; ++u) {            // loads first: rows ib+1 .. ib+UNROLL (periodic)
-                const int64_t i  = ib + u;
-                const int64_t in = (i + 1 >= n0) ? (i + 1 - n0) : i + 1;
-                const bool ok = i < i1;
-                an[u] = ok ? x0[in * n1 + jc] : make_double2(0.0, 0.0);
-                gn[u] = ok ? g0[in * n1 + jc] : make_double2(0.0, 0.0);
-                ae[u] = (ok && edge) ? x0[i * n1 + jr] : make_double2(0.0, 0.0);
-                ge[u] = (ok && edge) ? g0[i * n1 + jr] : make_double2(0.0, 0.0);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t i0 = int64_t(tile / tiles_x) * TVS_TH, j0 = int64_t(tile % tiles_x) * TVS_TW;
+        __syncthreads();                     // previous tile's reads of ys are done
+        for (int e = threadIdx.x; e < TVS_EXT; e += TVS_THREADS) {
+            const int ti = e / (TVS_TW + 1), tj = e - ti * (TVS_TW + 1);
+            int64_t i = i0 + ti, j = j0 + tj;
+            const bool mine = ti < TVS_TH && tj < TVS_TW && i < n0 && j < n1;
+            if (i >= n0) i -= n0;            // periodic wrap (tiles never exceed the image by more than one tile)
+            if (j >= n1) j -= n1;
+            if (i >= n0) i = 0;
+            if (j >= n1) j = 0;
+            const int64_t o = i * n1 + j;
+            const double2 a = x0[o], gr = g0[o];
+            double2 h;
+            const double2 y = tv_prox_point(a, gr, tau, h);
+            ys[e] = y;
+            if (mine) {
+                x1[o] = y;
+                const double dxx = y.x - a.x, dxy = y.y - a.y, ex = y.x - h.x, ey = y.y - h.y;
+                s[0] += dxx * gr.x; s[0] += dxy * gr.y;
+                s[1] += dxx * dxx;  s[1] += dxy * dxy;
+                s[2] += ex * ex;    s[2] += ey * ey;
             }
-#pragma unroll
-            for (int u = 0; u < TV_UNROLL; ++u) {
-                const int64_t i = ib + u;
-                double2 hn;
-                const double2 nxt = tv_prox_point(an[u], gn[u], tau, hn);      // x1 at (i+1, j)
-                double right = __shfl_down_sync(0xffffffffu, cur.y, 1);        // x1 at (i, j+1), y component
-                if (edge) {
-                    double2 he;
-                    right = tv_prox_point(ae[u], ge[u], tau, he).y;
-                }
-                if (i < i1 && live) {
-                    const double zi = (nxt.x - cur.x) + (right - cur.y);
-                    const int64_t o = i * n1 + j;
-                    double ri, fi;
-                    loss_elem<LOSS>(zi, b[o], ri, fi);
-                    r[o] = ri;
-                    s[3] += fi;
-                    if (i + 1 < i1) {                                          // row i+1 is ours too: store + sums
-                        x1[(i + 1) * n1 + j] = nxt;
-                        const double dxx = nxt.x - an[u].x, dxy = nxt.y - an[u].y, ex = nxt.x - hn.x, ey = nxt.y - hn.y;
-                        s[0] += dxx * gn[u].x; s[0] += dxy * gn[u].y;
-                        s[1] += dxx * dxx;     s[1] += dxy * dxy;
-                        s[2] += ex * ex;       s[2] += ey * ey;
-                    }
-                }
-                cur = nxt;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < TVS_TH * TVS_TW; e += TVS_THREADS) {
+            const int ti = e / TVS_TW, tj = e - ti * TVS_TW;
+            const int64_t i = i0 + ti, j = j0 + tj;
+            if (i < n0 && j < n1) {
+                const double2 c = ys[ti * (TVS_TW + 1) + tj];
+                // neighbours: (i+1, j) and (i, j+1); at the image edge inside a partial tile the wrapped
+                // row/column 0 sits at the next tile entry, which was filled with the wrapped index above
+                const double2 dn = ys[(ti + 1) * (TVS_TW + 1) + tj];
+                const double2 rt = ys[ti * (TVS_TW + 1) + tj + 1];
+                const double zi = (dn.x - c.x) + (rt.y - c.y);
+                const int64_t o = i * n1 + j;
+                double ri, fi;
+                loss_elem<LOSS>(zi, b[o], ri, fi);
+                r[o] = ri;
+                s[3] += fi;
             }
         }
     }
@@ -360,16 +351,19 @@ extern "C" int fb200_tv_step_div_loss(const double* x0, const double* g0, double
                                       const double* b, double* x1, double* r, double* scal, void* ws, void* stream) {
     Workspace w(ws);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dim3 grid;
-    int strip = TV_STRIP;
     if (n0 < 1 || n1 < 1) { set_error("tv_step_div_loss: bad shape"); return 1; }
-    if (tv_grid(n0, n1, &grid, &strip)) return 1;
+    const int64_t tx = (n1 + TVS_TW - 1) / TVS_TW, ty = (n0 + TVS_TH - 1) / TVS_TH;
+    if (tx * ty > (int64_t(1) << 30)) { set_error("tv_step_div_loss: image too large"); return 1; }
+    const int ntiles = int(tx * ty);
+    int grid = sm_count() * 8;
+    if (grid > ntiles) grid = ntiles;
+    if (grid > MAX_RED_BLOCKS) grid = MAX_RED_BLOCKS;
     switch (loss) {
         case FB200_LOSS_LEAST_SQUARES:
-            tv_step_div_loss_kernel<FB200_LOSS_LEAST_SQUARES><<<grid, TV_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, n0, n1, b, (double2*)x1, r, strip, scal, w.red, w.counter);
+            tv_step_div_loss_kernel<FB200_LOSS_LEAST_SQUARES><<<grid, TVS_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, n0, n1, b, (double2*)x1, r, int(tx), ntiles, scal, w.red, w.counter);
             break;
         case FB200_LOSS_LOGISTIC:
-            tv_step_div_loss_kernel<FB200_LOSS_LOGISTIC><<<grid, TV_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, n0, n1, b, (double2*)x1, r, strip, scal, w.red, w.counter);
+            tv_step_div_loss_kernel<FB200_LOSS_LOGISTIC><<<grid, TVS_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, n0, n1, b, (double2*)x1, r, int(tx), ntiles, scal, w.red, w.counter);
             break;
         default: set_error("tv_step_div_loss: unsupported loss tag %d", loss); return 1;
     }
