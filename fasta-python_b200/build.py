@@ -28,6 +28,7 @@ UNITS = [
     ("dense_stream.cu", []),
     ("dense_sweep.cu", []),
     ("batched_gemm.cu", []),
+    ("ozaki_gemm.cu", []),
     ("batched_vector.cu", ["-fmad=false"]),
 ]
 

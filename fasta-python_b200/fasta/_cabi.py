@@ -46,6 +46,11 @@ SIGNATURES = {
     "fb200_dense_sweep": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _int, _p, _p, _p, _dbl, _p, _p, _sz, _p]),
     "fb200_gemm_f64": (_int, [_int, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _int, _i64, _p]),
     "fb200_gemm_splits": (_int, [_i64, _i64, _i64]),
+    "fb200_ozaki_pad": (_i64, [_i64, _int]),
+    "fb200_ozaki_splits": (_int, [_i64, _i64, _i64]),
+    "fb200_ozaki_slice_rows": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
+    "fb200_ozaki_slice_cols": (_int, [_p, _i64, _i64, _p, _i64, _int, _p, _p, _p, _p]),
+    "fb200_ozaki_gemm": (_int, [_p, _p, _i64, _p, _p, _i64, _i64, _p, _i64, _p, _int, _i64, _p]),
     "fb200_batched_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "fb200_batched_fbs_step": (_int, [_p, _p, _p, _int, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "fb200_batched_loss": (_int, [_int, _p, _int, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p]),

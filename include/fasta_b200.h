@@ -153,6 +153,31 @@ int fb200_gemm_f64(int adjoint, const double* A, int64_t lda, const double* B, i
  * partial products which the batched epilogues add in index order                                */
 int fb200_gemm_splits(int64_t Mg, int64_t Ng, int64_t K);
 
+/* ---- K14 on tcgen05: fp64-accurate batched contractions from int8 digit planes (csrc/ozaki_gemm.cu) --
+ * Both operands are split error-free into 8 signed 7-bit digit planes with a power-of-two scale per row
+ * (left operand) / per column (right operand); the 36 digit-pair products with s + t <= 7 run as
+ * tcgen05.mma.kind::i8 GEMMs into int32 TMEM accumulators and are recombined in fp64.  Replaces the same
+ * reference lines as fb200_gemm_f64 (linalg.py:41, per column).
+ *   pad(n, tile)     = n rounded up to a multiple of tile
+ *   slice_rows       : P (R x C, ld) -> planes S [8][pad(R,128)][pad(C,128)] int8, scale [pad(R,128)]
+ *                      (left operand of the forward product: P = A, contraction over C)
+ *   slice_cols       : selected columns of P (R x C, ld) -> TRANSPOSED planes S [8][pad(ncols,tile)][pad(R,128)],
+ *                      scale [pad(ncols,tile)]; colmap == NULL selects columns 0..ncols-1; tile = 128 for a left
+ *                      operand (P = A for the adjoint product), 64 for a right operand (P = X or R);
+ *                      scratch = ncols * 8 bytes
+ *   gemm             : C[m][colmap ? colmap[n] : n] = sum_k L[m][k] R[k][n], m < Mg, n < Ng, from the planes of
+ *                      L (row-scaled, pad 128) and R (column-scaled transposed, pad 64); with splits > 1, C holds
+ *                      [splits][split_stride] partial products (use fb200_ozaki_splits, which also bounds the
+ *                      split length so that the int32 accumulation is exact)                                */
+int64_t fb200_ozaki_pad(int64_t n, int tile);
+int fb200_ozaki_splits(int64_t Mg, int64_t Ng, int64_t K);
+int fb200_ozaki_slice_rows(const double* P, int64_t ld, int64_t R, int64_t C, void* S, double* scale, void* stream);
+int fb200_ozaki_slice_cols(const double* P, int64_t ld, int64_t R, const int* colmap, int64_t ncols, int tile, void* S,
+                           double* scale, void* scratch, void* stream);
+int fb200_ozaki_gemm(const void* LS, const double* lscale, int64_t Mg, const void* RS, const double* rscale, int64_t Ng,
+                     int64_t K, double* C, int64_t ldc, const int* colmap, int splits, int64_t split_stride,
+                     void* stream);
+
 /* per-column vector kernels of the batched loop: arrays are (rows x B) row-major, batch fastest;
  * tau / p0 / p1 are per-column (device, B doubles), act is a per-column int mask (only active
  * columns are touched); out receives per-column sums as [k][B]:
