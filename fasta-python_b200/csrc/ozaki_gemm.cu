@@ -80,6 +80,36 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// one lane of a converged warp (the compiler can then keep tcgen05 / TMA operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// long wait of the epilogue warps: back off so that the spin does not compete with the MMA issuer for issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(512);
+    }
+}
+
 __device__ __forceinline__ void tma_load_2d_plain(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                      smem_u32(dst)),
@@ -133,15 +163,18 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = *tslot;
 
-    if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
+    if (warp == 0) {
+        // ===== TMA producer (whole warp waits, one elected lane issues) =====
         auto issue_x = [&](int k) {
             const int xb = k & 1;
             mbar_wait(&xempty[xb], ((k >> 1) & 1) ^ 1);
-            mbar_expect_tx(&xfull[xb], OZ_S * OZ_X_TILE);
+            if (elect_one()) {
+                mbar_expect_tx(&xfull[xb], OZ_S * OZ_X_TILE);
 #pragma unroll
-            for (int t = 0; t < OZ_S; ++t)
-                tma_load_2d_plain(smX + (xb * OZ_S + t) * OZ_X_TILE, &mapX, (kb_lo + k) * OZ_BK, t * npad + n0, &xfull[xb]);
+                for (int t = 0; t < OZ_S; ++t)
+                    tma_load_2d_plain(smX + (xb * OZ_S + t) * OZ_X_TILE, &mapX, (kb_lo + k) * OZ_BK, t * npad + n0, &xfull[xb]);
+            }
+            __syncwarp();
         };
         int slot = 0;
         uint32_t phase = 0;
@@ -150,39 +183,47 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             for (int s = 0; s < OZ_S; ++s) {
                 if (s == 3 && kb + 1 < nkb) issue_x(kb + 1);
                 mbar_wait(&aempty[slot], phase ^ 1);
-                mbar_expect_tx(&afull[slot], OZ_A_TILE);
-                tma_load_2d_plain(smA + slot * OZ_A_TILE, &mapA, (kb_lo + kb) * OZ_BK, s * mpad + m0, &afull[slot]);
+                if (elect_one()) {
+                    mbar_expect_tx(&afull[slot], OZ_A_TILE);
+                    tma_load_2d_plain(smA + slot * OZ_A_TILE, &mapA, (kb_lo + kb) * OZ_BK, s * mpad + m0, &afull[slot]);
+                }
+                __syncwarp();
                 if (++slot == OZ_NA) { slot = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp == 1) {
+        // ===== MMA issuer (whole warp waits, one elected lane issues) =====
         int slot = 0;
         uint32_t phase = 0;
         for (int kb = 0; kb < nkb; ++kb) {
             const int xb = kb & 1;
             mbar_wait(&xfull[xb], (kb >> 1) & 1);
-            tc_fence_after();
             const uint32_t xlo = umma_desc_lo(smX + xb * OZ_S * OZ_X_TILE);
+#pragma unroll
             for (int s = 0; s < OZ_S; ++s) {
                 mbar_wait(&afull[slot], phase);
                 tc_fence_after();
-                const uint32_t alo = umma_desc_lo(smA + slot * OZ_A_TILE);
-                for (int t = 0; t < OZ_S - s; ++t) {
-                    const uint32_t blo = xlo + t * (OZ_X_TILE >> 4);
-                    const uint32_t dcol = tmem + uint32_t(s + t) * OZ_BN;
+                if (elect_one()) {
+                    const uint32_t alo = umma_desc_lo(smA + slot * OZ_A_TILE);
 #pragma unroll
-                    for (int k = 0; k < OZ_BK / OZ_UK; ++k) {
-                        const uint32_t acc = (kb > 0 || s > 0 || k > 0) ? 1u : 0u;
-                        umma_i8(dcol, umma_desc(alo + k * (OZ_UK >> 4)), umma_desc(blo + k * (OZ_UK >> 4)), OZ_IDESC, acc);
+                    for (int t = 0; t < OZ_S - s; ++t) {
+                        const uint32_t blo = xlo + t * (OZ_X_TILE >> 4);
+                        const uint32_t dcol = tmem + uint32_t(s + t) * OZ_BN;
+#pragma unroll
+                        for (int k = 0; k < OZ_BK / OZ_UK; ++k) {
+                            const uint32_t acc = (kb > 0 || s > 0 || k > 0) ? 1u : 0u;
+                            umma_i8(dcol, umma_desc(alo + k * (OZ_UK >> 4)), umma_desc(blo + k * (OZ_UK >> 4)), OZ_IDESC, acc);
+                        }
                     }
+                    umma_commit(&aempty[slot]);
+                    if (s == OZ_S - 1) umma_commit(&xempty[xb]);
                 }
-                umma_commit(&aempty[slot]);
+                __syncwarp();
                 if (++slot == OZ_NA) { slot = 0; phase ^= 1; }
             }
-            umma_commit(&xempty[xb]);
         }
-        umma_commit(tfull);
+        if (elect_one()) umma_commit(tfull);
+        __syncwarp();
     } else if (warp >= 2) {
         // ===== epilogue: a warp may touch the TMEM lane quarter warp % 4 =====
         const int q = warp & 3;
@@ -191,7 +232,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const double sa = (m < Mg) ? ascale[m] : 0.0;
         double* crow = C + int64_t(sp) * split_stride + int64_t(m) * ldc;
         if (nkb > 0) {
-            mbar_wait(tfull, 0);
+            mbar_wait_backoff(tfull, 0);
             tc_fence_after();
         }
         const uint32_t tbase = tmem + (uint32_t(q * 32) << 16);

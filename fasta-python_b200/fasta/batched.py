@@ -16,10 +16,14 @@ column (the data term cancels in ``gradf1 - gradf2`` up to rounding), so each co
 run seeded identically would see.
 
 Device work per iteration: one batched step/prox kernel, the forward GEMM, one loss kernel, the
-adjoint GEMM, one BB kernel (csrc/batched_vector.cu, csrc/batched_gemm.cu), plus masked column copies.
+adjoint GEMM, one BB kernel (csrc/batched_vector.cu), plus masked column copies.  The GEMMs run on the
+tcgen05 tensor cores as int8 digit-plane products with int32 TMEM accumulators recombined in fp64
+(csrc/ozaki_gemm.cu; A is split into digit planes once per batch, the iterates once per product);
+small problems, and ``FASTA_B200_GEMM=dmma``, use the fp64 DMMA kernel (csrc/batched_gemm.cu) instead.
 Accelerated (FISTA) mode is not available in the batched loop yet.
 """
 
+import os
 from time import time
 
 import numpy as np
@@ -28,6 +32,10 @@ from . import _cabi, _device, linalg, losses, proximal, stopping
 from ._loop import Convergence, EPSILON
 
 __all__ = ["fasta_batched", "lasso_path"]
+
+# measurement hook (tools/bench_batched.py): when set to a list, every GEMM appends
+# (start_event, end_event, adjoint, active_columns) recorded on the launching stream
+GEMM_EVENTS = None
 
 
 class _Batch:
@@ -47,19 +55,65 @@ class _Batch:
         new = lambda r: t.empty((r, B), dtype=t.float64, device=dev)
         self.X0, self.X1, self.XH, self.DX, self.G0, self.G1, self.BEST = (new(self.N) for _ in range(7))
         self.Z, self.R = new(self.M), new(self.M)
-        self.sf = int(self.lib.fb200_gemm_splits(self.M, B, self.N))       # forward: (M x B) over K = N
-        self.sa = int(self.lib.fb200_gemm_splits(self.N, B, self.M))       # adjoint: (N x B) over K = M
-        self.ZP = t.empty((self.sf, self.M, B), dtype=t.float64, device=dev)
-        self.GP = t.empty((self.sa, self.N, B), dtype=t.float64, device=dev)
         self.ws = t.empty(int(self.lib.fb200_batched_workspace_bytes(self.M, self.N, B)), dtype=t.uint8, device=dev)
         self.out = t.zeros(5 * B, dtype=t.float64, device=dev)
         self.launches = 0
+        mode = os.environ.get("FASTA_B200_GEMM", "auto")
+        if mode not in ("auto", "dmma", "ozaki"):
+            raise ValueError("FASTA_B200_GEMM must be auto, dmma or ozaki")
+        self.ozaki = mode == "ozaki" or (mode == "auto" and self.M * self.N >= (1 << 24) and B >= 16)
+        if self.ozaki:
+            self._ozaki_setup()
+        else:
+            self.sf = int(self.lib.fb200_gemm_splits(self.M, B, self.N))       # forward: (M x B) over K = N
+            self.sa = int(self.lib.fb200_gemm_splits(self.N, B, self.M))       # adjoint: (N x B) over K = M
+            self.ZP = t.empty((self.sf, self.M, B), dtype=t.float64, device=dev)
+            self.GP = t.empty((self.sa, self.N, B), dtype=t.float64, device=dev)
         x0 = _device.to_device(X0, dev)
         if x0.ndim == 1:
             x0 = x0[:, None].expand(self.N, B)
         assert tuple(x0.shape) == (self.N, B)
         self.X1.copy_(x0)
         self.BEST.copy_(x0)
+
+    def _ozaki_setup(self):
+        """Digit planes of A for both products (once per batch) and the buffers of the per-product planes."""
+        t, lib, dev = self.t, self.lib, self.A.device
+        pad = lambda n, tile: int(lib.fb200_ozaki_pad(n, tile))
+        M, N, B = self.M, self.N, self.B
+        mp, np_, bp = pad(M, 128), pad(N, 128), pad(B, 64)
+        i8 = lambda *shape: t.empty(shape, dtype=t.int8, device=dev)
+        f8 = lambda n: t.empty(n, dtype=t.float64, device=dev)
+        self.oz_scratch = t.empty(max(B, N), dtype=t.int64, device=dev)
+        self.AF, self.af = i8(8, mp, np_), f8(mp)            # row-scaled planes of A     (forward: contraction over N)
+        self.AT, self.at = i8(8, np_, mp), f8(np_)           # column-scaled planes of A^T (adjoint: contraction over M)
+        _cabi.check(lib.fb200_ozaki_slice_rows(self.A.data_ptr(), self.lda, M, N, self.AF.data_ptr(), self.af.data_ptr(), self._st()),
+                    "fb200_ozaki_slice_rows")
+        _cabi.check(lib.fb200_ozaki_slice_cols(self.A.data_ptr(), self.lda, M, 0, N, 128, self.AT.data_ptr(), self.at.data_ptr(),
+                                               self.oz_scratch.data_ptr(), self._st()), "fb200_ozaki_slice_cols")
+        self.XS, self.xs = i8(8, bp, np_), f8(bp)            # planes of the iterate X (N x B), transposed
+        self.RS, self.rs = i8(8, bp, mp), f8(bp)             # planes of the residual R (M x B), transposed
+        widths = range(64, bp + 1, 64)
+        self.sf = max(int(lib.fb200_ozaki_splits(M, w, N)) for w in widths)
+        self.sa = max(int(lib.fb200_ozaki_splits(N, w, M)) for w in widths)
+        self.ZP = t.empty((self.sf, M, B), dtype=t.float64, device=dev)
+        self.GP = t.empty((self.sa, N, B), dtype=t.float64, device=dev)
+        self.launches += 3
+
+    def _gemm_ozaki(self, adjoint, src, part, rows, K, act):
+        lib, t = self.lib, self.t
+        cols = np.nonzero(act)[0]
+        n_act = len(cols)
+        cm = None if n_act == self.B else t.as_tensor(cols.astype(np.int32), device=src.device)
+        cmp_ = 0 if cm is None else cm.data_ptr()
+        LS, ls, RS, rs = (self.AT, self.at, self.RS, self.rs) if adjoint else (self.AF, self.af, self.XS, self.xs)
+        _cabi.check(lib.fb200_ozaki_slice_cols(src.data_ptr(), self.B, K, cmp_, n_act, 64, RS.data_ptr(), rs.data_ptr(),
+                                               self.oz_scratch.data_ptr(), self._st()), "fb200_ozaki_slice_cols")
+        s = int(lib.fb200_ozaki_splits(rows, n_act, K))
+        _cabi.check(lib.fb200_ozaki_gemm(LS.data_ptr(), ls.data_ptr(), rows, RS.data_ptr(), rs.data_ptr(), n_act, K, part.data_ptr(),
+                                         self.B, cmp_, s, rows * self.B, self._st()), "fb200_ozaki_gemm")
+        self.launches += 4
+        return s
 
     def _st(self):
         return _device.stream_ptr()
@@ -72,6 +126,21 @@ class _Batch:
         epilogue has to add (1 when the product was computed on a compacted column subset)."""
         lib, t = self.lib, self.t
         n_act = int(np.count_nonzero(act))
+        if n_act == 0:
+            return 1
+        if GEMM_EVENTS is not None:
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            ns = self._gemm_inner(adjoint, src, part, rows, K, splits, act, n_act)
+            e1.record()
+            GEMM_EVENTS.append((e0, e1, adjoint, n_act))
+            return ns
+        return self._gemm_inner(adjoint, src, part, rows, K, splits, act, n_act)
+
+    def _gemm_inner(self, adjoint, src, part, rows, K, splits, act, n_act):
+        lib, t = self.lib, self.t
+        if self.ozaki:
+            return self._gemm_ozaki(adjoint, src, part, rows, K, act)
         if n_act > 0.75 * self.B or self.B <= 8:
             _cabi.check(lib.fb200_gemm_f64(adjoint, self.A.data_ptr(), self.lda, src.data_ptr(), self.B, part.data_ptr(),
                                            self.B, rows, self.B, K, splits, rows * self.B, self._st()), "fb200_gemm_f64")
@@ -301,7 +370,8 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
         c = Convergence(resid_h[j], nresid_h[j], tau_h[j], int(total_bt[j]), tj, n, sol,
                         obj_h[j] if evaluate_objective else None, None, None)
         results.append(c)
-    results_meta = dict(kernel_launches=st.launches, gemm_splits=(st.sf, st.sa), iterations_lockstep=i)
+    results_meta = dict(kernel_launches=st.launches, gemm_splits=(st.sf, st.sa), iterations_lockstep=i,
+                        gemm="tcgen05-i8-digit-planes" if st.ozaki else "dmma-f64")
     for c in results:
         c.batch = results_meta
     return results

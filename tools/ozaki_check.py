@@ -136,3 +136,13 @@ if __name__ == "__main__":
     if what in ("big", "all"):
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         big()
+    if what == "prof":          # one forward + one adjoint product at config 5 size (for ncu)
+        M, N, B = 20000, 50000, 256
+        A = torch.randn(M, N, dtype=torch.float64, device=dev)
+        X = torch.randn(N, B, dtype=torch.float64, device=dev)
+        AF, af = slice_rows(A)
+        XS, xs = slice_cols(X, 64)
+        for _ in range(2):
+            Z = gemm(AF, af, M, XS, xs, B, N)
+        torch.cuda.synchronize()
+        print("ok", float(Z.norm()))
