@@ -52,16 +52,30 @@ __device__ __forceinline__ void bv_store(double (&s)[K], double* part, int B, in
     }
 }
 
-// out[k * B + col] = sum over blocks (in order) of part[(b * K + k) * B + col]   for active columns
-__global__ void bv_finalize_kernel(const double* __restrict__ part, int nblocks, int K, int B, const int* __restrict__ act,
-                                   double* __restrict__ out) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= K * B) return;
-    const int k = idx / B, col = idx - k * B;
-    if (act && !act[col]) return;
+// out[k * B + col] = sum over blocks of part[(b * K + k) * B + col] for active columns, in a fixed order:
+// 8 row lanes per (k, col) each add the blocks b = lane, lane + 8, ... in order, then the 8 lane sums are
+// added in lane order (block = 32 (k,col) pairs x 8 lanes; consecutive threads read consecutive columns)
+constexpr int BV_FIN_LANES = 8;
+__global__ void __launch_bounds__(256)
+bv_finalize_kernel(const double* __restrict__ part, int nblocks, int K, int B, const int* __restrict__ act,
+                   double* __restrict__ out) {
+    __shared__ double sm[BV_FIN_LANES][32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int idx = blockIdx.x * 32 + x;
+    const bool live = idx < K * B && (!act || act[idx % B]);
     double t = 0.0;
-    for (int b = 0; b < nblocks; ++b) t += part[(size_t(b) * K + k) * B + col];
-    out[idx] = t;
+    if (live) {
+        const int k = idx / B, col = idx - k * B;
+        for (int b = y; b < nblocks; b += BV_FIN_LANES) t += part[(size_t(b) * K + k) * B + col];
+    }
+    sm[y][x] = t;
+    __syncthreads();
+    if (y == 0 && live) {
+        double r = sm[0][x];
+#pragma unroll
+        for (int l = 1; l < BV_FIN_LANES; ++l) r += sm[l][x];
+        out[idx] = r;
+    }
 }
 
 // ---- forward step + prox + reductions, per column (reference __init__.py:181-186,200,272-274,285) ----
@@ -205,7 +219,7 @@ extern "C" int fb200_batched_fbs_step(const double* x0, const double* g0, const 
         default: set_error("batched_fbs_step: unsupported prox tag %d", prox); return 1;
     }
     if (check_launch("bv_fbs_step")) return 1;
-    bv_finalize_kernel<<<int((4 * B + 255) / 256), 256, 0, st>>>(part, l.nblocks, 4, int(B), act, out);
+    bv_finalize_kernel<<<int((4 * B + 31) / 32), 256, 0, st>>>(part, l.nblocks, 4, int(B), act, out);
     return check_launch("bv_finalize");
 }
 
@@ -223,7 +237,7 @@ extern "C" int fb200_batched_loss(int loss, const double* zsrc, int nsplit, int6
         default: set_error("batched_loss: unsupported loss tag %d", loss); return 1;
     }
     if (check_launch("bv_loss")) return 1;
-    bv_finalize_kernel<<<int((B + 255) / 256), 256, 0, st>>>(part, l.nblocks, 1, int(B), act, out);
+    bv_finalize_kernel<<<int((B + 31) / 32), 256, 0, st>>>(part, l.nblocks, 1, int(B), act, out);
     return check_launch("bv_finalize");
 }
 
@@ -237,7 +251,7 @@ extern "C" int fb200_batched_bb(const double* gsrc, int nsplit, int64_t split_st
     if (nsplit < 1) nsplit = 1;
     bv_bb_kernel<<<l.grid, BV_THREADS, 0, st>>>(gsrc, nsplit, split_stride, x0, xhat, dx, tau, act, bb, n, int(B), g1, part);
     if (check_launch("bv_bb")) return 1;
-    bv_finalize_kernel<<<int((3 * B + 255) / 256), 256, 0, st>>>(part, l.nblocks, 3, int(B), act, out);
+    bv_finalize_kernel<<<int((3 * B + 31) / 32), 256, 0, st>>>(part, l.nblocks, 3, int(B), act, out);
     return check_launch("bv_finalize");
 }
 

@@ -288,6 +288,141 @@ tv_grad_bb_fused_kernel(const double* __restrict__ R, int64_t n0, int64_t n1, do
     grid_sum<3>(s, red, counter, out);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Whole TV iteration in ONE pass (non-accelerated modes): forward step, ball projection, divergence,
+// loss, AND the speculative gradient with the Barzilai-Borwein sums,
+//     xhat = x0 - tau*g0 ; x1 = xhat / max(|xhat|_2, 1) ; r = div(x1) - b ; g1 = grad(r) ; 7 sums
+// (reference __init__.py:181-188,248-260,272-274 with tv_denoising.py:26-63,85-96).  Only x0, g0, b are
+// read and x1, g1 written: 9U bytes per trial, U = n0*n1*8 (the two-kernel pair above moves 17U).  If the
+// line search rejects the trial the kernel simply runs again with the shorter step (as the dense sweep).
+//
+// Shared-memory stencil with a two-deep halo: for a TH x TW tile the prox point is needed on
+// (TH+2) x (TW+2) pixels and the residual on (TH+1) x (TW+1); both live in shared memory.  The tile's own
+// x0 / g0 are read again for the BB sums (L1/L2 hits) rather than held in registers, which keeps the
+// kernel at 80 registers = 3 blocks (24 warps) per SM: the fp64 sqrt/divide chains of one block then
+// overlap the loads of the others.  Every expression is the one of the unfused kernels
+// (compiled -fmad=false), so x1 and g1 are bit-identical to them; only the order of the sums differs.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TVI_TH = 32, TVI_TW = 64, TVI_THREADS = 256;
+constexpr int TVI_BLOCKS_PER_SM = 3;
+constexpr int TVI_PX = TVI_TH * TVI_TW / TVI_THREADS;               // 8 pixels per thread
+constexpr int TVI_YW = TVI_TW + 2, TVI_YH = TVI_TH + 2;             // prox points: rows/cols -1 .. T
+constexpr int TVI_RW = TVI_TW + 1, TVI_RH = TVI_TH + 1;             // residuals:   rows/cols -1 .. T-1
+constexpr int TVI_SMEM = TVI_YH * TVI_YW * int(sizeof(double2)) + TVI_RH * TVI_RW * int(sizeof(double));
+
+// periodic index: one conditional add/subtract in the common case (|i| within one period), the
+// modulo only for images smaller than the tile halo
+__device__ __forceinline__ int tv_wrap(int i, int n) {
+    if (i < 0) i += n;
+    else if (i >= n) i -= n;
+    if (i < 0 || i >= n) { i %= n; if (i < 0) i += n; }
+    return i;
+}
+
+template <int LOSS>
+__global__ void __launch_bounds__(TVI_THREADS, TVI_BLOCKS_PER_SM)
+tv_iter_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, double tau, int n0, int n1,
+               const double* __restrict__ b, double2* __restrict__ x1, double2* __restrict__ g1, int tiles_x, int ntiles,
+               double* scal, double* red, unsigned* counter) {
+    extern __shared__ __align__(16) unsigned char tvi_raw[];
+    double2* ys = reinterpret_cast<double2*>(tvi_raw);
+    double*  rs = reinterpret_cast<double*>(tvi_raw + TVI_YH * TVI_YW * sizeof(double2));
+    // <dx,g0>, <dx,dx>, |x1-xhat|^2, f, <dx,dg>, <dg,dg>, <g1,g1>
+    double s[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const int tj = threadIdx.x & (TVI_TW - 1), tr = threadIdx.x / TVI_TW;         // own column, first own row
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int i0 = (tile / tiles_x) * TVI_TH, j0 = (tile % tiles_x) * TVI_TW;
+        const int j = j0 + tj;
+        const int jw = tv_wrap(j, n1);
+        __syncthreads();                     // the previous tile's reads of ys / rs are done
+        // phase 1a: prox point of the tile's own pixels (x1 is final here), step sums
+#pragma unroll
+        for (int kk = 0; kk < TVI_PX; kk += 4) {
+            double2 a[4], gr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t o = int64_t(tv_wrap(i0 + tr + (kk + u) * (TVI_THREADS / TVI_TW), n0)) * n1 + jw;
+                a[u]  = x0[o];
+                gr[u] = g0[o];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ti = tr + (kk + u) * (TVI_THREADS / TVI_TW);
+                const int i = i0 + ti;
+                double2 h;
+                const double2 y = tv_prox_point(a[u], gr[u], tau, h);
+                ys[(ti + 1) * TVI_YW + tj + 1] = y;
+                if (i < n0 && j < n1) {
+                    x1[int64_t(i) * n1 + j] = y;
+                    const double dxx = y.x - a[u].x, dxy = y.y - a[u].y, ex = y.x - h.x, ey = y.y - h.y;
+                    s[0] += dxx * gr[u].x; s[0] += dxy * gr[u].y;
+                    s[1] += dxx * dxx;     s[1] += dxy * dxy;
+                    s[2] += ex * ex;       s[2] += ey * ey;
+                }
+            }
+        }
+        // phase 1b: prox point on the halo ring (rows -1 and TH, columns -1 and TW)
+        for (int e = threadIdx.x; e < 2 * TVI_YW + 2 * TVI_TH; e += TVI_THREADS) {
+            int ti, tc;
+            if (e < TVI_YW) { ti = -1; tc = e - 1; }
+            else if (e < 2 * TVI_YW) { ti = TVI_TH; tc = e - TVI_YW - 1; }
+            else { const int q = e - 2 * TVI_YW; ti = q >> 1; tc = (q & 1) ? TVI_TW : -1; }
+            const int64_t o = int64_t(tv_wrap(i0 + ti, n0)) * n1 + tv_wrap(j0 + tc, n1);
+            double2 h;
+            ys[(ti + 1) * TVI_YW + tc + 1] = tv_prox_point(x0[o], g0[o], tau, h);
+        }
+        __syncthreads();
+        // phase 2: residual r = div(x1) - b on rows/cols -1 .. T-1; f over the tile's own pixels
+        for (int e = threadIdx.x; e < TVI_RH * TVI_RW; e += TVI_THREADS) {
+            const int ri = e / TVI_RW, rj = e - ri * TVI_RW;          // ti = ri - 1, tj = rj - 1
+            const double2 c  = ys[ri * TVI_YW + rj];
+            const double2 dn = ys[(ri + 1) * TVI_YW + rj];
+            const double2 rt = ys[ri * TVI_YW + rj + 1];
+            const double zi = (dn.x - c.x) + (rt.y - c.y);
+            const int i = i0 + ri - 1, jj = j0 + rj - 1;
+            double rv, fv;
+            loss_elem<LOSS>(zi, b[int64_t(tv_wrap(i, n0)) * n1 + tv_wrap(jj, n1)], rv, fv);
+            rs[e] = rv;
+            if (ri >= 1 && rj >= 1 && i < n0 && jj < n1) s[3] += fv;
+        }
+        __syncthreads();
+        // phase 3: g1 = grad(r) on the tile's own pixels, BB sums
+#pragma unroll
+        for (int kk = 0; kk < TVI_PX; kk += 4) {
+            double2 a[4], gr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t o = int64_t(tv_wrap(i0 + tr + (kk + u) * (TVI_THREADS / TVI_TW), n0)) * n1 + jw;
+                a[u]  = x0[o];
+                gr[u] = g0[o];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ti = tr + (kk + u) * (TVI_THREADS / TVI_TW);
+                const int i = i0 + ti;
+                if (i < n0 && j < n1) {
+                    const double c = rs[(ti + 1) * TVI_RW + tj + 1];
+                    double2 gi;
+                    gi.x = rs[ti * TVI_RW + tj + 1] - c;
+                    gi.y = rs[(ti + 1) * TVI_RW + tj] - c;
+                    g1[int64_t(i) * n1 + j] = gi;
+                    const double2 y = ys[(ti + 1) * TVI_YW + tj + 1];
+                    const double hx = a[u].x - tau * gr[u].x, hy = a[u].y - tau * gr[u].y;
+                    const double dxx = y.x - a[u].x, dxy = y.y - a[u].y;
+                    const double dg0 = gi.x + (hx - a[u].x) / tau;
+                    const double dg1 = gi.y + (hy - a[u].y) / tau;
+                    s[4] += dxx * dg0;   s[4] += dxy * dg1;
+                    s[5] += dg0 * dg0;   s[5] += dg1 * dg1;
+                    s[6] += gi.x * gi.x; s[6] += gi.y * gi.y;
+                }
+            }
+        }
+    }
+    double* const out[7] = {scal + FB200_S_DX_G0, scal + FB200_S_DX_SQ, scal + FB200_S_XMXH_SQ, scal + FB200_S_F,
+                            scal + FB200_S_DX_DG, scal + FB200_S_DG_SQ, scal + FB200_S_G1_SQ};
+    grid_sum<7>(s, red, counter, out);
+}
+
 static int tv_grid(int64_t n0, int64_t n1, dim3* grid, int* strip) {
     const int64_t gx = (n1 + TV_THREADS - 1) / TV_THREADS;
     int64_t st = TV_STRIP;
@@ -384,4 +519,34 @@ extern "C" int fb200_tv_grad_bb_fused(const double* R, int64_t n0, int64_t n1, d
     else
         tv_grad_bb_fused_kernel<1><<<grid, TV_THREADS, 0, st>>>(R, n0, n1, (double2*)g, (const double2*)x0, (const double2*)g0, (const double2*)x1, tau, strip, scal, w.red, w.counter);
     return check_launch("tv_grad_bb_fused");
+}
+
+extern "C" int fb200_tv_iter_fused(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, int loss,
+                                   const double* b, double* x1, double* g1, double* scal, void* ws, void* stream) {
+    Workspace w(ws);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n0 < 1 || n1 < 1 || n0 > (1 << 30) || n1 > (1 << 30)) { set_error("tv_iter_fused: bad shape"); return 1; }
+    const int64_t tx = (n1 + TVI_TW - 1) / TVI_TW, ty = (n0 + TVI_TH - 1) / TVI_TH;
+    if (tx * ty > (int64_t(1) << 30)) { set_error("tv_iter_fused: image too large"); return 1; }
+    const int ntiles = int(tx * ty);
+    int grid = sm_count() * TVI_BLOCKS_PER_SM;
+    if (grid > ntiles) grid = ntiles;
+    if (grid > MAX_RED_BLOCKS) grid = MAX_RED_BLOCKS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e1 = cudaFuncSetAttribute(tv_iter_kernel<FB200_LOSS_LEAST_SQUARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVI_SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(tv_iter_kernel<FB200_LOSS_LOGISTIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVI_SMEM);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("tv_iter_fused: smem attribute failed"); cudaGetLastError(); return 1; }
+        attr_done = true;
+    }
+    switch (loss) {
+        case FB200_LOSS_LEAST_SQUARES:
+            tv_iter_kernel<FB200_LOSS_LEAST_SQUARES><<<grid, TVI_THREADS, TVI_SMEM, st>>>((const double2*)x0, (const double2*)g0, tau, int(n0), int(n1), b, (double2*)x1, (double2*)g1, int(tx), ntiles, scal, w.red, w.counter);
+            break;
+        case FB200_LOSS_LOGISTIC:
+            tv_iter_kernel<FB200_LOSS_LOGISTIC><<<grid, TVI_THREADS, TVI_SMEM, st>>>((const double2*)x0, (const double2*)g0, tau, int(n0), int(n1), b, (double2*)x1, (double2*)g1, int(tx), ntiles, scal, w.red, w.counter);
+            break;
+        default: set_error("tv_iter_fused: unsupported loss tag %d", loss); return 1;
+    }
+    return check_launch("tv_iter_fused");
 }

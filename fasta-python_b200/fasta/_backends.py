@@ -113,6 +113,15 @@ class TVDriver:
                                                     ws.buf.data_ptr(), _device.stream_ptr()), "fb200_tv_grad_bb_fused")
         self.launches += 1
 
+    # the whole iteration in one kernel: step + projection + div + loss + speculative grad + BB sums (9U bytes)
+    iter_fused_ok = os.environ.get("FASTA_B200_TV_ITER", "1") != "0"
+
+    def iterate_fused(self, x0, g0, tau, loss_tag, b, x1, g1, ws):
+        _cabi.check(self.lib.fb200_tv_iter_fused(x0.data_ptr(), g0.data_ptr(), float(tau), self.n0, self.n1, loss_tag,
+                                                 b.data_ptr(), x1.data_ptr(), g1.data_ptr(), ws.scal.data_ptr(),
+                                                 ws.buf.data_ptr(), _device.stream_ptr()), "fb200_tv_iter_fused")
+        self.launches += 1
+
     def sync_point(self, v1, v2):
         pass
 
@@ -307,6 +316,13 @@ class FusedBackend:
         xa_prev = self.XA[self.ap] if self.accelerate else None
         p0, p1 = self.pen.params(tau)
         st = self._st()
+        if self.use_tv_fused and self.drv.iter_fused_ok:
+            # one kernel per trial; the gradient of an accepted trial is already in G[gc] (speculative, like the sweep)
+            self.drv.iterate_fused(x0, g0, tau, self.loss.tag, self.loss.b, x1, self.G[self.gc], self.ws)
+            s = self.ws.fetch()
+            self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
+            return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
+                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0))
         if self.use_tv_fused:
             self.drv.step_forward(x0, g0, tau, self.loss.tag, self.loss.b, x1, self.R, self.ws)
             s = self.ws.fetch()
@@ -349,8 +365,8 @@ class FusedBackend:
         return Scalars(f=self.loss.finalize(s[S.S_F]), xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]))
 
     def gradient(self, tau, adaptive):
-        if self.use_sweep and self._spec is not None:
-            spec, self._spec = self._spec, None      # produced by the accepted trial's sweep: no device work
+        if self._spec is not None:
+            spec, self._spec = self._spec, None      # produced by the accepted trial's single pass: no device work
             return spec
         if self.use_tv_fused:
             self.drv.adjoint_fused(self.R, self.G[self.gc], 2 if adaptive else 1, self.X[self.ip], self.G[self.gp],

@@ -38,6 +38,15 @@ __all__ = ["fasta_batched", "lasso_path"]
 GEMM_EVENTS = None
 
 
+# reference stopping.py:15,27,39,51 on whole columns of np.float64 (nan comparisons are False, as for scalars)
+_VECTOR_RULES = {
+    stopping.residual: lambda r, nr, mr, tol: r < tol,
+    stopping.norm_residual: lambda r, nr, mr, tol: nr < tol,
+    stopping.ratio_residual: lambda r, nr, mr, tol: r / mr < tol,
+    stopping.hybrid_residual: lambda r, nr, mr, tol: (r / mr < tol) | (nr < tol),
+}
+
+
 class _Batch:
     """Device state of a batch (all matrices row-major, batch index fastest)."""
 
@@ -348,12 +357,15 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
         st.select(st.BEST, st.X1, better)
         best_q[better] = quality[better]
 
-        for j in np.nonzero(act)[0]:
-            with np.errstate(all="ignore"):
-                stop = stop_rule(i, resid_h[j, i], nresid_h[j, i], max_resid[j], tolerance)
-            iters[j] = i + 1
-            if stop:
-                done[j] = True
+        iters[act] = i + 1
+        with np.errstate(all="ignore"):
+            if stop_rule in _VECTOR_RULES:       # the built-in rules, evaluated for all columns at once (same truth tables)
+                stop = _VECTOR_RULES[stop_rule](resid_h[:, i], nresid_h[:, i], max_resid, tolerance)
+                done |= act & stop
+            else:
+                for j in np.nonzero(act)[0]:
+                    if stop_rule(i, resid_h[j, i], nresid_h[j, i], max_resid[j], tolerance):
+                        done[j] = True
         if verbose:
             print(f"[{i:<6}]\tactive {int(act.sum()):4d}\tmax residual {np.max(resid[act]):e}")
         i += 1

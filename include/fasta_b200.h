@@ -217,6 +217,12 @@ int fb200_tv_grad_bb_fused(const double* R, int64_t n0, int64_t n1, double* g, i
                            const double* g0, const double* x1, double tau, double* scal, void* ws,
                            void* stream);
 
+/* whole TV iteration in one pass: step_div_loss plus the speculative g1 = grad(r) and the BB sums
+ * scal[S_DX_G0, S_DX_SQ, S_XMXH_SQ, S_F, S_DX_DG, S_DG_SQ, S_G1_SQ]; reads x0, g0, b and writes x1, g1 only
+ * (9U bytes, U = n0*n1*8; reference __init__.py:181-188,248-260 with tv_denoising.py:26-63,85-96)        */
+int fb200_tv_iter_fused(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, int loss,
+                        const double* b, double* x1, double* g1, double* scal, void* ws, void* stream);
+
 /* ---- small reductions used by the prologue and the generic (untagged-callable) path ---------
  * out (device) receives: dot = <a,b>; diff_nrm2sq = |a-b|^2; asum = sum |a|                   */
 int fb200_dot(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream);

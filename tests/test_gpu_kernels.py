@@ -154,6 +154,40 @@ def test_tv_stencils(n0, n1):
     assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), 1.0)                  # adjointness
 
 
+@pytest.mark.parametrize("n0,n1", [(64, 64), (128, 96), (33, 130), (1, 7), (5, 1), (2, 2), (300, 257), (70, 64)])
+def test_tv_whole_iteration_kernel(n0, n1):
+    """fb200_tv_iter_fused: x1 and g1 bit-identical to the numpy expressions of the reference lines
+    (tv_denoising.py:26-63,85-96; __init__.py:181-188,248-260), the seven sums to reduction rounding."""
+    from fasta import _cabi, _device
+    from oracle import problems
+    torch = _t()
+    lib = _cabi.load()
+    rng = np.random.RandomState(3 * n0 + n1)
+    x0, g0, b = rng.randn(n0, n1, 2), rng.randn(n0, n1, 2), rng.randn(n0, n1)
+    tau = 0.3
+    d = {k: torch.from_numpy(v).cuda() for k, v in dict(x0=x0, g0=g0, b=b).items()}
+    x1, g1 = (torch.full((n0, n1, 2), np.nan, dtype=torch.float64, device="cuda") for _ in range(2))
+    ws = _device.Workspace(1, 1)
+    _cabi.check(lib.fb200_tv_iter_fused(d["x0"].data_ptr(), d["g0"].data_ptr(), tau, n0, n1, _cabi.LOSS_LEAST_SQUARES,
+                                        d["b"].data_ptr(), x1.data_ptr(), g1.data_ptr(), ws.scal.data_ptr(),
+                                        ws.buf.data_ptr(), _device.stream_ptr()))
+    s = ws.fetch().copy()
+    h = x0 - tau * g0
+    nrm = np.maximum(np.sqrt(h[..., 0] * h[..., 0] + h[..., 1] * h[..., 1]), 1.0)
+    y = h / nrm[..., None]
+    r = problems.tv_div(y) - b
+    g = problems.tv_grad(r)
+    assert np.array_equal(x1.cpu().numpy(), y)
+    assert np.array_equal(g1.cpu().numpy(), g)
+    dx = y - x0
+    dg = g + (h - x0) / tau
+    dot = lambda u, v: float(np.sum(u * v))
+    for slot, want in ((_cabi.S_DX_G0, dot(dx, g0)), (_cabi.S_DX_SQ, dot(dx, dx)), (_cabi.S_XMXH_SQ, dot(y - h, y - h)),
+                       (_cabi.S_F, dot(r, r)), (_cabi.S_DX_DG, dot(dx, dg)), (_cabi.S_DG_SQ, dot(dg, dg)),
+                       (_cabi.S_G1_SQ, dot(g, g))):
+        assert abs(s[slot] - want) <= 1e-12 * max(abs(want), 1e-3), (n0, n1, slot, s[slot], want)
+
+
 def test_step_kernels_through_ctypes():
     """fbs_step / bb_reduce / accel_step scalars against numpy on ragged sizes."""
     import fasta

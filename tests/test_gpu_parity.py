@@ -63,6 +63,19 @@ def test_tv_unfused_kernels_match_golden(case, mode, monkeypatch):
     assert_trajectory(res, gold, label=f"tv-unfused/{case}/{mode}")
 
 
+@pytest.mark.parametrize("case,mode", [cm for cm in golden_cases(prefixes=("tv_",)) if cm[1] != "accelerated"])
+def test_tv_two_kernel_iteration_matches_golden(case, mode, monkeypatch):
+    """TV with the whole-iteration kernel disabled (step+div+loss and grad+BB as two fused kernels)."""
+    import fasta
+    monkeypatch.setattr(fasta._backends.TVDriver, "iter_fused_ok", False)
+    gold = load_golden(case, mode)
+    p = problems.build(case, int(gold["seed"]))
+    A, loss, pen = tagged(p)
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert res.tv_fused
+    assert_trajectory(res, gold, label=f"tv-two-kernel/{case}/{mode}")
+
+
 def test_tv_fused_is_default_for_non_accelerated():
     import fasta
     p = problems.build("tv_64", 0)
