@@ -22,8 +22,9 @@
 //   warp 0 (one lane)  TMA producer: per 128-byte K block, the 8 right-operand digit tiles (64 x 128 B,
 //                      double buffered) and the 8 left-operand digit tiles (128 x 128 B, through a ring),
 //                      SWIZZLE_128B, completion on mbarriers;
-//   warp 1 (one lane)  MMA issuer: for left digit s, tcgen05.mma against right digits t = 0..7-s (4 K
-//                      steps of 32 bytes each), tcgen05.commit releases the ring slot / the buffer;
+//   warp 1 (one lane)  MMA issuer: for left digit s and each of the 4 K steps (32 bytes), tcgen05.mma against
+//                      right digits t = 0..7-s with the A tile held in the A collector across them;
+//                      tcgen05.commit releases the ring slot / the buffer;
 //   warps 2..5         epilogue: tcgen05.ld of the 8 accumulators, Horner, scaling, fp64 stores.
 // Integer accumulation is exact as long as (d+1) * K_split * 64 * 64 < 2^31, i.e. K_split <= 65535; the
 // host picks the number of K splits accordingly (and to balance the 148 SMs).  Each split writes its own
@@ -57,15 +58,25 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// D[tmem] (+)= A[smem] . B[smem]^T, int8 x int8 -> int32, M = 128, N = 64, K = 32
+// D[tmem] (+)= A[smem] . B[smem]^T, int8 x int8 -> int32, M = 128, N = 64, K = 32.
+// COLL selects the A-operand collector use: consecutive UMMAs that share the A tile read it from shared
+// memory once (fill), reuse it from the collector buffer (use) and release it (lastuse); 0 = no reuse.
+enum { OZ_COLL_NONE = 0, OZ_COLL_FILL = 1, OZ_COLL_USE = 2, OZ_COLL_LAST = 3 };
+template <int COLL>
 __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+#define OZ_UMMA(QUAL)                                                                                          \
+    asm volatile(                                                                                              \
+        "{\n\t"                                                                                                \
+        ".reg .pred p;\n\t"                                                                                    \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                                            \
+        "tcgen05.mma.cta_group::1.kind::i8" QUAL " [%0], %1, %2, %3, p;\n\t"                                   \
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)                                 \
+        : "memory")
+    if (COLL == OZ_COLL_FILL) OZ_UMMA(".collector::a::fill");
+    else if (COLL == OZ_COLL_USE) OZ_UMMA(".collector::a::use");
+    else if (COLL == OZ_COLL_LAST) OZ_UMMA(".collector::a::lastuse");
+    else OZ_UMMA("");
+#undef OZ_UMMA
 }
 // mbarrier arrive once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -205,14 +216,20 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t alo = umma_desc_lo(smA + slot * OZ_A_TILE);
+                    // K step outermost: the OZ_S - s products of one K step share the A digit tile, which
+                    // then comes from shared memory once (A collector) instead of once per product
 #pragma unroll
-                    for (int t = 0; t < OZ_S - s; ++t) {
-                        const uint32_t blo = xlo + t * (OZ_X_TILE >> 4);
-                        const uint32_t dcol = tmem + uint32_t(s + t) * OZ_BN;
+                    for (int k = 0; k < OZ_BK / OZ_UK; ++k) {
+                        const uint64_t adesc = umma_desc(alo + k * (OZ_UK >> 4));
+                        const uint32_t acc = (kb > 0 || s > 0 || k > 0) ? 1u : 0u;
 #pragma unroll
-                        for (int k = 0; k < OZ_BK / OZ_UK; ++k) {
-                            const uint32_t acc = (kb > 0 || s > 0 || k > 0) ? 1u : 0u;
-                            umma_i8(dcol, umma_desc(alo + k * (OZ_UK >> 4)), umma_desc(blo + k * (OZ_UK >> 4)), OZ_IDESC, acc);
+                        for (int t = 0; t < OZ_S - s; ++t) {
+                            const uint64_t bdesc = umma_desc(xlo + t * (OZ_X_TILE >> 4) + k * (OZ_UK >> 4));
+                            const uint32_t dcol = tmem + uint32_t(s + t) * OZ_BN;
+                            if (OZ_S - s == 1) umma_i8<OZ_COLL_NONE>(dcol, adesc, bdesc, OZ_IDESC, acc);
+                            else if (t == 0) umma_i8<OZ_COLL_FILL>(dcol, adesc, bdesc, OZ_IDESC, acc);
+                            else if (t == OZ_S - s - 1) umma_i8<OZ_COLL_LAST>(dcol, adesc, bdesc, OZ_IDESC, acc);
+                            else umma_i8<OZ_COLL_USE>(dcol, adesc, bdesc, OZ_IDESC, acc);
                         }
                     }
                     umma_commit(&aempty[slot]);
