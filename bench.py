@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--workload", default="lasso_40000x100000", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--debug-phases", action="store_true", help="print host-side phase times of every timed solve to stderr")
     return ap.parse_args()
 
 
@@ -290,9 +291,30 @@ def main():
     _backends.DenseDriver.adjoint = timed(orig_adjoint, kernel_events)
     _backends.DenseDriver.sweep = timed(orig_sweep, sweep_events)
 
+    marks = []
+    if args.debug_phases:
+        def phase(cls, name):
+            orig = getattr(cls, name)
+
+            def f(self, *a, **k):
+                t0 = time.perf_counter()
+                out = orig(self, *a, **k)
+                marks.append((name, time.perf_counter() - t0))
+                return out
+            setattr(cls, name, f)
+        for name in ("__init__", "load", "lipschitz", "start", "solution", "close"):
+            phase(_backends.FusedBackend, name)
+
     def solve(xstart):
         np.random.seed(0)          # identical tau0 probes in every step and on every rank
-        return fasta.fasta(op, loss.f, loss.gradf, pen.g, pen.prox, xstart, **SOLVER_OPTS)
+        t0 = time.perf_counter()
+        res = fasta.fasta(op, loss.f, loss.gradf, pen.g, pen.prox, xstart, **SOLVER_OPTS)
+        if args.debug_phases and rank == 0:
+            loop = res.times[res.iteration_count] - res.times[0]
+            print(f"[phases] call {1e3 * (time.perf_counter() - t0):.1f} ms, loop {1e3 * loop:.1f} ms :: " +
+                  ", ".join(f"{n} {1e3 * t:.2f}" for n, t in marks), file=sys.stderr, flush=True)
+            marks.clear()
+        return res
 
     def barrier():
         if world > 1:
@@ -305,7 +327,11 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record()
-        outs = [fn() for _ in range(steps)]
+        outs = []
+        for _ in range(steps):
+            if outs:
+                outs[-1].solution = None     # drop the previous solution buffer, as a caller's loop would: the caching
+            outs.append(fn())                # allocator then stays in steady state (no cudaMalloc inside the timed region)
         e1.record()
         barrier()
         wall = time.time() - t0

@@ -384,7 +384,9 @@ class FusedBackend:
         return _device.like_input(self.X[self.ic].view(self.shape), self.x0_in)
 
     def solution(self):
-        return _device.like_input(self.BEST.clone().view(self.shape), self.x0_in)
+        # BEST belongs to this backend alone and the backend ends with the solve: hand the buffer over
+        # instead of cloning it (no allocation at the end of a solve)
+        return _device.like_input(self.BEST.view(self.shape), self.x0_in)
 
 
 # =================================================================================================
