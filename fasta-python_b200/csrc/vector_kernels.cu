@@ -356,6 +356,35 @@ reduce_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_
     grid_sum<1>(s, red, counter, o);
 }
 
+// ---- row-wise prox operators of the matrix-iterate examples ------------------------------------------
+// X is rows x cols row-major; one warp per row: nrm = sqrt(sum_j X[i][j]^2) (lane-strided partial sums,
+// butterfly combine), then
+//   mode 0 (mmv.py:53-61, prox of t*sum_i |X_i|_2):  X_i * (shrink(nrm, p) / (nrm + (nrm == 0)))
+//   mode 1 (max_norm.py:53-59, rows onto the p-ball): p * X_i / (max(nrm, p) + (nrm == 0))
+// norms (optional) receives nrm per row (for g = mu * sum_i |X_i|_2).
+__global__ void __launch_bounds__(256)
+prox_rows_kernel(const double* __restrict__ x, int64_t rows, int cols, int mode, double p, double* __restrict__ out,
+                 double* __restrict__ norms) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const double* xr = x + row * cols;
+    double s = 0.0;
+    for (int j = lane; j < cols; j += 32) s += xr[j] * xr[j];
+    s = warp_sum(s);
+    const double nrm = sqrt(s);
+    if (norms && lane == 0) norms[row] = nrm;
+    if (!out) return;
+    const double zero = (nrm == 0.0) ? 1.0 : 0.0;
+    if (mode == 0) {
+        const double scale = (sign_np(nrm) * fmax(fabs(nrm) - p, 0.0)) / (nrm + zero);
+        for (int j = lane; j < cols; j += 32) out[row * cols + j] = xr[j] * scale;
+    } else {
+        const double scale = fmax(nrm, p) + zero;
+        for (int j = lane; j < cols; j += 32) out[row * cols + j] = (p * xr[j]) / scale;
+    }
+}
+
 }  // namespace fb200
 
 using namespace fb200;
@@ -405,6 +434,15 @@ extern "C" int fb200_step_reduce(const double* x0, const double* x1, const doubl
     else
         step_reduce_kernel<false><<<vec_grid(n), VEC_THREADS, 0, st>>>(x0, x1, xhat, g0, nullptr, n, dx, scal, w.red, w.counter);
     return check_launch("step_reduce");
+}
+
+extern "C" int fb200_prox_rows(const double* x, int64_t rows, int64_t cols, int mode, double p, double* out, double* norms,
+                               void* stream) {
+    if (rows < 1 || cols < 1 || cols > INT32_MAX || (mode != 0 && mode != 1)) { set_error("prox_rows: bad arguments"); return 1; }
+    const int64_t grid = (rows + 7) / 8;
+    if (grid > INT32_MAX) { set_error("prox_rows: too many rows"); return 1; }
+    prox_rows_kernel<<<unsigned(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, int(cols), mode, p, out, norms);
+    return check_launch("prox_rows");
 }
 
 extern "C" int fb200_prox_apply(const double* x, int prox, double p0, double p1, int64_t n, double* out,

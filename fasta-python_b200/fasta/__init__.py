@@ -103,6 +103,8 @@ def _legacy_operator(A, At, x0):
     if isinstance(A, linalg.LinearMap):
         return A
     if _device.is_array(A):                                   # sparse_least_squares.py:46,76
+        if len(x0.shape) == 2:                                # matrix unknowns: A @ X (mmv.py:65)
+            return linalg.LinearMap.from_matrix(A).with_columns(int(x0.shape[1]))
         return linalg.LinearMap.from_matrix(A)
     if callable(A):
         if A is tv.div and At is tv.grad and len(x0.shape) == 3:
@@ -115,7 +117,7 @@ def _driver_for(A):
     from . import _backends
     if hasattr(A, "_fb200_driver"):
         return A._fb200_driver()
-    if getattr(A, "_fb200_dense", False) and not A.transposed:
+    if getattr(A, "_fb200_dense", False) and not A.transposed and A.cols is None:
         return _backends.DenseDriver(A.matrix)
     if getattr(A, "_fb200_tv", False):
         return _backends.TVDriver(A.n0, A.n1)
@@ -131,8 +133,8 @@ def _make_backend(A, f, gradf, g, proxg, x0, accelerate, evaluate_objective):
         pen = proximal._Penalty()
     else:
         pen = _owner(proxg, proximal._Penalty)
-        if pen is not None and _owner(g, proximal._Penalty) is not pen:
-            pen = None
+        if pen is not None and (_owner(g, proximal._Penalty) is not pen or pen.tag is None):
+            pen = None                                         # untagged / row-wise penalties: generic back-end
     driver = _driver_for(A) if (loss is not None and pen is not None) else None
     if driver is not None:
         return _backends.FusedBackend(driver, loss, pen, x0, accelerate)

@@ -117,7 +117,7 @@ class DenseMap(LinearMap):
     the one row-major copy.  ``_fb200_dense`` is the tag the solver looks for.
     """
 
-    def __init__(self, A, _transposed=False, _dev=None):
+    def __init__(self, A, _transposed=False, _dev=None, columns=None):
         if _dev is None:
             t = _device.torch()
             if isinstance(A, t.Tensor) and A.is_cuda and A.dtype == t.float64 and A.stride(1) == 1 and A.stride(0) >= A.shape[1]:
@@ -128,14 +128,23 @@ class DenseMap(LinearMap):
         self.transposed = bool(_transposed)
         M, N = self.matrix.shape
         self.M, self.N, self.lda = int(M), int(N), int(self.matrix.stride(0))
-        V, W = ((N,), (M,)) if not self.transposed else ((M,), (N,))
+        # columns = L: the map acts on matrix iterates, X (N x L) -> A @ X (M x L), as the reference's
+        # `A @ x` does when the examples pass 2-D unknowns (mmv.py:65); the contractions are then GEMMs
+        self.cols = None if columns is None else int(columns)
+        tail = () if self.cols is None else (self.cols,)
+        V, W = ((N,) + tail, (M,) + tail) if not self.transposed else ((M,) + tail, (N,) + tail)
+        self._padded = None
         super().__init__(self._apply, self._apply_adjoint, V, W)
 
     _fb200_dense = True
 
     @property
     def H(self) -> "DenseMap":
-        return DenseMap(None, _transposed=not self.transposed, _dev=self.matrix)
+        return DenseMap(None, _transposed=not self.transposed, _dev=self.matrix, columns=self.cols)
+
+    def with_columns(self, L) -> "DenseMap":
+        """The same matrix acting on N x L matrix iterates."""
+        return DenseMap(None, _transposed=self.transposed, _dev=self.matrix, columns=L)
 
     @property
     def uses_tma(self) -> bool:
@@ -155,7 +164,38 @@ class DenseMap(LinearMap):
                                        g_dev.data_ptr(), 0, 0, 0, 0, 0.0, ws.scal.data_ptr(), ws.buf.data_ptr(),
                                        ws.nbytes, _device.stream_ptr()), "fb200_gemvT_bb")
 
+    def _gemm(self, v, transposed):
+        """A @ V or A.T @ V for a matrix V with the fp64 DMMA kernel (csrc/batched_gemm.cu); shapes the kernel
+        cannot take directly (odd N, L or leading dimension) go through zero-padded copies."""
+        t = _device.torch()
+        lib = _cabi.load()
+        dev = self.matrix.device
+        V = _device.to_device(v, dev)
+        L = self.cols
+        Np, Lp = self.N + (self.N & 1), L + (L & 1)
+        A, lda = self.matrix, self.lda
+        if Np != self.N or (lda & 1) or (A.data_ptr() & 15):
+            if self._padded is None:
+                self._padded = t.zeros((self.M, Np), dtype=t.float64, device=dev)
+                self._padded[:, :self.N].copy_(A)
+            A, lda = self._padded, Np
+        rows_in = self.M if transposed else Np
+        if Lp != L or (not transposed and Np != self.N) or not V.is_contiguous() or (V.data_ptr() & 15):
+            Vp = t.zeros((rows_in, Lp), dtype=t.float64, device=dev)
+            Vp[:V.shape[0], :L].copy_(V)
+        else:
+            Vp = V
+        rows_out = Np if transposed else self.M
+        out = t.empty((rows_out, Lp), dtype=t.float64, device=dev)
+        K = self.M if transposed else Np
+        _cabi.check(lib.fb200_gemm_f64(1 if transposed else 0, A.data_ptr(), lda, Vp.data_ptr(), Lp, out.data_ptr(), Lp,
+                                       rows_out, Lp, K, 1, rows_out * Lp, _device.stream_ptr()), "fb200_gemm_f64")
+        res = out[:(self.N if transposed else self.M), :L]
+        return _device.like_input(res if res.is_contiguous() else res.contiguous(), v)
+
     def _run(self, v, transposed):
+        if self.cols is not None:
+            return self._gemm(v, transposed)
         t = _device.torch()
         ws = _device.shared_workspace(self.M, self.N)
         x = _device.to_device(v, self.matrix.device).reshape(-1)

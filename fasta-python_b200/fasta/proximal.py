@@ -13,14 +13,22 @@ the forward-step kernel (K1-K3): pass ``pen.g`` and ``pen.prox``.
   NonNegative()     g=0,         prox=max(x, 0)                nn_least_squares.py:41-42
   Box(lo, hi)       g=0,         prox=clip(x, lo, hi)          svm.py:71
   TVBall()          g=0,         prox=Y/max(|Y|_2, 1) on the last axis of size 2   tv_denoising.py:87-96
+  RowGroupL2(mu)    g=mu*sum_i|X_i|_2, prox=shrink_rows(X, t*mu)                   mmv.py:51-63
+  RowNormBall(mu)   g=0,         prox=project_rows_L2_ball(X, mu)                  max_norm.py:51-59
+  LinfNorm(mu)      g=mu*|x|_inf, prox=project_Linf_ball(x, t*mu)                   democratic_representation.py:43-45
+
+Row-wise operators on 2-D iterates (the prox bodies the matrix examples define inline):
+  shrink_rows(X, t)            X_i * shrink(|X_i|_2, t) / (|X_i|_2 + (|X_i|_2 == 0))     mmv.py:53-61
+  project_rows_L2_ball(X, mu)  mu * X_i / (max(|X_i|_2, mu) + (|X_i|_2 == 0))           max_norm.py:53-59
 """
 
 import numpy as np
 
 from . import _cabi, _device
 
-__all__ = ["project_Linf_ball", "project_L1_ball", "project_Lnuc_ball", "shrink",
-           "L1Norm", "L1Ball", "NonNegative", "Box", "TVBall"]
+__all__ = ["project_Linf_ball", "project_L1_ball", "project_Lnuc_ball", "shrink", "shrink_rows",
+           "project_rows_L2_ball", "row_norms", "L1Norm", "L1Ball", "NonNegative", "Box", "TVBall", "RowGroupL2",
+           "RowNormBall", "LinfNorm"]
 
 
 def _apply(x, tag, p0=0.0, p1=0.0, radius=None):
@@ -67,6 +75,36 @@ def project_Lnuc_ball(X, t):
     k = s.numel()
     S[:k, :k] = tt.diag(shrink(s, t))
     return _device.like_input(U @ S @ Vh, X)
+
+
+def _rows(X, mode, p, want_out=True, want_norms=False):
+    t = _device.torch()
+    lib = _cabi.load()
+    assert X.ndim == 2
+    Xd = _device.to_device(X).contiguous()
+    out = t.empty_like(Xd) if want_out else None
+    norms = t.empty(Xd.shape[0], dtype=t.float64, device=Xd.device) if want_norms else None
+    _cabi.check(lib.fb200_prox_rows(Xd.data_ptr(), Xd.shape[0], Xd.shape[1], mode, float(p), _device.ptr(out),
+                                    _device.ptr(norms), _device.stream_ptr()), "fb200_prox_rows")
+    return out, norms
+
+
+def shrink_rows(X, t):
+    """Row-group soft threshold, the prox of t*sum_i |X_i|_2 (reference mmv.py:53-61)."""
+    out, _ = _rows(X, 0, t)
+    return _device.like_input(out, X)
+
+
+def project_rows_L2_ball(X, mu):
+    """Every row scaled onto the l2 ball of radius mu (reference max_norm.py:53-59)."""
+    out, _ = _rows(X, 1, mu)
+    return _device.like_input(out, X)
+
+
+def row_norms(X):
+    """|X_i|_2 per row (la.norm(X, axis=1) of the reference's matrix examples)."""
+    _, norms = _rows(X, 0, 0.0, want_out=False, want_norms=True)
+    return _device.like_input(norms, X)
 
 
 class _Penalty:
@@ -144,3 +182,44 @@ class TVBall(_Penalty):
     def prox(self, x, t):
         assert x.shape[-1] == 2
         return _apply(x, self.tag)
+
+
+class RowGroupL2(_Penalty):
+    """g(X) = mu * sum_i |X_i|_2 on a 2-D iterate (reference mmv.py:51,63); generic back-end only."""
+    tag = None
+
+    def __init__(self, mu):
+        self.mu = mu
+
+    def g(self, X):
+        n = row_norms(X)
+        return self.mu * (n.sum() if _device.is_numpy(n) else n.sum().item())
+
+    def prox(self, X, t):
+        return shrink_rows(X, t * self.mu)
+
+
+class RowNormBall(_Penalty):
+    """Indicator of {|X_i|_2 <= mu for every row} (reference max_norm.py:51-59); generic back-end only."""
+    tag = None
+
+    def __init__(self, mu):
+        self.mu = mu
+
+    def prox(self, X, t):
+        return project_rows_L2_ball(X, self.mu)
+
+
+class LinfNorm(_Penalty):
+    """g(x) = mu * |x|_inf (reference democratic_representation.py:43-45); generic back-end only."""
+    tag = None
+
+    def __init__(self, mu):
+        self.mu = mu
+
+    def g(self, x):
+        a = abs(x).max()
+        return self.mu * (a if _device.is_numpy(x) else a.item())
+
+    def prox(self, x, t):
+        return project_Linf_ball(x, t * self.mu)

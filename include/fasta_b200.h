@@ -223,6 +223,13 @@ int fb200_tv_grad_bb_fused(const double* R, int64_t n0, int64_t n1, double* g, i
 int fb200_tv_iter_fused(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, int loss,
                         const double* b, double* x1, double* g1, double* scal, void* ws, void* stream);
 
+/* row-wise prox operators on a rows x cols row-major matrix iterate:
+ *   mode 0: X_i * shrink(|X_i|_2, p) / (|X_i|_2 + (|X_i|_2 == 0))      prox of p * sum_i |X_i|_2   mmv.py:53-61
+ *   mode 1: p * X_i / (max(|X_i|_2, p) + (|X_i|_2 == 0))               rows onto the p-ball        max_norm.py:53-59
+ * out == NULL skips the prox; norms (optional, rows doubles) receives |X_i|_2                              */
+int fb200_prox_rows(const double* x, int64_t rows, int64_t cols, int mode, double p, double* out, double* norms,
+                    void* stream);
+
 /* ---- small reductions used by the prologue and the generic (untagged-callable) path ---------
  * out (device) receives: dot = <a,b>; diff_nrm2sq = |a-b|^2; asum = sum |a|                   */
 int fb200_dot(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream);

@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_loader  # noqa: E402
 from oracle import problems  # noqa: E402
+from oracle import examples_extra  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -63,6 +64,47 @@ def run_case(ref, case, mode, seed=0):
     )
 
 
+def run_extra(ref, case, mode, seed=0):
+    """The remaining reference examples (oracle/examples_extra.py): same harness, generic callables."""
+    e = examples_extra.build(case, seed)
+    if e.apply is None:
+        A = ref.linalg.LinearMap.identity(e.x0.shape)                       # the examples pass None, None
+    else:
+        A = ref.linalg.LinearMap(e.apply, e.adjoint, e.x0.shape, e.wshape)
+    opts = dict(problems.HARNESS_OPTS)
+    opts.update(problems.MODES[mode])
+    opts.update(examples_extra.EXTRA_OPTS.get((case, mode), {}))
+    res = ref.fasta(A, e.f, e.gradf, e.g, e.proxg, e.x0, **opts)
+    n = res.iteration_count
+    return dict(
+        case=case, mode=mode, seed=seed,
+        opts_keys=np.array(sorted(opts.keys())),
+        opts_vals=np.array([repr(opts[k]) for k in sorted(opts.keys())]),
+        iteration_count=n, backtracks=res.backtracks,
+        residuals=res.residuals[:n], norm_residuals=res.norm_residuals[:n],
+        stepsizes=res.stepsizes[:n], objectives=res.objectives[:n + 1],
+        solution=res.solution,
+        numpy_version=np.__version__,
+    )
+
+
+def row_prox_kats():
+    """Known answers of the row-wise prox bodies of mmv.py:53-61 and max_norm.py:53-59 (restated in
+    oracle/examples_extra.py; the reference defines them inline inside solve())."""
+    rng = np.random.RandomState(77)
+    out = {}
+    Xs = [rng.randn(30, 10), rng.randn(7, 1), np.vstack([rng.randn(5, 33), np.zeros((2, 33))]), rng.randn(64, 2) * 1e-3]
+    ts = [0.9, 0.3, 4.0, 1e-3]
+    for i, (X, t) in enumerate(zip(Xs, ts)):
+        norms = np.linalg.norm(X, axis=1)
+        out[f"X{i}"], out[f"t{i}"] = X, t
+        out[f"norms{i}"] = norms
+        out[f"mmv{i}"] = X * (examples_extra._shrink(norms, t) / (norms + (norms == 0)))[:, np.newaxis]
+        out[f"ball{i}"] = t * X / (np.maximum(norms, t) + (norms == 0))[:, np.newaxis]
+    out["count"] = len(Xs)
+    return out
+
+
 def prox_kats(ref):
     rng = np.random.RandomState(1234)
     out = {}
@@ -99,10 +141,10 @@ def stopping_kats(ref):
 def main(argv):
     ref = ref_loader.load()
     os.makedirs(GOLDEN, exist_ok=True)
-    cases = argv or list(problems.CASES)
+    cases = argv or (list(problems.CASES) + list(examples_extra.CASES))
     for case in cases:
         for mode in problems.MODES:
-            rec = run_case(ref, case, mode)
+            rec = run_extra(ref, case, mode) if case in examples_extra.CASES else run_case(ref, case, mode)
             path = os.path.join(GOLDEN, f"{case}__{mode}.npz")
             np.savez_compressed(path, **rec)
             print(f"{case:28s} {mode:12s} iters={rec['iteration_count']:4d} bt={rec['backtracks']:3d} "
@@ -110,6 +152,7 @@ def main(argv):
     if not argv:
         np.savez_compressed(os.path.join(GOLDEN, "kat_prox.npz"), **prox_kats(ref))
         np.savez_compressed(os.path.join(GOLDEN, "kat_stopping.npz"), **stopping_kats(ref))
+        np.savez_compressed(os.path.join(GOLDEN, "kat_row_prox.npz"), **row_prox_kats())
         print("wrote prox / stopping known-answer vectors")
 
 

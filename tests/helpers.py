@@ -54,7 +54,8 @@ def assert_trajectory(res, gold, sol_tol=1e-9, obj_tol=1e-10, hist_tol=1e-4, lab
     assert e <= sol_tol, f"{label}: solution rel err {e:.3e}"
     if gold["objectives"] is not None and getattr(res, "objectives", None) is not None:
         obj = np.asarray(res.objectives)[:n + 1]
-        scale = np.maximum(np.abs(gold["objectives"]), abs(gold["objectives"][0]) * 1e-3)
+        floor = abs(gold["objectives"][0]) or np.max(np.abs(gold["objectives"]))      # objectives starting at exactly 0 (svm)
+        scale = np.maximum(np.abs(gold["objectives"]), floor * 1e-3)
         eo = float(np.max(np.abs(obj - gold["objectives"]) / scale))
         assert eo <= obj_tol, f"{label}: objective history rel err {eo:.3e}"
     for name in ("residuals", "stepsizes", "norm_residuals"):

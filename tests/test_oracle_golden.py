@@ -57,3 +57,26 @@ def test_oracle_stop_rules_truth_table(golden_dir):
         args = (3,) + tuple(row[:4])
         for fn, want in zip(fns, row[4:]):
             assert bool(fn(*args)) == bool(want)
+
+
+# ---- the remaining reference examples: generic callables through the oracle loop ----
+from oracle import examples_extra  # noqa: E402
+
+EXTRA = [(c, m) for c in examples_extra.CASES for m in problems.MODES]
+
+
+@pytest.mark.parametrize("case,mode", EXTRA)
+def test_oracle_matches_reference_on_extra_examples(case, mode):
+    gold = load_golden(case, mode)
+    e = examples_extra.build(case, int(gold["seed"]))
+    ident = lambda v: v
+    res = fasta_oracle.solve(e.apply or ident, e.adjoint or ident, e.f, e.gradf, e.g, e.proxg, e.x0, **gold["opts"])
+    n = gold["iteration_count"]
+    assert res.iteration_count == n and res.backtracks == gold["backtracks"]
+    if str(gold["numpy_version"]) == np.__version__:
+        assert np.array_equal(res.solution, gold["solution"])
+        assert np.array_equal(res.objectives[:n + 1], gold["objectives"])
+        assert np.array_equal(res.stepsizes[:n], gold["stepsizes"])
+    else:
+        np.testing.assert_allclose(res.solution, gold["solution"], rtol=0, atol=1e-9 * np.abs(gold["solution"]).max())
+        np.testing.assert_allclose(res.objectives[:n + 1], gold["objectives"], rtol=1e-10)
