@@ -197,6 +197,9 @@ class ShardedDriver:
         self.dist.broadcast(v1, src=self._root(), group=self.group)
         self.dist.broadcast(v2, src=self._root(), group=self.group)
 
+    def sync_probe(self, v):
+        self.dist.broadcast(v, src=self._root(), group=self.group)
+
 
 # =================================================================================================
 # fused back-end
@@ -261,20 +264,39 @@ class FusedBackend:
         if self.accelerate:
             self.XA[self.ac].copy_(x0d)
 
-    def lipschitz(self, v1, v2):
+    # -- prologue, pipelined: the F-2 work (z = A x0, f, gradf1; reference :135-139) does not depend on the two
+    # random probes of the Lipschitz estimate (:102-110), so it is queued first and the host draws the probes
+    # while the device works; each probe is uploaded from pinned staging and its sweep queued before the next
+    # draw.  The order of the draws from numpy's global RNG is the reference's.
+    def start_async(self):
+        """Queue start(); its sums are snapshotted on the stream, start() later only fetches them."""
+        self._queue_start()
+        self.ws.scal_saved.copy_(self.ws.scal, non_blocking=True)
+        self._start_queued = True
+
+    def _probe_outputs(self):
+        # X[other] and G[other] are free until the first advance(); Z / R are scratch here
+        return self.X[1 - self.ic], self.G[1 - self.gc]
+
+    def lipschitz_push(self, k, v):
+        """Upload probe k (0/1) and queue d_k = A^H gradf(A v_k)."""
         t = self.t
-        a = self.XH
-        b = self.DX
-        a.copy_(t.from_numpy(np.ascontiguousarray(v1.reshape(-1))), non_blocking=False)
-        b.copy_(t.from_numpy(np.ascontiguousarray(v2.reshape(-1))), non_blocking=False)
-        self.drv.sync_point(a, b)
-        d1, d2 = self.G[0], self.G[1]
-        for v, d in ((a, d1), (b, d2)):
-            if self.use_sweep:
-                self.drv.sweep(v, self.loss.tag, self.loss.b, self.Z, self.R, d, 0, None, None, None, 0.0, self.ws)
-            else:
-                self.drv.forward(v, self.loss.tag, self.loss.b, self.Z, self.R, self.ws)
-                self.drv.adjoint(self.R, d, 0, None, None, None, 0.0, self.ws)
+        dst = self.XH if k == 0 else self.DX
+        stage = self.ws.stage(k, self.n)
+        stage.copy_(t.from_numpy(np.ascontiguousarray(v.reshape(-1))))
+        dst.copy_(stage, non_blocking=True)
+        if hasattr(self.drv, "sync_probe"):
+            self.drv.sync_probe(dst)
+        d = self._probe_outputs()[k]
+        if self.use_sweep:
+            self.drv.sweep(dst, self.loss.tag, self.loss.b, self.Z, self.R, d, 0, None, None, None, 0.0, self.ws)
+        else:
+            self.drv.forward(dst, self.loss.tag, self.loss.b, self.Z, self.R, self.ws)
+            self.drv.adjoint(self.R, d, 0, None, None, None, 0.0, self.ws)
+
+    def lipschitz_finish(self):
+        d1, d2 = self._probe_outputs()
+        a, b = self.XH, self.DX
         sc = self.ws.scal
         _cabi.check(self.lib.fb200_diff_nrm2sq(d1.data_ptr(), d2.data_ptr(), self.n, sc[S.S_AUX0:].data_ptr(),
                                                self.ws.buf.data_ptr(), self._st()), "fb200_diff_nrm2sq")
@@ -284,6 +306,11 @@ class FusedBackend:
         s = self.ws.fetch()
         return np.sqrt(s[S.S_AUX0]), np.sqrt(s[S.S_AUX1])
 
+    def lipschitz(self, v1, v2):
+        self.lipschitz_push(0, v1)
+        self.lipschitz_push(1, v2)
+        return self.lipschitz_finish()
+
     def _penalty_of(self, x):
         """raw penalty reduction of a vector (only the l1 norm needs one)."""
         if self.pen.tag == S.PROX_SHRINK:
@@ -291,7 +318,7 @@ class FusedBackend:
                                             self.ws.buf.data_ptr(), self._st()), "fb200_asum")
             self.launches += 1
 
-    def start(self):
+    def _queue_start(self):
         z = self.ZA[self.ac] if self.accelerate else self.Z
         if self.use_sweep:
             self.drv.sweep(self.X[self.ic], self.loss.tag, self.loss.b, z, self.R, self.G[self.gc], 1, None, None, None,
@@ -300,7 +327,14 @@ class FusedBackend:
             self.drv.forward(self.X[self.ic], self.loss.tag, self.loss.b, z, self.R, self.ws)
             self.drv.adjoint(self.R, self.G[self.gc], 1, None, None, None, 0.0, self.ws)
         self._penalty_of(self.X[self.ic])
-        s = self.ws.fetch()
+
+    def start(self):
+        if getattr(self, "_start_queued", False):
+            self._start_queued = False
+            s = self.ws.fetch(saved=True)
+        else:
+            self._queue_start()
+            s = self.ws.fetch()
         return Scalars(f=self.loss.finalize(s[S.S_F]), pen=self.pen.value(s[S.S_PEN]), g_sq=s[S.S_G1_SQ])
 
     def advance(self):

@@ -61,6 +61,8 @@ class Workspace:
         self.scal = t.zeros(_cabi.NSCAL, dtype=t.float64, device=self.device)
         self.host = t.zeros(_cabi.NSCAL, dtype=t.float64).pin_memory()
         self._np = self.host.numpy()
+        self.scal_saved = t.zeros(_cabi.NSCAL, dtype=t.float64, device=self.device)   # snapshot of the start() sums
+        self._stage = None                                                            # pinned upload staging (2 vectors)
 
     def grow(self, M, N):
         need = int(self.lib.fb200_workspace_bytes(int(M), int(N)))
@@ -69,12 +71,20 @@ class Workspace:
             self.buf = t.zeros(need, dtype=t.uint8, device=self.device)
             self.nbytes = need
 
-    def fetch(self):
+    def fetch(self, saved=False):
         """One D2H copy of the scalar block + one stream sync: the per-decision-point sync."""
         t = torch()
-        self.host.copy_(self.scal, non_blocking=True)
+        self.host.copy_(self.scal_saved if saved else self.scal, non_blocking=True)
         t.cuda.current_stream().synchronize()
         return self._np      # np.float64 elements
+
+    def stage(self, slot, n):
+        """Pinned host staging vector `slot` (0/1) of n doubles, so that an upload neither blocks the host
+        behind the work already queued on the stream nor pays a cudaHostAlloc per solve."""
+        t = torch()
+        if self._stage is None or self._stage.shape[1] < n:
+            self._stage = t.empty((2, n), dtype=t.float64).pin_memory()
+        return self._stage[slot, :n]
 
 
 # ---- per-device pool: a solve borrows a workspace (device scratch + pinned scalar mirror) and gives

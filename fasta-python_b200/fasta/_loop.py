@@ -75,9 +75,17 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
 
     if not L or not tau0:                                   # ref :100 -- both are needed to skip
         # same two draws from numpy's global legacy RNG, in the same order (ref :102-103)
-        v1 = np.random.randn(*x0_shape)
-        v2 = np.random.randn(*x0_shape)
-        dgrad, dpoint = be.lipschitz(v1, v2)
+        if hasattr(be, "lipschitz_push"):
+            # pipelined prologue: the device starts on z = A x0 / gradf1 (ref :135-139, independent of the probes)
+            # and on each probe's sweep while the host draws the next probe
+            be.start_async()
+            be.lipschitz_push(0, np.random.randn(*x0_shape))
+            be.lipschitz_push(1, np.random.randn(*x0_shape))
+            dgrad, dpoint = be.lipschitz_finish()
+        else:
+            v1 = np.random.randn(*x0_shape)
+            v2 = np.random.randn(*x0_shape)
+            dgrad, dpoint = be.lipschitz(v1, v2)
         L = dgrad / dpoint                                  # ref :110
         tau0 = (2 / L) / 10                                 # ref :113
     if not tau0:                                            # ref :115-116 (unreachable, kept)
