@@ -353,6 +353,7 @@ def main():
     clocks = clocks_summary(sampler, sfile, local, t_begin, t_end) if rank == 0 else None
 
     iters = sum(r.iteration_count for r in outs)
+    peer_reductions = sum(getattr(r, "peer_reductions", 0) for r in outs)
     backtracks = sum(r.backtracks for r in outs)
     launches = sum(r.kernel_launches for r in outs)
     loop_s = sum(r.times[r.iteration_count] - r.times[0] for r in outs)
@@ -437,6 +438,9 @@ def main():
                     final_objective=float(outs[-1].residuals[outs[-1].iteration_count - 1]) and None,
                     wall_ms_per_step=1e3 * wall / args.steps)
         line["final_residual"] = float(outs[-1].residuals[outs[-1].iteration_count - 1])
+        if world > 1:
+            line["collective"] = ("fused peer-memory all-reduce + BB epilogue kernel over NVLink (fb200_peer_allreduce_bb), "
+                                  f"{peer_reductions} calls in the timed region" if peer_reductions else "ncclAllReduce + bb kernel")
         line.pop("final_objective")
         print(json.dumps(line), flush=True)
     if world > 1:

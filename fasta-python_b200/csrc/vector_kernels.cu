@@ -333,6 +333,45 @@ int launch_bb(int bb, const double* gsrc, int nsplit, int64_t ld, int64_t n, dou
     return check_launch("bb_kernel");
 }
 
+// ---- multi-GPU: all-reduce of the row-sharded A^T r partials over peer memory, fused with the BB epilogue ----
+// Every rank's partial gradient (n doubles) and raw loss partial (1 double at index n) sit in a buffer that is
+// mapped into every other rank's address space (NVLink peer memory; the mapping and the barrier before this
+// kernel are torch symmetric-memory plumbing).  Each rank reads all P partials directly from its peers and adds
+// them in rank order -- so all ranks hold the bit-identical g -- and forms the Barzilai-Borwein sums in the same
+// pass (reference __init__.py:248 + :254-260,274 on the row-partitioned map of SURVEY.md 8e).  One kernel
+// replaces {copy, ncclAllReduce, copy, bb_kernel}.
+struct PeerParts { const double* p[FB200_MAX_PEERS]; };
+
+template <int BB>
+__global__ void __launch_bounds__(VEC_THREADS)
+peer_allreduce_bb_kernel(PeerParts parts, int P, int64_t n, double* __restrict__ g, const double* __restrict__ x0,
+                         const double* __restrict__ xhat, const double* __restrict__ dx, double tau, int with_loss,
+                         double* scal, double* red, unsigned* counter) {
+    double s[3] = {0.0, 0.0, 0.0};
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double gi = __ldcg(&parts.p[0][i]);
+        for (int k = 1; k < P; ++k) gi += __ldcg(&parts.p[k][i]);
+        g[i] = gi;
+        if (BB >= 1) s[2] += gi * gi;
+        if (BB >= 2) {
+            const double dg = gi + (xhat[i] - x0[i]) / tau;     // __init__.py:254
+            s[0] += dx[i] * dg;                                  // :255
+            s[1] += dg * dg;                                     // :260
+        }
+    }
+    if (with_loss && blockIdx.x == 0 && threadIdx.x == 0) {
+        double f = __ldcg(&parts.p[0][n]);
+        for (int k = 1; k < P; ++k) f += __ldcg(&parts.p[k][n]);
+        scal[FB200_S_F] = f;
+    }
+    if (BB >= 1) {
+        double* const out[3] = {BB >= 2 ? scal + FB200_S_DX_DG : nullptr,
+                                BB >= 2 ? scal + FB200_S_DG_SQ : nullptr, scal + FB200_S_G1_SQ};
+        grid_sum<3>(s, red, counter, out);
+    }
+}
+
 // =================================================================================================
 // small reductions
 // =================================================================================================
@@ -434,6 +473,24 @@ extern "C" int fb200_step_reduce(const double* x0, const double* x1, const doubl
     else
         step_reduce_kernel<false><<<vec_grid(n), VEC_THREADS, 0, st>>>(x0, x1, xhat, g0, nullptr, n, dx, scal, w.red, w.counter);
     return check_launch("step_reduce");
+}
+
+extern "C" int fb200_peer_allreduce_bb(const uint64_t* peer_ptrs, int P, int64_t n, double* g, int bb, const double* x0,
+                                       const double* xhat, const double* dx, double tau, int with_loss, double* scal,
+                                       void* ws, void* stream) {
+    if (P < 1 || P > FB200_MAX_PEERS || n < 1) { set_error("peer_allreduce_bb: bad arguments"); return 1; }
+    Workspace w(ws);
+    PeerParts parts;
+    for (int k = 0; k < FB200_MAX_PEERS; ++k) parts.p[k] = reinterpret_cast<const double*>(k < P ? peer_ptrs[k] : peer_ptrs[0]);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = vec_grid(n);
+    switch (bb) {
+        case 0: peer_allreduce_bb_kernel<0><<<grid, VEC_THREADS, 0, st>>>(parts, P, n, g, x0, xhat, dx, tau, with_loss, scal, w.red, w.counter); break;
+        case 1: peer_allreduce_bb_kernel<1><<<grid, VEC_THREADS, 0, st>>>(parts, P, n, g, x0, xhat, dx, tau, with_loss, scal, w.red, w.counter); break;
+        case 2: peer_allreduce_bb_kernel<2><<<grid, VEC_THREADS, 0, st>>>(parts, P, n, g, x0, xhat, dx, tau, with_loss, scal, w.red, w.counter); break;
+        default: set_error("unknown bb mode %d", bb); return 1;
+    }
+    return check_launch("peer_allreduce_bb");
 }
 
 extern "C" int fb200_prox_rows(const double* x, int64_t rows, int64_t cols, int mode, double p, double* out, double* norms,

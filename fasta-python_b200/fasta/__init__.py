@@ -169,4 +169,5 @@ def fasta(*args, **kwargs) -> Convergence:
     result.single_pass = bool(getattr(be, "use_sweep", False))
     result.tv_fused = bool(getattr(be, "use_tv_fused", False))
     result.kernel_launches = be.total_launches()
+    result.peer_reductions = int(getattr(getattr(be, "drv", None), "peer_reductions", 0))   # fused NVLink all-reduce + BB calls
     return result

@@ -142,6 +142,7 @@ class ShardedDriver:
         self.group = group
         self.xshape, self.zshape = local.xshape, local.zshape
         self.collectives = 0
+        self.peer_reductions = 0
 
     @property
     def launches(self):
@@ -154,9 +155,61 @@ class ShardedDriver:
     def workspace_dims(self):
         return self.local.workspace_dims()
 
+    # -- peer-memory path: the partial gradients live in NVLink-mapped ("symmetric") buffers, and ONE kernel of ours
+    # (fb200_peer_allreduce_bb) reads every rank's partial, adds them in rank order and forms the BB sums.  torch
+    # supplies the mapping and the barrier; two buffers alternate so that one barrier per call suffices (a rank
+    # rewrites a buffer only after a later barrier, which every rank reaches after it finished reading).
+    _peer_cache = {}
+    peer_ok = os.environ.get("FASTA_B200_PEER", "1") != "0"
+
+    def _peer(self, n, device):
+        key = (id(self.group), int(n), device.index)
+        if key in ShardedDriver._peer_cache:
+            return ShardedDriver._peer_cache[key]
+        st = None
+        try:
+            if self.peer_ok and device.type == "cuda" and self.dist.get_backend(self.group) == "nccl" \
+                    and self.dist.get_world_size(self.group) <= 16:
+                import ctypes
+                import torch.distributed._symmetric_memory as symm
+                t = _device.torch()
+                pitch = (int(n) + 8 + 1) // 2 * 2
+                buf = symm.empty(2 * pitch, dtype=t.float64, device=device)
+                hdl = symm.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
+                P = hdl.world_size
+                ptrs = [(ctypes.c_uint64 * P)(*[int(hdl.buffer_ptrs[k]) + 8 * pitch * slot for k in range(P)])
+                        for slot in (0, 1)]
+                buf.zero_()
+                hdl.barrier(channel=0)
+                st = dict(buf=buf, hdl=hdl, P=P, pitch=pitch, ptrs=ptrs, calls=0)
+        except Exception as exc:                       # no peer mapping on this system: NCCL path below
+            import warnings
+            warnings.warn(f"fasta-b200: peer-memory all-reduce unavailable ({exc}); using ncclAllReduce")
+            st = None
+        ShardedDriver._peer_cache[key] = st
+        return st
+
     def sweep(self, x, loss_tag, b, z, r, g, bb, x0, xhat, dx, tau, ws):
-        self.local.sweep(x, loss_tag, b, z, r, g, 0, None, None, None, 0.0, ws)
         n = g.numel()
+        peer = self._peer(n, g.device) if g.is_cuda else None
+        if peer is not None:
+            slot = peer["calls"] & 1
+            peer["calls"] += 1
+            part = peer["buf"][slot * peer["pitch"]: slot * peer["pitch"] + n + 1]
+            self.local.sweep(x, loss_tag, b, z, r, part[:n], 0, None, None, None, 0.0, ws)
+            with_loss = 1 if loss_tag != S.LOSS_NONE else 0
+            if with_loss:
+                part[n:n + 1].copy_(ws.scal[S.S_F:S.S_F + 1])
+            peer["hdl"].barrier(channel=0)
+            _cabi.check(self.local.lib.fb200_peer_allreduce_bb(peer["ptrs"][slot], peer["P"], n, g.data_ptr(), int(bb),
+                                                               _device.ptr(x0), _device.ptr(xhat), _device.ptr(dx),
+                                                               float(tau), with_loss, ws.scal.data_ptr(), ws.buf.data_ptr(),
+                                                               _device.stream_ptr()), "fb200_peer_allreduce_bb")
+            self.local.launches += 1
+            self.collectives += 1
+            self.peer_reductions += 1
+            return
+        self.local.sweep(x, loss_tag, b, z, r, g, 0, None, None, None, 0.0, ws)
         base = getattr(g, "_base", None)
         packed = None
         if loss_tag != S.LOSS_NONE and base is not None and base.numel() > n and base.data_ptr() == g.data_ptr():

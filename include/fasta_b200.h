@@ -223,6 +223,17 @@ int fb200_tv_grad_bb_fused(const double* R, int64_t n0, int64_t n1, double* g, i
 int fb200_tv_iter_fused(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, int loss,
                         const double* b, double* x1, double* g1, double* scal, void* ws, void* stream);
 
+/* ---- multi-GPU (A row-partitioned): all-reduce of the A^T r partials over NVLink peer memory fused
+ * with the BB epilogue.  peer_ptrs[k] (host array, P entries) is the address, in THIS process, of rank k's partial:
+ * n doubles of gradient partial followed by one double of raw loss partial.  g = sum_k partial_k in rank order
+ * (bit-identical on every rank), scal[S_F] = sum of the loss partials (with_loss), BB sums as fb200_bb_reduce.
+ * The caller maps the buffers (torch symmetric memory / cudaIpc) and barriers the ranks before the call.
+ * Replaces ncclAllReduce + fb200_bb_reduce for reference __init__.py:248,254-260 on the sharded map.       */
+#define FB200_MAX_PEERS 16
+int fb200_peer_allreduce_bb(const uint64_t* peer_ptrs, int P, int64_t n, double* g, int bb, const double* x0,
+                            const double* xhat, const double* dx, double tau, int with_loss, double* scal, void* ws,
+                            void* stream);
+
 /* row-wise prox operators on a rows x cols row-major matrix iterate:
  *   mode 0: X_i * shrink(|X_i|_2, p) / (|X_i|_2 + (|X_i|_2 == 0))      prox of p * sum_i |X_i|_2   mmv.py:53-61
  *   mode 1: p * X_i / (max(|X_i|_2, p) + (|X_i|_2 == 0))               rows onto the p-ball        max_norm.py:53-59
