@@ -294,6 +294,8 @@ class FusedBackend:
         # a rejected trial costs exactly what the two-pass path would have paid for it).
         self.use_sweep = (not self.accelerate) and bool(getattr(driver, "sweep_ok", False))
         self._spec = None
+        self._ahead = False
+        self._pending = None
         # TV: one fused kernel per half-iteration (see TVDriver.step_forward)
         self.use_tv_fused = ((not self.accelerate) and isinstance(driver, TVDriver) and driver.fused_step_ok
                              and penalty.tag == S.PROX_TV_BALL and loss.tag != S.LOSS_NONE)
@@ -396,7 +398,10 @@ class FusedBackend:
         if self.accelerate:
             self.ap, self.ac = self.ac, 1 - self.ac
 
-    def trial(self, tau):
+    # A trial is queued (all kernels asynchronous) and collected (one fetch).  The host loop uses the split to queue
+    # the NEXT iteration's trial as soon as the new step size is known and to do its bookkeeping (histories, best
+    # iterate, stop rule) while the device already works; trial() is queue + collect.
+    def _queue_trial(self, tau):
         x0, g0 = self.X[self.ip], self.G[self.gp]
         x1 = self.XA[self.ac] if self.accelerate else self.X[self.ic]
         z1 = self.ZA[self.ac] if self.accelerate else self.Z
@@ -406,15 +411,10 @@ class FusedBackend:
         if self.use_tv_fused and self.drv.iter_fused_ok:
             # one kernel per trial; the gradient of an accepted trial is already in G[gc] (speculative, like the sweep)
             self.drv.iterate_fused(x0, g0, tau, self.loss.tag, self.loss.b, x1, self.G[self.gc], self.ws)
-            s = self.ws.fetch()
-            self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
-            return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
-                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0))
+            return "tv_iter"
         if self.use_tv_fused:
             self.drv.step_forward(x0, g0, tau, self.loss.tag, self.loss.b, x1, self.R, self.ws)
-            s = self.ws.fetch()
-            return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
-                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0))
+            return "tv_step"
         if self.pen.tag == S.PROX_L1BALL:
             _cabi.check(self.lib.fb200_forward_step(x0.data_ptr(), g0.data_ptr(), float(tau), self.n,
                                                     self.XH.data_ptr(), st), "fb200_forward_step")
@@ -430,13 +430,31 @@ class FusedBackend:
         if self.use_sweep:
             self.drv.sweep(x1, self.loss.tag, self.loss.b, z1, self.R, self.G[self.gc], 2, x0, self.XH, self.DX, tau,
                            self.ws)
-            s = self.ws.fetch()
+            return "sweep"
+        self.drv.forward(x1, self.loss.tag, self.loss.b, z1, self.R, self.ws)
+        return "forward"
+
+    def _collect_trial(self, kind):
+        s = self.ws.fetch()
+        if kind in ("tv_iter", "sweep"):
             self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
-        else:
-            self.drv.forward(x1, self.loss.tag, self.loss.b, z1, self.R, self.ws)
-            s = self.ws.fetch()
+        if kind in ("tv_iter", "tv_step"):
+            return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
+                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0))
         return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
                        xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART])
+
+    def trial(self, tau):
+        return self._collect_trial(self._queue_trial(tau))
+
+    def trial_launch(self, tau):
+        """Queue the next iteration's first trial; until trial_finish() the 'current' iterate is X[ip]."""
+        self._pending = self._queue_trial(tau)
+        self._ahead = True
+
+    def trial_finish(self):
+        self._ahead = False
+        return self._collect_trial(self._pending)
 
     def extrapolate(self, c):
         _cabi.check(self.lib.fb200_accel_step(float(c), self.XA[self.ac].data_ptr(), self.XA[self.ap].data_ptr(),
@@ -464,11 +482,15 @@ class FusedBackend:
         s = self.ws.fetch()
         return Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
 
+    def _current(self):
+        # after trial_launch() the buffers are already rotated for the next iteration
+        return self.X[self.ip] if self._ahead else self.X[self.ic]
+
     def keep_best(self):
-        self.BEST.copy_(self.X[self.ic])
+        self.BEST.copy_(self._current())
 
     def iterate(self):
-        return _device.like_input(self.X[self.ic].view(self.shape), self.x0_in)
+        return _device.like_input(self._current().view(self.shape), self.x0_in)
 
     def solution(self):
         # BEST belongs to this backend alone and the backend ends with the solve: hand the buffer over

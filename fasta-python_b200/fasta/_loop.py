@@ -19,6 +19,7 @@ device->host sync:
     solution()               best iterate in the caller's array type                  ref :317
 """
 
+import os
 from time import time
 
 import numpy as np
@@ -121,14 +122,23 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     max_residual = -np.inf                                  # ref :165-166
     best_quality = np.inf
 
+    # Back-ends that can queue a trial without waiting for it get the NEXT iteration's trial queued as soon as the
+    # new step size is known (end of the loop body); histories, best-iterate copy and stop rule then run on the host
+    # while the device works.  A trial queued before a stop is simply never collected.
+    run_ahead = hasattr(be, "trial_launch") and os.environ.get("FASTA_B200_RUN_AHEAD", "1") != "0"
+    queued = False
+
     i = 0
     while i < max_iters:
         times[i] = time()                                   # ref :173
-        be.advance()                                        # ref :176-178
         g0_sq = g1_sq
         tau0 = tau1
-
-        t = be.trial(tau0)                                  # ref :181-188
+        if queued:
+            t = be.trial_finish()
+            queued = False
+        else:
+            be.advance()                                    # ref :176-178
+            t = be.trial(tau0)                              # ref :181-188
         f1 = t.f
 
         backtrack_count = 0
@@ -177,6 +187,13 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
         f_hist[i + 1] = f1
         max_residual = max(max_residual, residual_hist[i])
 
+        # ref :308 -- evaluated here (it depends only on the residuals above) so that no trial is queued past the end
+        stop = stop_rule(i, residual_hist[i], norm_residual_hist[i], max_residual, tolerance)
+        if run_ahead and not stop and i + 1 < max_iters:
+            be.advance()                                    # next iteration's ref :176-188, queued now
+            be.trial_launch(tau1)
+            queued = True
+
         if evaluate_objective:                              # ref :284-300
             objective_hist[i + 1] = f1 + pen
             quality = objective_hist[i + 1]
@@ -195,7 +212,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
                 i, residual_hist[i], tau_hist[i], alpha0 if accelerate else 0.0,
                 backtrack_count if backtrack else 0, objective_hist[i] if evaluate_objective else 0))
 
-        if stop_rule(i, residual_hist[i], norm_residual_hist[i], max_residual, tolerance):   # ref :308-312
+        if stop:                                            # ref :308-312
             i += 1
             break
         i += 1
