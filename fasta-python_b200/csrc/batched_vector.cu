@@ -178,6 +178,20 @@ bv_select_kernel(double* __restrict__ dst, const double* __restrict__ src, const
         if (mask[o % B]) dst[o] = src[o];
 }
 
+// dst[:, dcol[k]] = src[:, scol[k]] for k < npairs (candidate fan-out of the batched line search: a column's
+// state is mirrored into spare slots, the winning slot is copied back); thread = (row, pair)
+__global__ void __launch_bounds__(BV_THREADS)
+bv_copy_cols_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t rows, int ld_dst, int ld_src,
+                    const int* __restrict__ scol, const int* __restrict__ dcol, int npairs) {
+    const int64_t total = rows * npairs;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t o = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += stride) {
+        const int64_t r = o / npairs;
+        const int k = int(o - r * npairs);
+        dst[r * ld_dst + dcol[k]] = src[r * ld_src + scol[k]];
+    }
+}
+
 struct BvLaunch {
     dim3 grid;
     int nblocks;
@@ -264,4 +278,15 @@ extern "C" int fb200_batched_select(double* dst, const double* src, const int* m
     if (grid < 1) grid = 1;
     bv_select_kernel<<<grid, BV_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, mask, n, int(B));
     return check_launch("bv_select");
+}
+
+extern "C" int fb200_batched_copy_cols(double* dst, const double* src, int64_t rows, int64_t ld_dst, int64_t ld_src,
+                                       const int* scol, const int* dcol, int npairs, void* stream) {
+    if (rows < 1 || npairs < 1) return 0;
+    const int64_t total = rows * npairs;
+    int grid = int((total + BV_THREADS - 1) / BV_THREADS);
+    const int cap = sm_count() * 8;
+    if (grid > cap) grid = cap;
+    bv_copy_cols_kernel<<<grid, BV_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, rows, int(ld_dst), int(ld_src), scol, dcol, npairs);
+    return check_launch("bv_copy_cols");
 }

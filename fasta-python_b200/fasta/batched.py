@@ -50,23 +50,33 @@ _VECTOR_RULES = {
 class _Batch:
     """Device state of a batch (all matrices row-major, batch index fastest)."""
 
-    def __init__(self, A, loss, pen, X0, B):
+    def __init__(self, A, loss, pen, X0, Bu, spare=0):
         t = _device.torch()
         self.t, self.lib = t, _cabi.load()
         self.A = A.matrix
         self.M, self.N, self.lda = A.M, A.N, A.lda
-        self.B = B
+        # columns 0..Bu-1 are the caller's problems; columns Bu..B-1 are spare slots in which the line search
+        # evaluates further shrunken step sizes of a column in the same pass (candidate fan-out)
+        self.Bu, self.spare = Bu, int(spare)
+        B = self.B = Bu + self.spare
         dev = self.A.device
         self.loss, self.pen = loss, pen
         b = loss.b
-        assert b.shape[0] == self.M and (b.ndim == 1 or b.shape[1] == B)
-        self.b, self.b_ld = (b.contiguous(), 0 if b.ndim == 1 else B)
+        assert b.shape[0] == self.M and (b.ndim == 1 or b.shape[1] == Bu)
+        if b.ndim == 1:
+            self.b, self.b_ld = b.contiguous(), 0
+        else:
+            self.b, self.b_ld = t.zeros((self.M, B), dtype=t.float64, device=dev), B
+            self.b[:, :Bu].copy_(b)
         new = lambda r: t.empty((r, B), dtype=t.float64, device=dev)
         self.X0, self.X1, self.XH, self.DX, self.G0, self.G1, self.BEST = (new(self.N) for _ in range(7))
         self.Z, self.R = new(self.M), new(self.M)
         self.ws = t.empty(int(self.lib.fb200_batched_workspace_bytes(self.M, self.N, B)), dtype=t.uint8, device=dev)
         self.out = t.zeros(5 * B, dtype=t.float64, device=dev)
         self.launches = 0
+        self._stage_w = max(B, 64)
+        self._stage = t.empty((64, 8 * self._stage_w), dtype=t.uint8).pin_memory()
+        self._stage_next = 0
         mode = os.environ.get("FASTA_B200_GEMM", "auto")
         if mode not in ("auto", "dmma", "ozaki"):
             raise ValueError("FASTA_B200_GEMM must be auto, dmma or ozaki")
@@ -74,16 +84,18 @@ class _Batch:
         if self.ozaki:
             self._ozaki_setup()
         else:
-            self.sf = int(self.lib.fb200_gemm_splits(self.M, B, self.N))       # forward: (M x B) over K = N
-            self.sa = int(self.lib.fb200_gemm_splits(self.N, B, self.M))       # adjoint: (N x B) over K = M
+            self.sf = int(self.lib.fb200_gemm_splits(self.M, Bu, self.N))      # forward: (M x B) over K = N
+            self.sa = int(self.lib.fb200_gemm_splits(self.N, Bu, self.M))      # adjoint: (N x B) over K = M
             self.ZP = t.empty((self.sf, self.M, B), dtype=t.float64, device=dev)
             self.GP = t.empty((self.sa, self.N, B), dtype=t.float64, device=dev)
         x0 = _device.to_device(X0, dev)
         if x0.ndim == 1:
-            x0 = x0[:, None].expand(self.N, B)
-        assert tuple(x0.shape) == (self.N, B)
-        self.X1.copy_(x0)
-        self.BEST.copy_(x0)
+            x0 = x0[:, None].expand(self.N, Bu)
+        assert tuple(x0.shape) == (self.N, Bu)
+        for buf in (self.X0, self.X1, self.XH, self.DX, self.G0, self.G1, self.BEST, self.Z, self.R):
+            buf[:, Bu:].zero_()
+        self.X1[:, :Bu].copy_(x0)
+        self.BEST[:, :Bu].copy_(x0)
 
     def _ozaki_setup(self):
         """Digit planes of A for both products (once per batch) and the buffers of the per-product planes."""
@@ -102,7 +114,9 @@ class _Batch:
                                                self.oz_scratch.data_ptr(), self._st()), "fb200_ozaki_slice_cols")
         self.XS, self.xs = i8(8, bp, np_), f8(bp)            # planes of the iterate X (N x B), transposed
         self.RS, self.rs = i8(8, bp, mp), f8(bp)             # planes of the residual R (M x B), transposed
-        widths = range(64, bp + 1, 64)
+        # ONE K-split count per product, whatever the number of active columns: a column's result must not depend
+        # on which other columns happen to be multiplied with it (the partials are added in split order)
+        widths = range(64, pad(self.Bu, 64) + 1, 64)
         self.sf = max(int(lib.fb200_ozaki_splits(M, w, N)) for w in widths)
         self.sa = max(int(lib.fb200_ozaki_splits(N, w, M)) for w in widths)
         self.ZP = t.empty((self.sf, M, B), dtype=t.float64, device=dev)
@@ -113,12 +127,12 @@ class _Batch:
         lib, t = self.lib, self.t
         cols = np.nonzero(act)[0]
         n_act = len(cols)
-        cm = None if n_act == self.B else t.as_tensor(cols.astype(np.int32), device=src.device)
+        cm = None if n_act == self.B else self._vec(cols, np.int32)
         cmp_ = 0 if cm is None else cm.data_ptr()
         LS, ls, RS, rs = (self.AT, self.at, self.RS, self.rs) if adjoint else (self.AF, self.af, self.XS, self.xs)
         _cabi.check(lib.fb200_ozaki_slice_cols(src.data_ptr(), self.B, K, cmp_, n_act, 64, RS.data_ptr(), rs.data_ptr(),
                                                self.oz_scratch.data_ptr(), self._st()), "fb200_ozaki_slice_cols")
-        s = int(lib.fb200_ozaki_splits(rows, n_act, K))
+        s = self.sa if adjoint else self.sf
         _cabi.check(lib.fb200_ozaki_gemm(LS.data_ptr(), ls.data_ptr(), rows, RS.data_ptr(), rs.data_ptr(), n_act, K, part.data_ptr(),
                                          self.B, cmp_, s, rows * self.B, self._st()), "fb200_ozaki_gemm")
         self.launches += 4
@@ -128,7 +142,20 @@ class _Batch:
         return _device.stream_ptr()
 
     def _vec(self, a, dtype):
-        return self.t.as_tensor(np.array(a, dtype=dtype, copy=True), device=self.A.device)
+        """Upload a short per-column host vector without blocking the host: pinned staging ring + async copy (a
+        pageable cudaMemcpy would wait for everything already queued on the stream).  Every round of the loop ends
+        in a device->host fetch, so far fewer than the ring's 64 uploads are ever in flight."""
+        t = self.t
+        a = np.asarray(a, dtype=dtype)
+        if a.size > self._stage_w:
+            return t.as_tensor(np.array(a, copy=True), device=self.A.device)
+        slot = self._stage_next
+        self._stage_next = (slot + 1) % 64
+        view = self._stage[slot, :a.size * a.itemsize].numpy().view(dtype)
+        view[:] = a.ravel()
+        out = t.empty(a.size, dtype=t.float64 if dtype == np.float64 else t.int32, device=self.A.device)
+        out.view(t.uint8).copy_(self._stage[slot, :a.size * a.itemsize], non_blocking=True)
+        return out
 
     def _gemm(self, adjoint, src, part, rows, K, splits, act):
         """Columns `act` of (A or A^T) . src into `part`; returns the number of split partials the
@@ -163,7 +190,7 @@ class _Batch:
         idx = t.as_tensor(cols, device=src.device)
         nb = len(cols)
         sub = src.index_select(1, idx).contiguous()
-        s = int(lib.fb200_gemm_splits(rows, nb, K))
+        s = splits                              # the same K split as the full-width product: results independent of the active set
         out = t.empty((s, rows, nb), dtype=t.float64, device=src.device)
         _cabi.check(lib.fb200_gemm_f64(adjoint, self.A.data_ptr(), self.lda, sub.data_ptr(), nb, out.data_ptr(), nb, rows, nb, K,
                                        s, rows * nb, self._st()), "fb200_gemm_f64")
@@ -198,9 +225,18 @@ class _Batch:
         o = self.out[:3 * self.B].cpu().numpy().reshape(3, self.B)
         return o[0], o[1], o[2]
 
-    def step(self, act, tau):
-        """xhat, x1 = prox, dx for the active columns -> (dx_g0, dx_sq, xmxh_sq, pen_raw) each (B,)"""
-        p0, p1 = self.pen.params(np.asarray(tau, dtype=np.float64))
+    def step(self, act, tau, owner=None):
+        """xhat, x1 = prox, dx for the active columns -> (dx_g0, dx_sq, xmxh_sq, pen_raw) each (B,);
+        owner[j] = the caller's column whose penalty a (spare) column j uses"""
+        tau = np.asarray(tau, dtype=np.float64)
+        if isinstance(self.pen, proximal.L1Norm):
+            mu = np.asarray(self.pen.mu, dtype=np.float64)
+            mu = np.concatenate([mu, np.zeros(self.B - len(mu))]) if mu.ndim else np.full(self.B, mu)
+            if owner is not None:
+                mu = mu[owner]
+            p0, p1 = tau * mu, 0.0                            # as L1Norm.params: shrink threshold t * mu
+        else:
+            p0, p1 = self.pen.params(tau)
         p0 = np.broadcast_to(np.asarray(p0, dtype=np.float64), (self.B,))
         p1 = np.broadcast_to(np.asarray(p1, dtype=np.float64), (self.B,))
         a, tv = self._vec(act, np.int32), self._vec(tau, np.float64)
@@ -212,6 +248,17 @@ class _Batch:
         self.launches += 2
         o = self.out[:4 * self.B].cpu().numpy().reshape(4, self.B)
         return o[0], o[1], o[2], o[3]
+
+    def copy_cols(self, arrays, scol, dcol):
+        """arr[:, dcol[k]] = arr[:, scol[k]] for every array in `arrays`."""
+        if len(scol) == 0:
+            return
+        sc, dc = self._vec(scol, np.int32), self._vec(dcol, np.int32)
+        for a in arrays:
+            _cabi.check(self.lib.fb200_batched_copy_cols(a.data_ptr(), a.data_ptr(), a.shape[0], a.shape[1], a.shape[1],
+                                                         sc.data_ptr(), dc.data_ptr(), len(scol), self._st()),
+                        "fb200_batched_copy_cols")
+            self.launches += 1
 
     def select(self, dst, src, mask):
         if not np.any(mask):
@@ -257,7 +304,14 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
         penalty = proximal.L1Norm(mus)
     if B % 2:
         raise ValueError("fasta_batched: the batch width must be even (pad with a duplicate column)")
-    st = _Batch(A, loss, penalty, x0a, B)
+    # candidate fan-out of the line search: up to `fan` consecutive shrunken step sizes of a column are evaluated
+    # in ONE pass (the extra candidates live in `spare` scratch columns), because a retry round costs a whole
+    # stream over A however few columns take part in it
+    fan = max(1, int(os.environ.get("FASTA_B200_FANOUT", "3"))) if backtrack else 1
+    spare = int(os.environ.get("FASTA_B200_FANOUT_SLOTS", "0" if fan == 1 else ("64" if B >= 32 else "8")))
+    spare += (B + spare) % 2
+    st = _Batch(A, loss, penalty, x0a, B, spare)
+    BT = st.B
 
     if stepsize_shrink is None and backtrack:
         stepsize_shrink = 0.2 if adaptive else 0.5
@@ -268,6 +322,12 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
     if verbose:
         print(f"Initializing batched FASTA: {B} columns\n")
 
+    def ext(v, fill=0):
+        """host vector over the caller's columns -> over all device columns (spare slots filled)"""
+        out = np.full(BT, fill, dtype=np.asarray(v).dtype)
+        out[:B] = v
+        return out
+
     ones = np.ones(B, dtype=bool)
     resid_h = np.zeros((B, max_iters))
     nresid_h = np.zeros((B, max_iters))
@@ -277,13 +337,13 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
     times = np.zeros(max_iters + 1)
 
     tau1 = np.full(B, tau0, dtype=np.float64)
-    f1 = loss.finalize(st.forward(ones))
-    _, _, g1_sq = st.adjoint(ones, tau1, 1)
-    g1_sq = g1_sq.copy()
+    f1 = loss.finalize(st.forward(ext(ones, False)))[:B]
+    _, _, g1_sq = st.adjoint(ext(ones, False), ext(tau1, 1.0), 1)
+    g1_sq = g1_sq[:B].copy()
     f_h[:, 0] = f1
     pen_raw0 = np.zeros(B)
     if evaluate_objective:
-        pen_raw0 = st.X1.abs().sum(dim=0).cpu().numpy() if isinstance(penalty, proximal.L1Norm) else np.zeros(B)
+        pen_raw0 = st.X1[:, :B].abs().sum(dim=0).cpu().numpy() if isinstance(penalty, proximal.L1Norm) else np.zeros(B)
         obj_h[:, 0] = f1 + penalty.value(pen_raw0)
 
     done = np.zeros(B, dtype=bool)
@@ -293,38 +353,105 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
     best_q = np.full(B, np.inf)
     dx_g0, dx_sq, xmxh_sq, pen_raw = (np.zeros(B) for _ in range(4))
     f1 = f1.copy()
+    bt_prev = np.zeros(B, dtype=np.int64)
+    fan_rounds = fan_hits = 0
+    state_arrays = (st.XH, st.X1, st.DX, st.Z, st.R)
 
     i = 0
     while i < max_iters and not done.all():
         times[i] = time()
         act = ~done
-        st.select(st.X0, st.X1, act)                      # x0 <- x1, gradf0 <- gradf1 (reference :176-177)
-        st.select(st.G0, st.G1, act)
+        st.select(st.X0, st.X1, ext(act, False))          # x0 <- x1, gradf0 <- gradf1 (reference :176-177)
+        st.select(st.G0, st.G1, ext(act, False))
         g0_sq = g1_sq.copy()
         tau_cur = tau1.copy()
+        lo = max(i - window + 1, 0)
+        f_max = np.max(f_h[:, lo:i + 1], axis=1)
 
-        def trial(mask):
-            a, b_, c, d = st.step(mask, tau_cur)
+        def fails(f, dxg, dxsq, tau, fm):
+            with np.errstate(all="ignore"):
+                return f - (fm + dxg + np.sqrt(dxsq) ** 2 / (2 * tau)) > EPSILON      # reference :200
+
+        def run_round(cols, first_shrunk, depth):
+            """For every column j in `cols`, evaluate depth[j] consecutive candidates tau, tau*s, tau*s*s, ...
+            (starting at tau*s when first_shrunk) in one pass: candidate 0 in the column itself, the others in
+            spare slots; adopt the first one that passes the line-search test (else the last).  Returns the
+            number of shrinks applied per column of `cols`."""
+            nonlocal fan_rounds, fan_hits
+            mask = np.zeros(BT, dtype=bool)
+            tau_e = np.ones(BT)
+            owner = np.arange(BT)
+            owner[B:] = 0
+            slots = {}
+            nxt = B
+            for j in cols:
+                tj = tau_cur[j] * stepsize_shrink if first_shrunk else tau_cur[j]
+                mask[j], tau_e[j] = True, tj
+                slots[j] = [(j, tj)]
+                for _ in range(1, int(depth[j])):
+                    tj = tj * stepsize_shrink                 # the same sequence of products as repeated tau0 *= shrink
+                    mask[nxt], tau_e[nxt], owner[nxt] = True, tj, j
+                    slots[j].append((nxt, tj))
+                    nxt += 1
+            mirror = [(j, q) for j in cols for q, _ in slots[j][1:]]
+            if mirror:
+                src, dst = [m[0] for m in mirror], [m[1] for m in mirror]
+                st.copy_cols((st.X0, st.G0) + ((st.b,) if st.b_ld else ()), src, dst)
+                fan_rounds += 1
+            a, b_, c, d = st.step(mask, tau_e, owner)
             fm = loss.finalize(st.forward(mask))
-            dx_g0[mask], dx_sq[mask], xmxh_sq[mask], pen_raw[mask] = a[mask], b_[mask], c[mask], d[mask]
-            f1[mask] = fm[mask]
+            shrinks = {}
+            win_src, win_dst = [], []
+            for j in cols:
+                pick = len(slots[j]) - 1
+                for k, (q, tq) in enumerate(slots[j]):
+                    if not backtrack or not fails(fm[q], a[q], b_[q], tq, f_max[j]):
+                        pick = k
+                        break
+                q, tq = slots[j][pick]
+                dx_g0[j], dx_sq[j], xmxh_sq[j], pen_raw[j], f1[j] = a[q], b_[q], c[q], d[q], fm[q]
+                tau_cur[j] = tq
+                shrinks[j] = pick + (1 if first_shrunk else 0)
+                if q != j:
+                    win_src.append(q)
+                    win_dst.append(j)
+                    fan_hits += 1
+            st.copy_cols(state_arrays, win_src, win_dst)
+            return shrinks
 
-        trial(act)
+        cols = np.nonzero(act)[0]
+        depth = np.ones(B, dtype=np.int64)
+        if fan > 1 and spare:
+            # predictive fan-out: a column that had to backtrack in the previous iteration brings its next
+            # candidates along in the first trial, as long as spare slots last
+            budget = spare
+            for j in cols[np.argsort(-bt_prev[cols], kind="stable")]:
+                if bt_prev[j] == 0 or budget <= 0:
+                    break
+                depth[j] = 1 + min(fan - 1, budget, max_backtracks)
+                budget -= depth[j] - 1
+        sh = run_round(cols, False, depth)
         bt = np.zeros(B, dtype=np.int64)
+        for j, k in sh.items():
+            bt[j] = k
         if backtrack:
-            lo = max(i - window + 1, 0)
-            f_max = np.max(f_h[:, lo:i + 1], axis=1)
             while True:
-                with np.errstate(all="ignore"):
-                    need = act & (f1 - (f_max + dx_g0 + np.sqrt(dx_sq) ** 2 / (2 * tau_cur)) > EPSILON) & (bt < max_backtracks)
+                need = act & fails(f1, dx_g0, dx_sq, tau_cur, f_max) & (bt < max_backtracks)
                 if not need.any():
                     break
-                tau_cur[need] *= stepsize_shrink
-                trial(need)
-                bt[need] += 1
+                cols = np.nonzero(need)[0]
+                depth = np.ones(B, dtype=np.int64)
+                if fan > 1 and spare:
+                    per = 1 + min(fan - 1, spare // len(cols))
+                    depth[cols] = np.minimum(per, max_backtracks - bt[cols])
+                sh = run_round(cols, True, depth)
+                for j, k in sh.items():
+                    bt[j] += k
             total_bt += bt
+        bt_prev = bt
 
-        dx_dg, dg_sq, gsq = st.adjoint(act, tau_cur, 2 if adaptive else 1)
+        act_e, tau_e = ext(act, False), ext(tau_cur, 1.0)
+        dx_dg, dg_sq, gsq = (v[:B] for v in st.adjoint(act_e, tau_e, 2 if adaptive else 1))
         g1_sq[act] = gsq[act]
         tau1[act] = tau_cur[act]
         dx_norm = np.sqrt(dx_sq)
@@ -354,7 +481,7 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
         else:
             quality = resid
         better = act & (quality < best_q)
-        st.select(st.BEST, st.X1, better)
+        st.select(st.BEST, st.X1, ext(better, False))
         best_q[better] = quality[better]
 
         iters[act] = i + 1
@@ -371,7 +498,7 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
         i += 1
     times[i] = time()
 
-    best = st.BEST.t().contiguous()          # (B, N)
+    best = st.BEST[:, :B].t().contiguous()   # (B, N)
     results = []
     for j in range(B):
         n = int(iters[j])
@@ -383,6 +510,7 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
                         obj_h[j] if evaluate_objective else None, None, None)
         results.append(c)
     results_meta = dict(kernel_launches=st.launches, gemm_splits=(st.sf, st.sa), iterations_lockstep=i,
+                        fanout=dict(depth=fan, spare_columns=spare, rounds_with_fanout=fan_rounds, candidates_adopted_from_slots=fan_hits),
                         gemm="tcgen05-i8-digit-planes" if st.ozaki else "dmma-f64")
     for c in results:
         c.batch = results_meta

@@ -196,6 +196,10 @@ int fb200_batched_bb(const double* gsrc, int nsplit, int64_t split_stride, const
                      const double* dx, const double* tau, const int* act, int bb, int64_t n, int64_t B,
                      double* g1, double* out, void* ws, void* stream);
 int fb200_batched_select(double* dst, const double* src, const int* mask, int64_t n, int64_t B, void* stream);
+/* dst[:, dcol[k]] = src[:, scol[k]], k < npairs (device index arrays): moves a column's state between its own
+ * slot and the spare slots in which the batched line search evaluates several shrunken step sizes at once   */
+int fb200_batched_copy_cols(double* dst, const double* src, int64_t rows, int64_t ld_dst, int64_t ld_src,
+                            const int* scol, const int* dcol, int npairs, void* stream);
 
 /* ---- K11/K12: total-variation stencils (periodic)               tv_denoising.py:26-63
  * Y is n0 x n1 x 2 (last axis interleaved), Z is n0 x n1.

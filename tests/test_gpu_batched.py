@@ -192,3 +192,30 @@ def test_tcgen05_digit_plane_gemm_matches_extended_precision():
         assert np.all(Zc[:, [c for c in range(B) if c % 3 == 1]] == 0.0)
         # run-to-run reproducibility (integer accumulation, fixed-order recombination)
         assert np.array_equal(Z, product(AF, af, M, XS, xs, B, N, B))
+
+
+@pytest.mark.parametrize("gemm", ["dmma", "ozaki"])
+def test_line_search_fanout_is_bitwise_the_sequential_search(gemm, monkeypatch):
+    """Evaluating several shrunken step sizes of a column at once (spare slots) must reproduce the one-at-a-time
+    line search exactly: same counts, bit-identical histories and solutions.  (Both runs carry the same number of
+    spare columns: the per-column reduction geometry of the vector kernels depends on the device batch width.)"""
+    import fasta
+    monkeypatch.setenv("FASTA_B200_GEMM", gemm)
+    monkeypatch.setenv("FASTA_B200_FANOUT_SLOTS", "8")
+    p = problems.build("lasso_200x1000_k50", 0)
+    lam_max = np.max(np.abs(p.A.T @ p.b))
+    mus = lam_max * np.logspace(-1.6, -0.3, 8)            # the small mus backtrack many times
+    opts = dict(problems.HARNESS_OPTS, adaptive=True)
+    runs = {}
+    for fan in ("1", "3"):
+        monkeypatch.setenv("FASTA_B200_FANOUT", fan)
+        np.random.seed(11)
+        runs[fan] = fasta.batched.lasso_path(p.A, p.b, mus, **opts)
+    meta = runs["3"][0].batch["fanout"]
+    assert meta["depth"] == 3 and meta["rounds_with_fanout"] > 0 and meta["candidates_adopted_from_slots"] > 0
+    assert runs["1"][0].batch["fanout"]["rounds_with_fanout"] == 0
+    assert sum(r.backtracks for r in runs["1"]) > 10
+    for a, b in zip(runs["1"], runs["3"]):
+        assert (a.iteration_count, a.backtracks) == (b.iteration_count, b.backtracks)
+        assert np.array_equal(a.stepsizes, b.stepsizes) and np.array_equal(a.residuals, b.residuals)
+        assert np.array_equal(a.objectives, b.objectives) and np.array_equal(a.solution, b.solution)
