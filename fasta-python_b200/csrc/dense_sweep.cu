@@ -64,7 +64,8 @@ template <int LOSS, int CPT>
 __global__ void __launch_bounds__(SW_THREADS, 1)
 dense_sweep_kernel(const double* __restrict__ A, int64_t lda, int M, int N, int Nc, const double* __restrict__ x,
                    const double* __restrict__ b, double* __restrict__ z, double* __restrict__ r,
-                   double* __restrict__ gpart, int64_t ldg, double* __restrict__ fpart, int nstage) {
+                   double* __restrict__ gpart, int64_t ldg, double* __restrict__ fpart, int nstage,
+                   const double* __restrict__ za0, double* __restrict__ za1, double cacc, double* __restrict__ fpart2) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int STAGE_BYTES = CPT * SW_GROUP * 16;
     double*   recv  = reinterpret_cast<double*>(smem + size_t(nstage) * STAGE_BYTES);     // [NSLOT][MAXCS]
@@ -170,13 +171,18 @@ dense_sweep_kernel(const double* __restrict__ A, int64_t lda, int M, int N, int 
         int stage = 0;
         uint32_t phase = 0;
         double bnext = (row_lo < row_hi && b) ? __ldg(b + row_lo) : 0.0;
+        // FISTA mode (za0 != nullptr): x is the prox point, z_i its image; the gradient is taken at the
+        // extrapolated z_i + c (z_i - za0_i) (reference __init__.py:244-248), a per-row function of z_i
+        double qnext = (row_lo < row_hi && za0) ? __ldg(za0 + row_lo) : 0.0;
+        double facc2 = 0.0;
         for (int row = row_lo; row < row_hi; ++row) {
             const int it = row - row_lo;
             const int slot = it & (SW_NSLOT - 1);
             const uint32_t rpar = uint32_t(it / SW_NSLOT) & 1u;
             if (t == 0) mbar_expect_tx(&rbar[slot], csize * 8u);
-            const double bi = bnext;
+            const double bi = bnext, qi = qnext;
             if (row + 1 < row_hi && b) bnext = __ldg(b + row + 1);
+            if (row + 1 < row_hi && za0) qnext = __ldg(za0 + row + 1);
             // st.async data is visible to whoever observes the phase completion of the barrier it signals
             // (a cluster-scope acquire here would make ptxas emit an L1 invalidate, CCTL.IVALL, per row)
             mbar_wait(&rbar[slot], rpar);
@@ -190,7 +196,8 @@ dense_sweep_kernel(const double* __restrict__ A, int64_t lda, int M, int N, int 
                 zi = (s0 + s1) + (s2 + s3);
             }
             double ri, fi;
-            loss_strict<LOSS>(zi, bi, ri, fi);
+            const double ze = za0 ? __dadd_rn(zi, __dmul_rn(cacc, __dsub_rn(zi, qi))) : zi;   // p + c*(p - za0), as accel_step
+            loss_strict<LOSS>(ze, bi, ri, fi);
             if (slab_bytes > 0) {
                 mbar_wait(&full[stage], phase);      // already complete (the A-group saw it); orders the TMA data for us
                 const double2* a = reinterpret_cast<const double2*>(smem + size_t(stage) * STAGE_BYTES) + t;
@@ -205,8 +212,14 @@ dense_sweep_kernel(const double* __restrict__ A, int64_t lda, int M, int N, int 
             }
             if (rank == 0 && t == 0) {
                 facc = __dadd_rn(facc, fi);
-                z[row] = zi;
+                z[row] = ze;
                 if (LOSS != FB200_LOSS_NONE) r[row] = ri;
+                if (za0) {                           // f at the prox point (line search) and the prox image itself
+                    double rp, fp;
+                    loss_strict<LOSS>(zi, bi, rp, fp);
+                    facc2 = __dadd_rn(facc2, fp);
+                    za1[row] = zi;
+                }
             }
             if (++stage == nstage) { stage = 0; phase ^= 1u; }
         }
@@ -217,7 +230,10 @@ dense_sweep_kernel(const double* __restrict__ A, int64_t lda, int M, int N, int 
             const int col = c0 + 2 * (t + SW_GROUP * k);
             if (col < c0 + ncols) *reinterpret_cast<double2*>(gp + col) = gr[k];
         }
-        if (rank == 0 && t == 0) fpart[cid] = facc;
+        if (rank == 0 && t == 0) {
+            fpart[cid] = facc;
+            if (za0) fpart2[cid] = facc2;
+        }
     }
     cluster_sync_all();         // nobody leaves while a peer might still address its shared memory
 }
@@ -237,7 +253,7 @@ struct SweepPlan {
 };
 
 typedef void (*SweepKernel)(const double*, int64_t, int, int, int, const double*, const double*, double*, double*,
-                            double*, int64_t, double*, int);
+                            double*, int64_t, double*, int, const double*, double*, double, double*);
 
 template <int LOSS>
 static SweepKernel pick_kernel(int cpt) {
@@ -339,10 +355,11 @@ extern "C" int fb200_sweep_supported(const double* A, int64_t lda, int64_t M, in
     return p.ok ? p.cs : 0;
 }
 
-extern "C" int fb200_dense_sweep(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss,
-                                 const double* b, double* z, double* r, double* g, int bb, const double* x0,
-                                 const double* xhat, const double* dx, double tau, double* scal, void* ws,
-                                 size_t ws_bytes, void* stream) {
+// za0 != nullptr: FISTA mode (see the kernel); S_F then holds f at the prox point and S_AUX3 f at the extrapolated z
+static int sweep_launch(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss, const double* b,
+                        double* z, double* r, double* g, int bb, const double* x0, const double* xhat, const double* dx,
+                        double tau, double* scal, void* ws, size_t ws_bytes, void* stream, const double* za0,
+                        double* za1, double c) {
     if (!sweep_eligible(A, lda, M, N) || reinterpret_cast<uintptr_t>(x) % 16 != 0) {
         set_error("dense_sweep: matrix not eligible (needs 16-byte aligned base and x, even lda and N, N <= %d)", SW_MAXCS * SW_GROUP * 26);
         return 1;
@@ -358,19 +375,42 @@ extern "C" int fb200_dense_sweep(const double* A, int64_t lda, int64_t M, int64_
     if (ncl > M) ncl = int(M);
     const int64_t cap = int64_t(fb200_workspace_bytes(M, N) - DENSE_OFF) / 8 / ldg;
     if (ncl > cap) ncl = int(cap);
-    if (ncl > FPART_MAX) ncl = FPART_MAX;
+    const int fcap = za0 ? FPART_MAX / 2 : FPART_MAX;       // FISTA mode keeps two loss partials per cluster
+    if (ncl > fcap) ncl = fcap;
     SweepKernel k = kernel_for(loss, p.cpt);
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     fill_launch(&cfg, attr, p, ncl, st);
     double* fpart = w.fpart;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k, A, lda, int(M), int(N), p.nc, x, b, z, r, w.dense, ldg, fpart, p.nstage);
+    double* fpart2 = w.fpart + FPART_MAX / 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, A, lda, int(M), int(N), p.nc, x, b, z, r, w.dense, ldg, fpart, p.nstage, za0, za1,
+                                       c, fpart2);
     if (e != cudaSuccess) { set_error("dense_sweep: launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 1; }
     if (loss != FB200_LOSS_NONE) {
-        sweep_fsum_kernel<<<1, 32, 0, st>>>(fpart, ncl, scal + FB200_S_F);
+        if (za0) {
+            sweep_fsum_kernel<<<1, 32, 0, st>>>(fpart2, ncl, scal + FB200_S_F);       // prox point: the line-search value
+            sweep_fsum_kernel<<<1, 32, 0, st>>>(fpart, ncl, scal + FB200_S_AUX3);     // extrapolated point
+        } else {
+            sweep_fsum_kernel<<<1, 32, 0, st>>>(fpart, ncl, scal + FB200_S_F);
+        }
         if (check_launch("sweep_fsum_kernel")) return 1;
     }
     // Barzilai-Borwein epilogue: fixed-order sum of the cluster partials (+ reductions)
     if (g) return launch_bb(bb, w.dense, ncl, ldg, N, g, x0, xhat, dx, tau, scal, w, st);
     return 0;
+}
+
+extern "C" int fb200_dense_sweep(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss,
+                                 const double* b, double* z, double* r, double* g, int bb, const double* x0,
+                                 const double* xhat, const double* dx, double tau, double* scal, void* ws,
+                                 size_t ws_bytes, void* stream) {
+    return sweep_launch(A, lda, M, N, x, loss, b, z, r, g, bb, x0, xhat, dx, tau, scal, ws, ws_bytes, stream, nullptr, nullptr, 0.0);
+}
+
+extern "C" int fb200_dense_sweep_accel(const double* A, int64_t lda, int64_t M, int64_t N, const double* xa1, int loss,
+                                       const double* b, const double* za0, double c, double* za1, double* z, double* r,
+                                       double* g, int bb, const double* x0, const double* xhat, const double* dx,
+                                       double tau, double* scal, void* ws, size_t ws_bytes, void* stream) {
+    if (!za0 || !za1) { set_error("dense_sweep_accel: za0 / za1 required"); return 1; }
+    return sweep_launch(A, lda, M, N, xa1, loss, b, z, r, g, bb, x0, xhat, dx, tau, scal, ws, ws_bytes, stream, za0, za1, c);
 }

@@ -50,6 +50,16 @@ class DenseDriver:
                                                _device.stream_ptr()), "fb200_dense_sweep")
         self.launches += 3
 
+    def sweep_accel(self, xa1, loss_tag, b, za0, c, za1, z, r, g, bb, x0, xhat, dx, tau, ws):
+        """FISTA mode of the single pass: za1 = A xa1, z = za1 + c (za1 - za0), r = gradf(z), g = A^T r;
+        S_F = f(za1) (line search), S_AUX3 = f(z)."""
+        _cabi.check(self.lib.fb200_dense_sweep_accel(self.A.data_ptr(), self.lda, self.M, self.N, xa1.data_ptr(), loss_tag,
+                                                     _device.ptr(b), za0.data_ptr(), float(c), za1.data_ptr(), z.data_ptr(),
+                                                     _device.ptr(r), _device.ptr(g), bb, _device.ptr(x0), _device.ptr(xhat),
+                                                     _device.ptr(dx), float(tau), ws.scal.data_ptr(), ws.buf.data_ptr(),
+                                                     ws.nbytes, _device.stream_ptr()), "fb200_dense_sweep_accel")
+        self.launches += 4
+
     def forward(self, x, loss_tag, b, z, r, ws):
         _cabi.check(self.lib.fb200_gemv_loss(self.A.data_ptr(), self.lda, self.M, self.N, x.data_ptr(), loss_tag,
                                              _device.ptr(b), z.data_ptr(), _device.ptr(r), ws.scal.data_ptr(),
@@ -293,6 +303,11 @@ class FusedBackend:
         # pass over A (the line search accepts the first trial in the vast majority of iterations;
         # a rejected trial costs exactly what the two-pass path would have paid for it).
         self.use_sweep = (not self.accelerate) and bool(getattr(driver, "sweep_ok", False))
+        # FISTA: the extrapolated z is a per-row function of A xa1 and the previous prox image, so the same single
+        # pass serves the accelerated mode once the restart decision (one scalar) is known
+        self.use_sweep_accel = (self.accelerate and bool(getattr(driver, "sweep_ok", False))
+                                and hasattr(driver, "sweep_accel") and loss.tag != S.LOSS_NONE
+                                and os.environ.get("FASTA_B200_SWEEP_ACCEL", "1") != "0")
         self._spec = None
         self._ahead = False
         self._pending = None
@@ -343,7 +358,7 @@ class FusedBackend:
         if hasattr(self.drv, "sync_probe"):
             self.drv.sync_probe(dst)
         d = self._probe_outputs()[k]
-        if self.use_sweep:
+        if self.use_sweep or self.use_sweep_accel:
             self.drv.sweep(dst, self.loss.tag, self.loss.b, self.Z, self.R, d, 0, None, None, None, 0.0, self.ws)
         else:
             self.drv.forward(dst, self.loss.tag, self.loss.b, self.Z, self.R, self.ws)
@@ -375,7 +390,7 @@ class FusedBackend:
 
     def _queue_start(self):
         z = self.ZA[self.ac] if self.accelerate else self.Z
-        if self.use_sweep:
+        if self.use_sweep or self.use_sweep_accel:
             self.drv.sweep(self.X[self.ic], self.loss.tag, self.loss.b, z, self.R, self.G[self.gc], 1, None, None, None,
                            0.0, self.ws)
         else:
@@ -446,6 +461,46 @@ class FusedBackend:
 
     def trial(self, tau):
         return self._collect_trial(self._queue_trial(tau))
+
+    def trial_accel(self, tau, alpha_prev, restart):
+        """One FISTA trial with the contractions in a single pass (reference :181-188 and :220-249): forward step and
+        prox, fetch the restart dot, form alpha / the extrapolation weight exactly as the host loop does, then queue
+        the x extrapolation and the sweep (z_accel1 = A x_accel1, extrapolated z, f at both, gradient, BB sums)."""
+        x0, g0 = self.X[self.ip], self.G[self.gp]
+        xa1, xa0 = self.XA[self.ac], self.XA[self.ap]
+        p0, p1 = self.pen.params(tau)
+        st = self._st()
+        if self.pen.tag == S.PROX_L1BALL:
+            _cabi.check(self.lib.fb200_forward_step(x0.data_ptr(), g0.data_ptr(), float(tau), self.n,
+                                                    self.XH.data_ptr(), st), "fb200_forward_step")
+            _cabi.check(self.lib.fb200_l1ball_threshold(self.XH.data_ptr(), self.n, float(self.pen.radius),
+                                                        self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
+                        "fb200_l1ball_threshold")
+            self.launches += 2
+        _cabi.check(self.lib.fb200_fbs_step(x0.data_ptr(), g0.data_ptr(), float(tau), self.pen.tag, float(p0), float(p1),
+                                            xa0.data_ptr(), self.n, self.XH.data_ptr(), xa1.data_ptr(),
+                                            self.DX.data_ptr(), self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
+                    "fb200_fbs_step")
+        self.launches += 1
+        s = self.ws.fetch()
+        step = Scalars(dx_g0=s[S.S_DX_G0].copy(), dx_sq=s[S.S_DX_SQ].copy(), restart=s[S.S_RESTART].copy())
+        alpha0 = alpha_prev                                          # reference :224-240
+        if restart and step.restart > 1E-30:
+            alpha0 = 1.0
+        alpha1 = (1 + np.sqrt(1 + 4 * alpha0 ** 2)) / 2
+        c = (alpha0 - 1) / alpha1
+        # x1 = x_accel1 + c (x_accel1 - x_accel0), |x1 - x1hat|^2, sum |x1|   (m = 0: the z part is the sweep's)
+        _cabi.check(self.lib.fb200_accel_step(float(c), xa1.data_ptr(), xa0.data_ptr(), self.XH.data_ptr(), self.n,
+                                              self.X[self.ic].data_ptr(), 0, 0, 0, 0, S.LOSS_NONE, self.pen.tag, 0, 0,
+                                              self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st), "fb200_accel_step")
+        self.launches += 1
+        self.drv.sweep_accel(xa1, self.loss.tag, self.loss.b, self.ZA[self.ap], c, self.ZA[self.ac], self.Z, self.R,
+                             self.G[self.gc], 2, x0, self.XH, self.DX, tau, self.ws)
+        s = self.ws.fetch()
+        self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
+        extrap = Scalars(f=self.loss.finalize(s[S.S_AUX3]), xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]))
+        return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=step.dx_g0, dx_sq=step.dx_sq, xmxh_sq=s[S.S_XMXH_SQ],
+                       pen=self.pen.value(s[S.S_PEN]), restart=step.restart, extrap=extrap)
 
     def trial_launch(self, tau):
         """Queue the next iteration's first trial; until trial_finish() the 'current' iterate is X[ip]."""

@@ -44,6 +44,8 @@ SIGNATURES = {
     "fb200_sweep_supported": (_int, [_p, _i64, _i64, _i64]),
     "fb200_sweep_plan": (_int, [_i64, _i64, ctypes.POINTER(ctypes.c_int)]),
     "fb200_dense_sweep": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _int, _p, _p, _p, _dbl, _p, _p, _sz, _p]),
+    "fb200_dense_sweep_accel": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _dbl, _p, _p, _p, _p, _int, _p, _p, _p, _dbl,
+                                      _p, _p, _sz, _p]),
     "fb200_gemm_f64": (_int, [_int, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _int, _i64, _p]),
     "fb200_gemm_splits": (_int, [_i64, _i64, _i64]),
     "fb200_ozaki_pad": (_i64, [_i64, _int]),

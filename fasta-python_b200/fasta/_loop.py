@@ -125,7 +125,8 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     # Back-ends that can queue a trial without waiting for it get the NEXT iteration's trial queued as soon as the
     # new step size is known (end of the loop body); histories, best-iterate copy and stop rule then run on the host
     # while the device works.  A trial queued before a stop is simply never collected.
-    run_ahead = hasattr(be, "trial_launch") and os.environ.get("FASTA_B200_RUN_AHEAD", "1") != "0"
+    fused_accel = accelerate and getattr(be, "use_sweep_accel", False)     # FISTA trial incl. extrapolation in one pass
+    run_ahead = hasattr(be, "trial_launch") and not fused_accel and os.environ.get("FASTA_B200_RUN_AHEAD", "1") != "0"
     queued = False
 
     i = 0
@@ -138,7 +139,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
             queued = False
         else:
             be.advance()                                    # ref :176-178
-            t = be.trial(tau0)                              # ref :181-188
+            t = be.trial_accel(tau0, alpha1, restart) if fused_accel else be.trial(tau0)   # ref :181-188
         f1 = t.f
 
         backtrack_count = 0
@@ -147,7 +148,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
             while f1 - (f_window_max + t.dx_g0 + _sq(t.dx_sq) / (2 * tau0)) > EPSILON \
                     and backtrack_count < max_backtracks:
                 tau0 *= stepsize_shrink
-                t = be.trial(tau0)
+                t = be.trial_accel(tau0, alpha1, restart) if fused_accel else be.trial(tau0)
                 f1 = t.f
                 backtrack_count += 1
             total_backtracks += backtrack_count
@@ -162,7 +163,8 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
                 if verbose:
                     print("Restarted acceleration.")
             alpha1 = (1 + np.sqrt(1 + 4 * alpha0 ** 2)) / 2
-            e = be.extrapolate((alpha0 - 1) / alpha1)
+            # fused FISTA trial: the accepted trial already extrapolated with this very weight
+            e = t.extrap if fused_accel else be.extrapolate((alpha0 - 1) / alpha1)
             f1, xmxh_sq, pen = e.f, e.xmxh_sq, e.pen
 
         gr = be.gradient(tau0, adaptive)                    # ref :248-249

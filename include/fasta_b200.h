@@ -142,6 +142,14 @@ int fb200_dense_sweep(const double* A, int64_t lda, int64_t M, int64_t N, const 
                       const double* xhat, const double* dx, double tau, double* scal, void* ws,
                       size_t ws_bytes, void* stream);
 
+/* the same single pass in FISTA (accelerated) mode, reference __init__.py:187-188,242-249: xa1 is the prox point,
+ * za1 = A xa1 its image (written), the gradient is taken at the extrapolated z = za1 + c (za1 - za0) (written to z,
+ * r = gradf(z)); scal[S_F] = f(za1) for the line search, scal[S_AUX3] = f(z); g and the BB epilogue as above   */
+int fb200_dense_sweep_accel(const double* A, int64_t lda, int64_t M, int64_t N, const double* xa1, int loss,
+                            const double* b, const double* za0, double c, double* za1, double* z, double* r,
+                            double* g, int bb, const double* x0, const double* xhat, const double* dx, double tau,
+                            double* scal, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K14: batched contractions (B columns, batch index fastest), fp64 DMMA GEMM -----------------
  * adjoint = 0:  C (Mg x Ng) = A (Mg x K) . B (K x Ng)         the per-column `A @ x`   of linalg.py:41
  * adjoint = 1:  C (Mg x Ng) = A^T . B with A stored (K x Mg)  the per-column `A.T @ r` of linalg.py:41

@@ -84,14 +84,30 @@ def test_tv_fused_is_default_for_non_accelerated():
     assert not fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3, accelerate=True).tv_fused
 
 
-def test_single_pass_is_default_for_dense_non_accelerated():
+def test_single_pass_is_default_for_dense_solves(monkeypatch):
     import fasta
     p = problems.build("lasso_200x1000_k10", 0)
     A, loss, pen = tagged(p)
     res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3)
     assert res.single_pass
     res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3, accelerate=True)
+    assert res.single_pass                                # FISTA mode of the sweep (extrapolated z formed per row)
+    monkeypatch.setenv("FASTA_B200_SWEEP_ACCEL", "0")
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3, accelerate=True)
     assert not res.single_pass
+
+
+@pytest.mark.parametrize("case", ["lasso_200x1000_k50", "logistic_1000x2000", "l1ball_200x1000", "lasso_333x1414_k40"])
+def test_accelerated_without_the_fused_fista_sweep_matches_golden(case, monkeypatch):
+    """Accelerated mode with the separate forward / extrapolate / adjoint kernels (the fused FISTA sweep is the default)."""
+    import fasta
+    monkeypatch.setenv("FASTA_B200_SWEEP_ACCEL", "0")
+    gold = load_golden(case, "accelerated")
+    p = problems.build(case, int(gold["seed"]))
+    A, loss, pen = tagged(p)
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert not res.single_pass
+    assert_trajectory(res, gold, label=f"accel-unfused/{case}")
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
