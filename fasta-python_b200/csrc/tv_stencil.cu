@@ -10,6 +10,8 @@
 // issued UNROLL rows ahead to keep >100 KB per SM in flight.  Outputs, the loss (r = gradf(z),
 // sum f) and the BB reductions are produced in the same pass, so an FBS iteration on an image
 // is three streaming kernels.  Compiled with -fmad=false (one rounding per numpy operation).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fb200 {
@@ -423,6 +425,105 @@ tv_iter_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, d
     grid_sum<7>(s, red, counter, out);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same whole iteration WITHOUT shared memory or block barriers: a warp owns 30 adjacent image columns
+// (lanes 1..30; lanes 0 and 31 carry the halo columns j0-1 and j0+30) and marches down a strip of rows.  The
+// prox point of row i+1 is computed while row i is finished, the vertical neighbours live in registers, the
+// horizontal ones come from the adjacent lane by shuffle; loads of the next TVM_UNROLL rows are issued before
+// the current rows are computed.  No barrier ever separates the fp64 sqrt/divide chains from the loads, which
+// is what bounded the tiled kernel above (3 phases per tile at 24 warps/SM).  Same expressions, same bits.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TVM_THREADS = 128, TVM_COLS = 30;
+
+template <int LOSS, int TVM_UNROLL, int MINB>
+__global__ void __launch_bounds__(TVM_THREADS, MINB)
+tv_iter_march_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, double tau, int n0, int n1,
+                     const double* __restrict__ b, double2* __restrict__ x1, double2* __restrict__ g1, int warps_x, int strip,
+                     double* scal, double* red, unsigned* counter) {
+    const int lane = threadIdx.x & 31;
+    const int wid  = blockIdx.x * (TVM_THREADS / 32) + (threadIdx.x >> 5);
+    const int wx = wid % warps_x, wy = wid / warps_x;
+    const int j  = wx * TVM_COLS - 1 + lane;                  // unwrapped column of this lane
+    const int jw = tv_wrap(j, n1);
+    const int i0 = wy * strip;
+    const int i1 = min(n0, i0 + strip);
+    const bool out_lane = lane >= 1 && lane <= TVM_COLS && j < n1;
+    double s[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (i0 < n0) {
+        auto point = [&](int i, double2& a, double2& gr) {    // x0, g0 at (wrapped) row i of this lane's column
+            const int64_t o = int64_t(tv_wrap(i, n0)) * n1 + jw;
+            a = x0[o];
+            gr = g0[o];
+        };
+        auto resid = [&](double2 c, double2 dn, int i) {      // r = div(y)(i, j) - b(i, j)
+            const double rty = __shfl_down_sync(0xffffffffu, c.y, 1);
+            const double zi = (dn.x - c.x) + (rty - c.y);
+            double rv, fv;
+            loss_elem<LOSS>(zi, b[int64_t(tv_wrap(i, n0)) * n1 + jw], rv, fv);
+            return make_double2(rv, fv);
+        };
+        double2 a_c, g_c, a_t, g_t, h;
+        point(i0 - 1, a_t, g_t);
+        const double2 y_m = tv_prox_point(a_t, g_t, tau, h);       // row i0-1
+        point(i0, a_c, g_c);
+        double2 y_c = tv_prox_point(a_c, g_c, tau, h);             // row i0
+        double r_up = resid(y_m, y_c, i0 - 1).x;                   // r(i0-1, j)
+        for (int ib = i0; ib < i1; ib += TVM_UNROLL) {
+            double2 an[TVM_UNROLL], gn[TVM_UNROLL];
+            double bb[TVM_UNROLL];
+#pragma unroll
+            for (int u = 0; u < TVM_UNROLL; ++u) {                 // rows ib+1 .. ib+UNROLL and b of rows ib .. ib+UNROLL-1
+                const int i = ib + u;
+                if (i < i1) {
+                    point(i + 1, an[u], gn[u]);
+                    bb[u] = b[int64_t(i) * n1 + jw];
+                } else {
+                    an[u] = gn[u] = make_double2(0.0, 0.0);
+                    bb[u] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < TVM_UNROLL; ++u) {
+                const int i = ib + u;
+                if (i >= i1) break;                                // warp-uniform
+                double2 hn;
+                const double2 y_n = tv_prox_point(an[u], gn[u], tau, hn);        // row i+1
+                const double rty = __shfl_down_sync(0xffffffffu, y_c.y, 1);
+                const double zi = (y_n.x - y_c.x) + (rty - y_c.y);
+                double rc, fc;
+                loss_elem<LOSS>(zi, bb[u], rc, fc);
+                const double r_left = __shfl_up_sync(0xffffffffu, rc, 1);
+                if (out_lane) {
+                    const int64_t o = int64_t(i) * n1 + j;
+                    double2 gi;
+                    gi.x = r_up - rc;
+                    gi.y = r_left - rc;
+                    x1[o] = y_c;
+                    g1[o] = gi;
+                    const double hx = a_c.x - tau * g_c.x, hy = a_c.y - tau * g_c.y;
+                    const double dxx = y_c.x - a_c.x, dxy = y_c.y - a_c.y, ex = y_c.x - hx, ey = y_c.y - hy;
+                    s[0] += dxx * g_c.x; s[0] += dxy * g_c.y;
+                    s[1] += dxx * dxx;   s[1] += dxy * dxy;
+                    s[2] += ex * ex;     s[2] += ey * ey;
+                    s[3] += fc;
+                    const double dg0 = gi.x + (hx - a_c.x) / tau;
+                    const double dg1 = gi.y + (hy - a_c.y) / tau;
+                    s[4] += dxx * dg0;   s[4] += dxy * dg1;
+                    s[5] += dg0 * dg0;   s[5] += dg1 * dg1;
+                    s[6] += gi.x * gi.x; s[6] += gi.y * gi.y;
+                }
+                r_up = rc;
+                y_c = y_n;
+                a_c = an[u];
+                g_c = gn[u];
+            }
+        }
+    }
+    double* const out[7] = {scal + FB200_S_DX_G0, scal + FB200_S_DX_SQ, scal + FB200_S_XMXH_SQ, scal + FB200_S_F,
+                            scal + FB200_S_DX_DG, scal + FB200_S_DG_SQ, scal + FB200_S_G1_SQ};
+    grid_sum<7>(s, red, counter, out);
+}
+
 static int tv_grid(int64_t n0, int64_t n1, dim3* grid, int* strip) {
     const int64_t gx = (n1 + TV_THREADS - 1) / TV_THREADS;
     int64_t st = TV_STRIP;
@@ -526,6 +627,31 @@ extern "C" int fb200_tv_iter_fused(const double* x0, const double* g0, double ta
     Workspace w(ws);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n0 < 1 || n1 < 1 || n0 > (1 << 30) || n1 > (1 << 30)) { set_error("tv_iter_fused: bad shape"); return 1; }
+    static int variant = -1;                // 0: register-marching kernel (default), 1: shared-memory tiles
+    if (variant < 0) {
+        const char* e = getenv("FASTA_B200_TV_TILED");
+        variant = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (variant == 0) {
+        const int64_t warps_x = (n1 + TVM_COLS - 1) / TVM_COLS;
+        int64_t strip = 64;
+        while ((warps_x * ((n0 + strip - 1) / strip) + 3) / 4 > MAX_RED_BLOCKS) strip *= 2;
+        const int64_t warps = warps_x * ((n0 + strip - 1) / strip);
+        const int64_t blocks = (warps + TVM_THREADS / 32 - 1) / (TVM_THREADS / 32);
+        if (blocks > MAX_RED_BLOCKS || warps_x > (1 << 24)) { set_error("tv_iter_fused: image too large"); return 1; }
+        static int mv = -1;                 // experiment knob: unroll depth / occupancy target of the marching kernel
+        if (mv < 0) { const char* e = getenv("FASTA_B200_TVM_VARIANT"); mv = e ? atoi(e) : 0; }
+#define TVM_LAUNCH(L, U, B) tv_iter_march_kernel<L, U, B><<<unsigned(blocks), TVM_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, int(n0), int(n1), b, (double2*)x1, (double2*)g1, int(warps_x), int(strip), scal, w.red, w.counter)
+#define TVM_PICK(L) switch (mv) { case 1: TVM_LAUNCH(L, 4, 6); break; case 2: TVM_LAUNCH(L, 8, 4); break; case 3: TVM_LAUNCH(L, 2, 8); break; default: TVM_LAUNCH(L, 4, 4); }
+        switch (loss) {
+            case FB200_LOSS_LEAST_SQUARES: TVM_PICK(FB200_LOSS_LEAST_SQUARES) break;
+            case FB200_LOSS_LOGISTIC: TVM_LAUNCH(FB200_LOSS_LOGISTIC, 4, 4); break;
+            default: set_error("tv_iter_fused: unsupported loss tag %d", loss); return 1;
+        }
+#undef TVM_PICK
+#undef TVM_LAUNCH
+        return check_launch("tv_iter_march");
+    }
     const int64_t tx = (n1 + TVI_TW - 1) / TVI_TW, ty = (n0 + TVI_TH - 1) / TVI_TH;
     if (tx * ty > (int64_t(1) << 30)) { set_error("tv_iter_fused: image too large"); return 1; }
     const int ntiles = int(tx * ty);
