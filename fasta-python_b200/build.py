@@ -30,6 +30,7 @@ UNITS = [
     ("batched_gemm.cu", []),
     ("ozaki_gemm.cu", []),
     ("batched_vector.cu", ["-fmad=false"]),
+    ("resident_loop.cu", ["-fmad=false"]),
 ]
 
 

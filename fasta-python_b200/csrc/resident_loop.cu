@@ -1,0 +1,317 @@
+// Device-resident FBS loop for SMALL dense problems (A fits the L2: BASELINE config 1, the reference's own
+// 200 x 1000 lasso and its relatives).
+//
+// At this size an iteration of the host-driven path is ~100 us of launch, sync and Python latency around
+// ~5 us of arithmetic.  Here the WHOLE loop of the reference (fasta/__init__.py:172-313: forward step, prox,
+// A x, f, non-monotone backtracking line search, A^T r, Barzilai-Borwein step size, residuals, best iterate,
+// stop rule) runs inside ONE cooperative kernel; the phases of an iteration are separated by grid-wide
+// barriers, every block forms every cross-block sum in the same fixed order and therefore takes the same
+// scalar decisions, and the histories are written to device arrays that the host reads once at the end.
+// Non-accelerated modes, built-in stop rules, elementwise prox (shrink / nonneg / box / identity).
+//
+// Compiled with -fmad=false: the elementwise lines and the scalar step-size algebra round once per numpy
+// operation of the reference line (np.float64 scalars are IEEE doubles); dot products use explicit fma().
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace fb200 {
+
+constexpr int RL_THREADS = 256;
+constexpr int RL_MAXK    = 4;
+
+struct ResidentArgs {
+    const double* A; int64_t lda; int M, N;
+    const double* b;
+    double* X[2]; double* G[2];          // ping-pong iterate / gradient; [0] holds the start point and its gradient
+    double *xhat, *dx, *best, *z, *r;
+    double* part;                        // [6][grid][RL_MAXK] per-block partial sums (two copies per phase)
+    double *resid_h, *nresid_h, *tau_h, *f_h, *obj_h;   // histories; f_h[0] / obj_h[0] preset by the host
+    int* bt_h;
+    unsigned long long* clock_h;         // %globaltimer at the start of every iteration and at exit
+    double* out;                         // [0] iterations, [1] total backtracks, [2] which buffer holds the last iterate
+    double tau_init, g1_sq_init, tolerance, shrink, pen_mu, p_lo, p_hi;
+    int adaptive, backtrack, window, max_backtracks, max_iters, stop_rule, evaluate_objective;
+};
+
+__device__ __forceinline__ unsigned long long rl_clock() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// sum of the per-block partials in block order, identical in every block; result broadcast to all threads
+template <int K>
+__device__ __forceinline__ void rl_collect(const double* part, int nblocks, double (&tot)[K], double* sm) {
+    if (threadIdx.x < 32) {
+        double acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.0;
+        for (int bk = threadIdx.x; bk < nblocks; bk += 32) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] += __ldcg(&part[bk * RL_MAXK + k]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            acc[k] = warp_sum(acc[k]);
+            if (threadIdx.x == 0) sm[k] = acc[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) tot[k] = sm[k];
+    __syncthreads();
+}
+
+template <int K>
+__device__ __forceinline__ void rl_publish(double (&v)[K], double* part, double* sm) {
+    block_sum<K>(v, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) part[blockIdx.x * RL_MAXK + k] = v[k];
+    }
+}
+
+__device__ __forceinline__ double rl_sq(double v) {          // la.norm(.)**2 = sqrt(dot)**2
+    const double t = sqrt(v);
+    return t * t;
+}
+__device__ __forceinline__ double rl_pymax(double a, double b) { return (b > a) ? b : a; }   // Python max(a, b)
+
+template <int LOSS, int PROX>
+__global__ void __launch_bounds__(RL_THREADS)
+resident_fbs_kernel(ResidentArgs p) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[RL_MAXK * 32 + RL_MAXK];
+    __shared__ double gsm[8][33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = gridDim.x;
+    const int gtid = blockIdx.x * RL_THREADS + tid, gthreads = nb * RL_THREADS;
+    const int gwarp = blockIdx.x * (RL_THREADS / 32) + warp, gwarps = nb * (RL_THREADS / 32);
+    const int M = p.M, N = p.N;
+    double* partA[2] = {p.part, p.part + size_t(nb) * RL_MAXK};
+    double* partB[2] = {p.part + 2 * size_t(nb) * RL_MAXK, p.part + 3 * size_t(nb) * RL_MAXK};
+    double* partC[2] = {p.part + 4 * size_t(nb) * RL_MAXK, p.part + 5 * size_t(nb) * RL_MAXK};
+    unsigned ua = 0, ub = 0, uc = 0;     // uses of each partial buffer (toggle the copy)
+
+    double tau1 = p.tau_init, g1_sq = p.g1_sq_init;
+    double max_residual = -INFINITY, best_q = INFINITY;
+    int cur = 0, it = 0;
+    long long total_bt = 0;
+
+    while (it < p.max_iters) {
+        if (gtid == 0) p.clock_h[it] = rl_clock();
+        const double* x0 = p.X[cur];
+        const double* g0 = p.G[cur];
+        double* x1 = p.X[1 - cur];
+        double* g1 = p.G[1 - cur];
+        const double g0_sq = g1_sq;
+        double tau0 = tau1;
+        int bt = 0;
+        double f_window_max = -INFINITY;
+        for (int k = (it - p.window + 1 > 0 ? it - p.window + 1 : 0); k <= it; ++k) f_window_max = fmax(f_window_max, __ldcg(&p.f_h[k]));
+        double dx_g0, dx_sq, xmxh_sq, pen_raw, f1;
+        while (true) {
+            // ---- forward step, prox, Dx and their sums (reference :181-186) ----
+            double s[4] = {0.0, 0.0, 0.0, 0.0};
+            const double p0 = (PROX == FB200_PROX_SHRINK) ? tau0 * p.pen_mu : p.p_lo;
+            for (int i = gtid; i < N; i += gthreads) {
+                const double a = __ldcg(&x0[i]), gr = __ldcg(&g0[i]);
+                const double h = a - tau0 * gr;
+                const double y = prox_elem<PROX>(h, p0, p.p_hi);
+                const double d = y - a;
+                p.xhat[i] = h;
+                x1[i] = y;
+                p.dx[i] = d;
+                s[0] += d * gr;
+                s[1] += d * d;
+                const double e = y - h;
+                s[2] += e * e;
+                s[3] += fabs(y);
+            }
+            rl_publish<4>(s, partA[ua & 1], sm);
+            grid.sync();
+            // ---- z = A x1, r = gradf(z), f (reference :187-188): one warp per row ----
+            double fs[1] = {0.0};
+            for (int row = gwarp; row < M; row += gwarps) {
+                const double* ar = p.A + int64_t(row) * p.lda;
+                double acc = 0.0;
+                for (int j = lane; j < N; j += 32) acc = fma(ar[j], __ldcg(&x1[j]), acc);
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    double ri, fi;
+                    loss_elem<LOSS>(acc, p.b[row], ri, fi);
+                    p.z[row] = acc;
+                    p.r[row] = ri;
+                    fs[0] += fi;
+                }
+            }
+            rl_publish<1>(fs, partB[ub & 1], sm);
+            grid.sync();
+            double ta[4], tb[1];
+            rl_collect<4>(partA[ua & 1], nb, ta, sm);
+            rl_collect<1>(partB[ub & 1], nb, tb, sm);
+            ++ua; ++ub;
+            dx_g0 = ta[0]; dx_sq = ta[1]; xmxh_sq = ta[2]; pen_raw = ta[3];
+            f1 = (LOSS == FB200_LOSS_LEAST_SQUARES) ? .5 * rl_sq(tb[0]) : tb[0];
+            // ---- non-monotone line search (reference :195-217) ----
+            if (p.backtrack && (f1 - (f_window_max + dx_g0 + rl_sq(dx_sq) / (2 * tau0)) > 1E-12) && bt < p.max_backtracks) {
+                tau0 *= p.shrink;
+                ++bt;
+                continue;
+            }
+            break;
+        }
+        total_bt += bt;
+        // ---- g1 = A^T r (reference :248): 32 columns x 8 row lanes per block pass, + BB sums (:254-260) ----
+        double sc[3] = {0.0, 0.0, 0.0};
+        for (int c0 = blockIdx.x * 32; c0 < N; c0 += nb * 32) {
+            const int col = c0 + lane;
+            double acc = 0.0;
+            if (col < N)
+                for (int row = warp; row < M; row += 8) acc = fma(p.A[int64_t(row) * p.lda + col], __ldcg(&p.r[row]), acc);
+            gsm[warp][lane] = acc;
+            __syncthreads();
+            if (warp == 0 && col < N) {
+                double gi = gsm[0][lane];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) gi += gsm[w][lane];
+                g1[col] = gi;
+                sc[2] += gi * gi;
+                if (p.adaptive) {
+                    const double dg = gi + (__ldcg(&p.xhat[col]) - __ldcg(&x0[col])) / tau0;
+                    sc[0] += __ldcg(&p.dx[col]) * dg;
+                    sc[1] += dg * dg;
+                }
+            }
+            __syncthreads();
+        }
+        rl_publish<3>(sc, partC[uc & 1], sm);
+        grid.sync();
+        double tc[3];
+        rl_collect<3>(partC[uc & 1], nb, tc, sm);
+        ++uc;
+        g1_sq = tc[2];
+        // ---- step-size algebra, residuals, histories (reference :253-300) ----
+        const double dx_norm = sqrt(dx_sq);
+        tau1 = tau0;
+        if (p.adaptive) {
+            const double dotprod = tc[0];
+            const double tau_s = (dx_norm * dx_norm) / dotprod;
+            const double q = dotprod / rl_sq(tc[1]);
+            const double tau_m = (0.0 > q) ? 0.0 : q;             // Python max(q, 0): a nan q stays
+            if (2 * tau_m > tau_s) tau1 = tau_m;
+            else tau1 = tau_s - .5 * tau_m;
+            if (tau1 <= 0 || isinf(tau1) || isnan(tau1)) tau1 = tau0 * 1.5;
+        }
+        const double resid = dx_norm / tau0;
+        const double normalizer = rl_pymax(sqrt(g0_sq), sqrt(xmxh_sq) / tau0) + 1E-12;
+        const double nresid = resid / normalizer;
+        max_residual = rl_pymax(max_residual, resid);
+        const double objective = f1 + ((PROX == FB200_PROX_SHRINK) ? p.pen_mu * pen_raw : 0.0);
+        const double quality = p.evaluate_objective ? objective : resid;
+        if (gtid == 0) {
+            p.resid_h[it] = resid;
+            p.nresid_h[it] = nresid;
+            p.tau_h[it] = tau0;
+            p.f_h[it + 1] = f1;
+            if (p.evaluate_objective) p.obj_h[it + 1] = objective;
+            p.bt_h[it] = bt;
+        }
+        if (quality < best_q) {
+            for (int i = gtid; i < N; i += gthreads) p.best[i] = __ldcg(&x1[i]);
+            best_q = quality;
+        }
+        bool stop;
+        switch (p.stop_rule) {
+            case 0: stop = resid < p.tolerance; break;
+            case 1: stop = nresid < p.tolerance; break;
+            case 2: stop = resid / max_residual < p.tolerance; break;
+            default: stop = (resid / max_residual < p.tolerance) || (nresid < p.tolerance); break;
+        }
+        cur = 1 - cur;
+        ++it;
+        // f_h[it] must be visible to every block before the next window maximum; the partial buffers and
+        // xhat / dx / z / r are protected by the two barriers of the next trial
+        grid.sync();
+        if (stop) break;
+    }
+    if (gtid == 0) {
+        p.clock_h[it] = rl_clock();
+        p.out[0] = double(it);
+        p.out[1] = double(total_bt);
+        p.out[2] = double(cur);
+    }
+}
+
+typedef void (*ResidentKernel)(ResidentArgs);
+
+template <int LOSS>
+static ResidentKernel resident_pick(int prox) {
+    switch (prox) {
+        case FB200_PROX_SHRINK: return resident_fbs_kernel<LOSS, FB200_PROX_SHRINK>;
+        case FB200_PROX_NONNEG: return resident_fbs_kernel<LOSS, FB200_PROX_NONNEG>;
+        case FB200_PROX_BOX: return resident_fbs_kernel<LOSS, FB200_PROX_BOX>;
+        case FB200_PROX_IDENTITY: return resident_fbs_kernel<LOSS, FB200_PROX_IDENTITY>;
+        default: return nullptr;
+    }
+}
+
+}  // namespace fb200
+
+using namespace fb200;
+
+// blocks the resident loop would use for an M x N problem (0 = not eligible: too large for the L2, or the
+// device cannot co-schedule the grid)
+extern "C" int fb200_resident_blocks(int64_t M, int64_t N) {
+    if (M < 1 || N < 1 || M > (1 << 24) || N > (1 << 24) || M * N * 8 > (int64_t(48) << 20)) return 0;
+    int64_t want = (M + 7) / 8;                       // one warp per row
+    if ((N + 31) / 32 > want) want = (N + 31) / 32;   // 32 columns per block pass
+    const int cap = sm_count();
+    return int(want < cap ? want : cap);
+}
+
+extern "C" size_t fb200_resident_scratch_doubles(int64_t M, int64_t N) {
+    const int nb = fb200_resident_blocks(M, N);
+    return size_t(6) * size_t(nb > 0 ? nb : 1) * RL_MAXK;
+}
+
+// One launch = the whole solve after the prologue.  Pointers as in ResidentArgs; stop_rule 0..3 = residual,
+// norm_residual, ratio_residual, hybrid_residual (reference stopping.py:15,27,39,51).
+extern "C" int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64_t N, const double* b, int loss, int prox,
+                                  double pen_mu, double p_lo, double p_hi, double* x_a, double* x_b, double* g_a, double* g_b,
+                                  double* xhat, double* dx, double* best, double* z, double* r, double* part,
+                                  double* resid_h, double* nresid_h, double* tau_h, double* f_h, double* obj_h, int* bt_h,
+                                  unsigned long long* clock_h, double* out, double tau_init, double g1_sq_init,
+                                  double tolerance, double shrink, int adaptive, int backtrack, int window,
+                                  int max_backtracks, int max_iters, int stop_rule, int evaluate_objective, void* stream) {
+    const int nb = fb200_resident_blocks(M, N);
+    if (nb < 1) { set_error("resident_fbs: problem not eligible"); return 1; }
+    ResidentKernel k = nullptr;
+    if (loss == FB200_LOSS_LEAST_SQUARES) k = resident_pick<FB200_LOSS_LEAST_SQUARES>(prox);
+    else if (loss == FB200_LOSS_LOGISTIC) k = resident_pick<FB200_LOSS_LOGISTIC>(prox);
+    if (!k) { set_error("resident_fbs: unsupported loss / prox tags %d / %d", loss, prox); return 1; }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, RL_THREADS, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        set_error("resident_fbs: occupancy query failed");
+        return 1;
+    }
+    ResidentArgs a{};
+    a.A = A; a.lda = lda; a.M = int(M); a.N = int(N); a.b = b;
+    a.X[0] = x_a; a.X[1] = x_b; a.G[0] = g_a; a.G[1] = g_b;
+    a.xhat = xhat; a.dx = dx; a.best = best; a.z = z; a.r = r; a.part = part;
+    a.resid_h = resid_h; a.nresid_h = nresid_h; a.tau_h = tau_h; a.f_h = f_h; a.obj_h = obj_h; a.bt_h = bt_h;
+    a.clock_h = clock_h; a.out = out;
+    a.tau_init = tau_init; a.g1_sq_init = g1_sq_init; a.tolerance = tolerance; a.shrink = shrink;
+    a.pen_mu = pen_mu; a.p_lo = p_lo; a.p_hi = p_hi;
+    a.adaptive = adaptive; a.backtrack = backtrack; a.window = window; a.max_backtracks = max_backtracks;
+    a.max_iters = max_iters; a.stop_rule = stop_rule; a.evaluate_objective = evaluate_objective;
+    void* params[1] = {&a};
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k), dim3(unsigned(nb)), dim3(RL_THREADS), params, 0,
+                                                static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) { set_error("resident_fbs: cooperative launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 1; }
+    return 0;
+}

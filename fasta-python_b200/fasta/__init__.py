@@ -25,7 +25,7 @@ There is no CPU fallback: without a CUDA device or the built library, fasta() ra
 import numpy as np
 
 from . import linalg, losses, proximal, stopping, tv
-from . import _cabi, _device
+from . import _cabi, _device, _resident
 from ._loop import Convergence, EPSILON, run as _run
 
 __all__ = ["fasta", "Convergence", "EPSILON", "linalg", "losses", "proximal", "stopping", "tv"]
@@ -161,13 +161,17 @@ def fasta(*args, **kwargs) -> Convergence:
                        opts.get("evaluate_objective", False))
     try:
         be.load()
-        result = _run(be, tuple(x0.shape), **opts)
+        if _resident.eligible(be, opts):
+            result = _resident.run(be, tuple(x0.shape), **opts)      # small problem: the whole loop in one kernel
+        else:
+            result = _run(be, tuple(x0.shape), **opts)
     finally:
         if hasattr(be, "close"):
             be.close()
     result.backend = type(be).__name__
     result.single_pass = bool(getattr(be, "use_sweep", False) or getattr(be, "use_sweep_accel", False))
     result.tv_fused = bool(getattr(be, "use_tv_fused", False))
+    result.resident = bool(getattr(result, "resident", False))
     result.kernel_launches = be.total_launches()
     result.peer_reductions = int(getattr(getattr(be, "drv", None), "peer_reductions", 0))   # fused NVLink all-reduce + BB calls
     return result

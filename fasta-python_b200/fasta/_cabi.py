@@ -46,6 +46,10 @@ SIGNATURES = {
     "fb200_dense_sweep": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _int, _p, _p, _p, _dbl, _p, _p, _sz, _p]),
     "fb200_dense_sweep_accel": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _dbl, _p, _p, _p, _p, _int, _p, _p, _p, _dbl,
                                       _p, _p, _sz, _p]),
+    "fb200_resident_blocks": (_int, [_i64, _i64]),
+    "fb200_resident_scratch_doubles": (_sz, [_i64, _i64]),
+    "fb200_resident_fbs": (_int, [_p, _i64, _i64, _i64, _p, _int, _int, _dbl, _dbl, _dbl] + [_p] * 18 +
+                           [_dbl, _dbl, _dbl, _dbl, _int, _int, _int, _int, _int, _int, _int, _p]),
     "fb200_gemm_f64": (_int, [_int, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _int, _i64, _p]),
     "fb200_gemm_splits": (_int, [_i64, _i64, _i64]),
     "fb200_ozaki_pad": (_i64, [_i64, _int]),

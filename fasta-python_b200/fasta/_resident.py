@@ -1,0 +1,109 @@
+"""Device-resident solve for small dense problems: the prologue as in ``_loop.run``, then the WHOLE
+forward-backward-splitting loop (reference ``fasta/__init__.py:172-313``) in one cooperative kernel
+(``fb200_resident_fbs``, csrc/resident_loop.cu) -- no host round trip per iteration.
+
+Used by ``fasta.fasta`` when the problem is eligible: dense tagged operator that fits the L2, tagged loss and
+elementwise penalty, non-accelerated mode, a built-in stop rule, no per-iterate hooks.  Everything else takes the
+host-driven loop.  ``FASTA_B200_RESIDENT=0`` disables it.
+"""
+
+import os
+from time import time
+
+import numpy as np
+
+from . import _cabi, _device, stopping
+from ._loop import Convergence
+
+_RULES = {stopping.residual: 0, stopping.norm_residual: 1, stopping.ratio_residual: 2, stopping.hybrid_residual: 3}
+_PROX_OK = (_cabi.PROX_SHRINK, _cabi.PROX_NONNEG, _cabi.PROX_BOX, _cabi.PROX_IDENTITY)
+
+
+def eligible(be, opts):
+    from . import _backends
+    if os.environ.get("FASTA_B200_RESIDENT", "1") == "0":
+        return False
+    if not isinstance(be, _backends.FusedBackend) or not isinstance(be.drv, _backends.DenseDriver):
+        return False
+    if opts.get("accelerate", False) or opts.get("record_iterates", False) or opts.get("func", None) is not None:
+        return False
+    if opts.get("stop_rule", stopping.hybrid_residual) not in _RULES:
+        return False
+    if be.loss.tag not in (_cabi.LOSS_LEAST_SQUARES, _cabi.LOSS_LOGISTIC) or be.pen.tag not in _PROX_OK:
+        return False
+    if be.pen.tag == _cabi.PROX_SHRINK and np.ndim(be.pen.mu) != 0:
+        return False
+    if opts.get("max_iters", 1000) < 1:
+        return False
+    return int(_cabi.load().fb200_resident_blocks(be.drv.M, be.drv.N)) > 0
+
+
+def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iters=1000, tolerance=1e-5,
+        stop_rule=stopping.hybrid_residual, L=None, tau0=None, backtrack=True, stepsize_shrink=None,
+        window=10, max_backtracks=20, restart=True, evaluate_objective=False, record_iterates=False,
+        func=None) -> Convergence:
+    t = _device.torch()
+    lib = _cabi.load()
+    S = _cabi
+    if stepsize_shrink is None and backtrack:               # ref :92-97
+        stepsize_shrink = 0.2 if adaptive else 0.5
+    if not L or not tau0:                                   # ref :100-113, pipelined as in _loop.run
+        be.start_async()
+        be.lipschitz_push(0, np.random.randn(*x0_shape))
+        be.lipschitz_push(1, np.random.randn(*x0_shape))
+        dgrad, dpoint = be.lipschitz_finish()
+        L = dgrad / dpoint
+        tau0 = (2 / L) / 10
+    if not tau0:
+        tau0 = 1 / L
+    if verbose:                                             # ref :118-120
+        print("Initializing FASTA...\n")
+        print("Iteration #\tResidual\tStepsize\tAccel. param\tBacktracks\tObjective")
+
+    s = be.start()                                          # ref :135-143
+    dev = be.X[0].device
+    f64 = lambda n: t.zeros(n, dtype=t.float64, device=dev)
+    resid_d, nresid_d, tau_d = f64(max_iters), f64(max_iters), f64(max_iters)
+    f_d, obj_d = f64(max_iters + 1), f64(max_iters + 1)
+    bt_d = t.zeros(max_iters, dtype=t.int32, device=dev)
+    clk_d = t.zeros(max_iters + 1, dtype=t.int64, device=dev)
+    out_d = f64(4)
+    part = t.empty(int(lib.fb200_resident_scratch_doubles(be.drv.M, be.drv.N)), dtype=t.float64, device=dev)
+    head = np.array([s.f, (s.f + s.pen) if evaluate_objective else 0.0])
+    f_d[0:1].copy_(t.from_numpy(head[0:1]))
+    obj_d[0:1].copy_(t.from_numpy(head[1:2]))
+
+    pen = be.pen
+    mu = float(pen.mu) if pen.tag == S.PROX_SHRINK else 0.0
+    lo, hi = (float(pen.lo), float(pen.hi)) if pen.tag == S.PROX_BOX else (0.0, 0.0)
+    xa, xb = be.X[be.ic], be.X[1 - be.ic]
+    ga, gb = be.G[be.gc], be.G[1 - be.gc]
+    t_launch = time()
+    _cabi.check(lib.fb200_resident_fbs(
+        be.drv.A.data_ptr(), be.drv.lda, be.drv.M, be.drv.N, be.loss.b.data_ptr(), be.loss.tag, pen.tag, mu, lo, hi,
+        xa.data_ptr(), xb.data_ptr(), ga.data_ptr(), gb.data_ptr(), be.XH.data_ptr(), be.DX.data_ptr(), be.BEST.data_ptr(),
+        be.Z.data_ptr(), be.R.data_ptr(), part.data_ptr(), resid_d.data_ptr(), nresid_d.data_ptr(), tau_d.data_ptr(),
+        f_d.data_ptr(), obj_d.data_ptr(), bt_d.data_ptr(), clk_d.data_ptr(), out_d.data_ptr(), float(tau0), float(s.g_sq),
+        float(tolerance), float(stepsize_shrink if stepsize_shrink is not None else 1.0), int(bool(adaptive)),
+        int(bool(backtrack)), int(window), int(max_backtracks), int(max_iters), _RULES[stop_rule],
+        int(bool(evaluate_objective)), _device.stream_ptr()), "fb200_resident_fbs")
+    be.launches += 1
+    out = out_d.cpu().numpy()                               # the one sync of the solve
+    n = int(out[0])
+    if int(out[2]) != 0:                                    # the kernel rotated the buffers an odd number of times
+        be.ic, be.ip = 1 - be.ic, be.ic
+    residual_hist, norm_residual_hist, tau_hist = (v.cpu().numpy() for v in (resid_d, nresid_d, tau_d))
+    objective_hist = obj_d.cpu().numpy() if evaluate_objective else None
+    clk = clk_d.cpu().numpy().astype(np.float64)
+    times = np.zeros(max_iters + 1)
+    times[:n + 1] = t_launch + (clk[:n + 1] - clk[0]) * 1e-9     # %globaltimer stamps mapped onto the host clock
+    if verbose:                                             # ref :302-306, printed after the fact
+        bts = bt_d.cpu().numpy()
+        for i in range(n):
+            print("[{:<6}]\t{:e}\t{:e}\t{:e}\t{:6}\t{:e}".format(
+                i, residual_hist[i], tau_hist[i], 0.0, int(bts[i]) if backtrack else 0,
+                objective_hist[i] if evaluate_objective else 0))
+    res = Convergence(residual_hist, norm_residual_hist, tau_hist, int(out[1]), times, n, be.solution(),
+                      objective_hist, None, None)
+    res.resident = True
+    return res

@@ -150,6 +150,24 @@ int fb200_dense_sweep_accel(const double* A, int64_t lda, int64_t M, int64_t N, 
                             double* g, int bb, const double* x0, const double* xhat, const double* dx, double tau,
                             double* scal, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- device-resident FBS loop for small dense problems (csrc/resident_loop.cu) -------------------------
+ * The whole loop of reference __init__.py:172-313 (non-accelerated modes, built-in stop rules 0..3 =
+ * stopping.residual / norm_residual / ratio_residual / hybrid_residual, elementwise prox) in ONE cooperative
+ * kernel: no host round trip per iteration.  x_a / g_a hold the start point and its gradient, f_h[0] (and
+ * obj_h[0]) the start values; histories, per-iteration backtrack counts and %globaltimer stamps are device arrays
+ * of max_iters (+1) entries; out[0..2] = iterations, total backtracks, index of the buffer with the last iterate;
+ * best receives the best iterate.  fb200_resident_blocks returns 0 when the problem is not eligible (A must fit
+ * the L2); part: fb200_resident_scratch_doubles(M, N) doubles.                                              */
+int fb200_resident_blocks(int64_t M, int64_t N);
+size_t fb200_resident_scratch_doubles(int64_t M, int64_t N);
+int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64_t N, const double* b, int loss, int prox,
+                       double pen_mu, double p_lo, double p_hi, double* x_a, double* x_b, double* g_a, double* g_b,
+                       double* xhat, double* dx, double* best, double* z, double* r, double* part,
+                       double* resid_h, double* nresid_h, double* tau_h, double* f_h, double* obj_h, int* bt_h,
+                       unsigned long long* clock_h, double* out, double tau_init, double g1_sq_init,
+                       double tolerance, double shrink, int adaptive, int backtrack, int window,
+                       int max_backtracks, int max_iters, int stop_rule, int evaluate_objective, void* stream);
+
 /* ---- K14: batched contractions (B columns, batch index fastest), fp64 DMMA GEMM -----------------
  * adjoint = 0:  C (Mg x Ng) = A (Mg x K) . B (K x Ng)         the per-column `A @ x`   of linalg.py:41
  * adjoint = 1:  C (Mg x Ng) = A^T . B with A stored (K x Mg)  the per-column `A.T @ r` of linalg.py:41

@@ -37,6 +37,73 @@ def test_fused_path_matches_golden(case, mode):
     assert_trajectory(res, gold, label=f"{case}/{mode}")
 
 
+SMALL_DENSE = ("lasso_200x1000_k10", "lasso_200x1000_k50", "lasso_333x1414_k40", "nnls_200x1000", "logistic_1000x2000")
+
+
+@pytest.mark.parametrize("case,mode", [cm for cm in golden_cases(prefixes=SMALL_DENSE) if cm[1] != "accelerated"])
+def test_device_resident_loop_matches_golden(case, mode):
+    """Small dense problems run the whole loop in one cooperative kernel (csrc/resident_loop.cu)."""
+    import fasta
+    gold = load_golden(case, mode)
+    p = problems.build(case, int(gold["seed"]))
+    A, loss, pen = tagged(p)
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert res.resident and res.backend == "FusedBackend"
+    assert_trajectory(res, gold, label=f"resident/{case}/{mode}")
+    n = res.iteration_count
+    assert np.all(np.diff(res.times[:n + 1]) >= 0) and res.times[n] > res.times[0]
+
+
+@pytest.mark.parametrize("case,mode", [cm for cm in golden_cases(prefixes=SMALL_DENSE) if cm[1] != "accelerated"])
+def test_host_driven_loop_matches_golden_on_small_problems(case, mode, monkeypatch):
+    """The same cases with the device-resident loop disabled (host loop + single-pass sweep)."""
+    import fasta
+    monkeypatch.setenv("FASTA_B200_RESIDENT", "0")
+    gold = load_golden(case, mode)
+    p = problems.build(case, int(gold["seed"]))
+    A, loss, pen = tagged(p)
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert not res.resident and res.single_pass
+    assert_trajectory(res, gold, label=f"host-loop/{case}/{mode}")
+
+
+def test_device_resident_loop_options(capsys):
+    """Other stop rules, no backtracking, no objective, verbose lines, user-supplied L / tau0."""
+    import fasta
+    from oracle import fasta_oracle
+    p = problems.build("lasso_200x1000_k50", 0)
+    A, loss, pen = tagged(p)
+    f, gradf, g, proxg = problems.numpy_callables(p)
+    for opts in (dict(stop_rule_name="residual", tolerance=1e-3), dict(stop_rule_name="norm_residual", tolerance=1e-4),
+                 dict(stop_rule_name="ratio_residual", tolerance=1e-4), dict(backtrack=False, adaptive=False, max_iters=50),
+                 dict(L=1.3, tau0=0.11, max_iters=40, evaluate_objective=False), dict(window=3, stepsize_shrink=0.5, max_iters=60)):
+        o = dict(verbose=False, evaluate_objective=True)
+        o.update(opts)
+        name = o.pop("stop_rule_name", None)
+        o_ref = dict(o)
+        if name:
+            o["stop_rule"] = getattr(fasta.stopping, name)
+            o_ref["stop_rule"] = getattr(fasta_oracle, "stop_" + name)
+        np.random.seed(5)
+        res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **o)
+        np.random.seed(5)
+        ref = fasta_oracle.solve(lambda x: p.A @ x, lambda y: p.A.T @ y, f, gradf, g, proxg, p.x0, **o_ref)
+        assert res.resident
+        assert (res.iteration_count, res.backtracks) == (ref.iteration_count, ref.backtracks), opts
+        n = ref.iteration_count
+        assert np.linalg.norm(res.solution - ref.solution) <= 1e-9 * np.linalg.norm(ref.solution)
+        assert np.allclose(res.stepsizes[:n], ref.stepsizes[:n], rtol=1e-6, atol=0)
+        assert np.all(res.residuals[n:] == 0)
+        if o["evaluate_objective"]:
+            assert np.max(np.abs(res.objectives[:n + 1] - ref.objectives[:n + 1]) / np.abs(ref.objectives[:n + 1])) <= 1e-10
+        else:
+            assert res.objectives is None
+    capsys.readouterr()
+    fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, max_iters=3, evaluate_objective=True)      # verbose default
+    outp = capsys.readouterr().out
+    assert outp.startswith("Initializing FASTA...\n\nIteration #\tResidual") and outp.count("\n[") == 3
+
+
 @pytest.mark.parametrize("case,mode", golden_cases(prefixes=("lasso_200x1000_k50", "logistic", "lasso_333", "l1ball")))
 def test_two_pass_path_matches_golden(case, mode, monkeypatch):
     """Same parity bar with the single-pass sweep disabled (separate A x and A^T r kernels)."""
