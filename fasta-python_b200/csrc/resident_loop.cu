@@ -7,7 +7,7 @@
 // stop rule) runs inside ONE cooperative kernel; the phases of an iteration are separated by grid-wide
 // barriers, every block forms every cross-block sum in the same fixed order and therefore takes the same
 // scalar decisions, and the histories are written to device arrays that the host reads once at the end.
-// Non-accelerated modes, built-in stop rules, elementwise prox (shrink / nonneg / box / identity).
+// All three modes (plain, adaptive, FISTA), built-in stop rules, elementwise prox (shrink / nonneg / box / identity).
 //
 // Compiled with -fmad=false: the elementwise lines and the scalar step-size algebra round once per numpy
 // operation of the reference line (np.float64 scalars are IEEE doubles); dot products use explicit fma().
@@ -20,20 +20,22 @@ namespace cg = cooperative_groups;
 namespace fb200 {
 
 constexpr int RL_THREADS = 256;
-constexpr int RL_MAXK    = 4;
+constexpr int RL_MAXK    = 5;
 
 struct ResidentArgs {
     const double* A; int64_t lda; int M, N;
     const double* b;
     double* X[2]; double* G[2];          // ping-pong iterate / gradient; [0] holds the start point and its gradient
+    double* XA[2]; double* ZA[2];        // FISTA: prox points and their images; [0] = start point and A x0
     double *xhat, *dx, *best, *z, *r;
     double* part;                        // [6][grid][RL_MAXK] per-block partial sums (two copies per phase)
     double *resid_h, *nresid_h, *tau_h, *f_h, *obj_h;   // histories; f_h[0] / obj_h[0] preset by the host
-    int* bt_h;
+    int* bt_h;                           // backtracks per iteration; bit 30 set = acceleration restarted
+    double* alpha_h;                     // FISTA: alpha0 per iteration (verbose line)
     unsigned long long* clock_h;         // %globaltimer at the start of every iteration and at exit
     double* out;                         // [0] iterations, [1] total backtracks, [2] which buffer holds the last iterate
     double tau_init, g1_sq_init, tolerance, shrink, pen_mu, p_lo, p_hi;
-    int adaptive, backtrack, window, max_backtracks, max_iters, stop_rule, evaluate_objective;
+    int adaptive, backtrack, window, max_backtracks, max_iters, stop_rule, evaluate_objective, restart;
 };
 
 __device__ __forceinline__ unsigned long long rl_clock() {
@@ -80,7 +82,7 @@ __device__ __forceinline__ double rl_sq(double v) {          // la.norm(.)**2 = 
 }
 __device__ __forceinline__ double rl_pymax(double a, double b) { return (b > a) ? b : a; }   // Python max(a, b)
 
-template <int LOSS, int PROX>
+template <int LOSS, int PROX, bool ACCEL>
 __global__ void __launch_bounds__(RL_THREADS)
 resident_fbs_kernel(ResidentArgs p) {
     cg::grid_group grid = cg::this_grid();
@@ -94,7 +96,10 @@ resident_fbs_kernel(ResidentArgs p) {
     double* partA[2] = {p.part, p.part + size_t(nb) * RL_MAXK};
     double* partB[2] = {p.part + 2 * size_t(nb) * RL_MAXK, p.part + 3 * size_t(nb) * RL_MAXK};
     double* partC[2] = {p.part + 4 * size_t(nb) * RL_MAXK, p.part + 5 * size_t(nb) * RL_MAXK};
-    unsigned ua = 0, ub = 0, uc = 0;     // uses of each partial buffer (toggle the copy)
+    double* partE[2] = {p.part + 6 * size_t(nb) * RL_MAXK, p.part + 7 * size_t(nb) * RL_MAXK};
+    unsigned ua = 0, ub = 0, uc = 0, ue = 0;     // uses of each partial buffer (toggle the copy)
+    double alpha1 = 1.0;                 // reference :157
+    int acur = 0;                        // XA[acur] / ZA[acur]: previous prox point and its image
 
     double tau1 = p.tau_init, g1_sq = p.g1_sq_init;
     double max_residual = -INFINITY, best_q = INFINITY;
@@ -112,49 +117,52 @@ resident_fbs_kernel(ResidentArgs p) {
         int bt = 0;
         double f_window_max = -INFINITY;
         for (int k = (it - p.window + 1 > 0 ? it - p.window + 1 : 0); k <= it; ++k) f_window_max = fmax(f_window_max, __ldcg(&p.f_h[k]));
-        double dx_g0, dx_sq, xmxh_sq, pen_raw, f1;
+        double dx_g0, dx_sq, xmxh_sq, pen_raw, f1, restart_dot = 0.0;
         while (true) {
             // ---- forward step, prox, Dx and their sums (reference :181-186) ----
-            double s[4] = {0.0, 0.0, 0.0, 0.0};
+            double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             const double p0 = (PROX == FB200_PROX_SHRINK) ? tau0 * p.pen_mu : p.p_lo;
+            double* xp = ACCEL ? p.XA[1 - acur] : x1;             // the prox point (x_accel1 when accelerating)
             for (int i = gtid; i < N; i += gthreads) {
                 const double a = __ldcg(&x0[i]), gr = __ldcg(&g0[i]);
                 const double h = a - tau0 * gr;
                 const double y = prox_elem<PROX>(h, p0, p.p_hi);
                 const double d = y - a;
                 p.xhat[i] = h;
-                x1[i] = y;
+                xp[i] = y;
                 p.dx[i] = d;
                 s[0] += d * gr;
                 s[1] += d * d;
                 const double e = y - h;
                 s[2] += e * e;
                 s[3] += fabs(y);
+                if (ACCEL) s[4] += (a - y) * (y - __ldcg(&p.XA[acur][i]));      // restart test, reference :231
             }
-            rl_publish<4>(s, partA[ua & 1], sm);
+            rl_publish<5>(s, partA[ua & 1], sm);
             grid.sync();
             // ---- z = A x1, r = gradf(z), f (reference :187-188): one warp per row ----
             double fs[1] = {0.0};
+            double* zp = ACCEL ? p.ZA[1 - acur] : p.z;
             for (int row = gwarp; row < M; row += gwarps) {
                 const double* ar = p.A + int64_t(row) * p.lda;
                 double acc = 0.0;
-                for (int j = lane; j < N; j += 32) acc = fma(ar[j], __ldcg(&x1[j]), acc);
+                for (int j = lane; j < N; j += 32) acc = fma(ar[j], __ldcg(&xp[j]), acc);
                 acc = warp_sum(acc);
                 if (lane == 0) {
                     double ri, fi;
                     loss_elem<LOSS>(acc, p.b[row], ri, fi);
-                    p.z[row] = acc;
-                    p.r[row] = ri;
+                    zp[row] = acc;
+                    if (!ACCEL) p.r[row] = ri;
                     fs[0] += fi;
                 }
             }
             rl_publish<1>(fs, partB[ub & 1], sm);
             grid.sync();
-            double ta[4], tb[1];
-            rl_collect<4>(partA[ua & 1], nb, ta, sm);
+            double ta[5], tb[1];
+            rl_collect<5>(partA[ua & 1], nb, ta, sm);
             rl_collect<1>(partB[ub & 1], nb, tb, sm);
             ++ua; ++ub;
-            dx_g0 = ta[0]; dx_sq = ta[1]; xmxh_sq = ta[2]; pen_raw = ta[3];
+            dx_g0 = ta[0]; dx_sq = ta[1]; xmxh_sq = ta[2]; pen_raw = ta[3]; restart_dot = ta[4];
             f1 = (LOSS == FB200_LOSS_LEAST_SQUARES) ? .5 * rl_sq(tb[0]) : tb[0];
             // ---- non-monotone line search (reference :195-217) ----
             if (p.backtrack && (f1 - (f_window_max + dx_g0 + rl_sq(dx_sq) / (2 * tau0)) > 1E-12) && bt < p.max_backtracks) {
@@ -165,6 +173,46 @@ resident_fbs_kernel(ResidentArgs p) {
             break;
         }
         total_bt += bt;
+        double alpha0 = 0.0;
+        bool restarted = false;
+        if (ACCEL) {
+            // ---- FISTA extrapolation of x and z, f at the extrapolated z (reference :220-245) ----
+            alpha0 = alpha1;
+            if (p.restart && restart_dot > 1E-30) { alpha0 = 1.0; restarted = true; }
+            alpha1 = (1 + sqrt(1 + 4 * (alpha0 * alpha0))) / 2;
+            const double c = (alpha0 - 1) / alpha1;
+            const double* xa1 = p.XA[1 - acur];
+            const double* xa0 = p.XA[acur];
+            const double* za1 = p.ZA[1 - acur];
+            const double* za0 = p.ZA[acur];
+            double se[3] = {0.0, 0.0, 0.0};
+            for (int i = gtid; i < N; i += gthreads) {
+                const double q = __ldcg(&xa1[i]);
+                const double y = q + c * (q - __ldcg(&xa0[i]));
+                x1[i] = y;
+                const double e = y - __ldcg(&p.xhat[i]);
+                se[1] += e * e;
+                se[2] += fabs(y);
+            }
+            for (int row = gtid; row < M; row += gthreads) {
+                const double q = __ldcg(&za1[row]);
+                const double zz = q + c * (q - __ldcg(&za0[row]));
+                double ri, fi;
+                loss_elem<LOSS>(zz, p.b[row], ri, fi);
+                p.z[row] = zz;
+                p.r[row] = ri;
+                se[0] += fi;
+            }
+            rl_publish<3>(se, partE[ue & 1], sm);
+            grid.sync();
+            double te[3];
+            rl_collect<3>(partE[ue & 1], nb, te, sm);
+            ++ue;
+            f1 = (LOSS == FB200_LOSS_LEAST_SQUARES) ? .5 * rl_sq(te[0]) : te[0];
+            xmxh_sq = te[1];
+            pen_raw = te[2];
+            acur = 1 - acur;
+        }
         // ---- g1 = A^T r (reference :248): 32 columns x 8 row lanes per block pass, + BB sums (:254-260) ----
         double sc[3] = {0.0, 0.0, 0.0};
         for (int c0 = blockIdx.x * 32; c0 < N; c0 += nb * 32) {
@@ -218,7 +266,8 @@ resident_fbs_kernel(ResidentArgs p) {
             p.tau_h[it] = tau0;
             p.f_h[it + 1] = f1;
             if (p.evaluate_objective) p.obj_h[it + 1] = objective;
-            p.bt_h[it] = bt;
+            p.bt_h[it] = bt | (restarted ? (1 << 30) : 0);
+            if (ACCEL) p.alpha_h[it] = alpha0;
         }
         if (quality < best_q) {
             for (int i = gtid; i < N; i += gthreads) p.best[i] = __ldcg(&x1[i]);
@@ -248,13 +297,13 @@ resident_fbs_kernel(ResidentArgs p) {
 
 typedef void (*ResidentKernel)(ResidentArgs);
 
-template <int LOSS>
+template <int LOSS, bool ACCEL>
 static ResidentKernel resident_pick(int prox) {
     switch (prox) {
-        case FB200_PROX_SHRINK: return resident_fbs_kernel<LOSS, FB200_PROX_SHRINK>;
-        case FB200_PROX_NONNEG: return resident_fbs_kernel<LOSS, FB200_PROX_NONNEG>;
-        case FB200_PROX_BOX: return resident_fbs_kernel<LOSS, FB200_PROX_BOX>;
-        case FB200_PROX_IDENTITY: return resident_fbs_kernel<LOSS, FB200_PROX_IDENTITY>;
+        case FB200_PROX_SHRINK: return resident_fbs_kernel<LOSS, FB200_PROX_SHRINK, ACCEL>;
+        case FB200_PROX_NONNEG: return resident_fbs_kernel<LOSS, FB200_PROX_NONNEG, ACCEL>;
+        case FB200_PROX_BOX: return resident_fbs_kernel<LOSS, FB200_PROX_BOX, ACCEL>;
+        case FB200_PROX_IDENTITY: return resident_fbs_kernel<LOSS, FB200_PROX_IDENTITY, ACCEL>;
         default: return nullptr;
     }
 }
@@ -275,7 +324,7 @@ extern "C" int fb200_resident_blocks(int64_t M, int64_t N) {
 
 extern "C" size_t fb200_resident_scratch_doubles(int64_t M, int64_t N) {
     const int nb = fb200_resident_blocks(M, N);
-    return size_t(6) * size_t(nb > 0 ? nb : 1) * RL_MAXK;
+    return size_t(8) * size_t(nb > 0 ? nb : 1) * RL_MAXK;
 }
 
 // One launch = the whole solve after the prologue.  Pointers as in ResidentArgs; stop_rule 0..3 = residual,
@@ -286,12 +335,15 @@ extern "C" int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64
                                   double* resid_h, double* nresid_h, double* tau_h, double* f_h, double* obj_h, int* bt_h,
                                   unsigned long long* clock_h, double* out, double tau_init, double g1_sq_init,
                                   double tolerance, double shrink, int adaptive, int backtrack, int window,
-                                  int max_backtracks, int max_iters, int stop_rule, int evaluate_objective, void* stream) {
+                                  int max_backtracks, int max_iters, int stop_rule, int evaluate_objective, int accelerate,
+                                  int restart, double* xa_a, double* xa_b, double* za_a, double* za_b, double* alpha_h,
+                                  void* stream) {
     const int nb = fb200_resident_blocks(M, N);
     if (nb < 1) { set_error("resident_fbs: problem not eligible"); return 1; }
     ResidentKernel k = nullptr;
-    if (loss == FB200_LOSS_LEAST_SQUARES) k = resident_pick<FB200_LOSS_LEAST_SQUARES>(prox);
-    else if (loss == FB200_LOSS_LOGISTIC) k = resident_pick<FB200_LOSS_LOGISTIC>(prox);
+    if (accelerate && (!xa_a || !xa_b || !za_a || !za_b || !alpha_h)) { set_error("resident_fbs: FISTA buffers missing"); return 1; }
+    if (loss == FB200_LOSS_LEAST_SQUARES) k = accelerate ? resident_pick<FB200_LOSS_LEAST_SQUARES, true>(prox) : resident_pick<FB200_LOSS_LEAST_SQUARES, false>(prox);
+    else if (loss == FB200_LOSS_LOGISTIC) k = accelerate ? resident_pick<FB200_LOSS_LOGISTIC, true>(prox) : resident_pick<FB200_LOSS_LOGISTIC, false>(prox);
     if (!k) { set_error("resident_fbs: unsupported loss / prox tags %d / %d", loss, prox); return 1; }
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, RL_THREADS, 0) != cudaSuccess || per_sm < 1) {
@@ -305,6 +357,7 @@ extern "C" int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64
     a.xhat = xhat; a.dx = dx; a.best = best; a.z = z; a.r = r; a.part = part;
     a.resid_h = resid_h; a.nresid_h = nresid_h; a.tau_h = tau_h; a.f_h = f_h; a.obj_h = obj_h; a.bt_h = bt_h;
     a.clock_h = clock_h; a.out = out;
+    a.XA[0] = xa_a; a.XA[1] = xa_b; a.ZA[0] = za_a; a.ZA[1] = za_b; a.alpha_h = alpha_h; a.restart = restart;
     a.tau_init = tau_init; a.g1_sq_init = g1_sq_init; a.tolerance = tolerance; a.shrink = shrink;
     a.pen_mu = pen_mu; a.p_lo = p_lo; a.p_hi = p_hi;
     a.adaptive = adaptive; a.backtrack = backtrack; a.window = window; a.max_backtracks = max_backtracks;

@@ -49,7 +49,7 @@ SIGNATURES = {
     "fb200_resident_blocks": (_int, [_i64, _i64]),
     "fb200_resident_scratch_doubles": (_sz, [_i64, _i64]),
     "fb200_resident_fbs": (_int, [_p, _i64, _i64, _i64, _p, _int, _int, _dbl, _dbl, _dbl] + [_p] * 18 +
-                           [_dbl, _dbl, _dbl, _dbl, _int, _int, _int, _int, _int, _int, _int, _p]),
+                           [_dbl, _dbl, _dbl, _dbl, _int, _int, _int, _int, _int, _int, _int, _int, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_gemm_f64": (_int, [_int, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _int, _i64, _p]),
     "fb200_gemm_splits": (_int, [_i64, _i64, _i64]),
     "fb200_ozaki_pad": (_i64, [_i64, _int]),

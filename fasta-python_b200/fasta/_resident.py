@@ -3,7 +3,7 @@ forward-backward-splitting loop (reference ``fasta/__init__.py:172-313``) in one
 (``fb200_resident_fbs``, csrc/resident_loop.cu) -- no host round trip per iteration.
 
 Used by ``fasta.fasta`` when the problem is eligible: dense tagged operator that fits the L2, tagged loss and
-elementwise penalty, non-accelerated mode, a built-in stop rule, no per-iterate hooks.  Everything else takes the
+elementwise penalty, a built-in stop rule, no per-iterate hooks (all three modes: plain, adaptive, FISTA).  Everything else takes the
 host-driven loop.  ``FASTA_B200_RESIDENT=0`` disables it.
 """
 
@@ -25,7 +25,7 @@ def eligible(be, opts):
         return False
     if not isinstance(be, _backends.FusedBackend) or not isinstance(be.drv, _backends.DenseDriver):
         return False
-    if opts.get("accelerate", False) or opts.get("record_iterates", False) or opts.get("func", None) is not None:
+    if opts.get("record_iterates", False) or opts.get("func", None) is not None:
         return False
     if opts.get("stop_rule", stopping.hybrid_residual) not in _RULES:
         return False
@@ -78,6 +78,8 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     lo, hi = (float(pen.lo), float(pen.hi)) if pen.tag == S.PROX_BOX else (0.0, 0.0)
     xa, xb = be.X[be.ic], be.X[1 - be.ic]
     ga, gb = be.G[be.gc], be.G[1 - be.gc]
+    alpha_d = f64(max_iters) if accelerate else None
+    fista = [be.XA[be.ac], be.XA[1 - be.ac], be.ZA[be.ac], be.ZA[1 - be.ac], alpha_d] if accelerate else [None] * 5
     t_launch = time()
     _cabi.check(lib.fb200_resident_fbs(
         be.drv.A.data_ptr(), be.drv.lda, be.drv.M, be.drv.N, be.loss.b.data_ptr(), be.loss.tag, pen.tag, mu, lo, hi,
@@ -86,7 +88,8 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
         f_d.data_ptr(), obj_d.data_ptr(), bt_d.data_ptr(), clk_d.data_ptr(), out_d.data_ptr(), float(tau0), float(s.g_sq),
         float(tolerance), float(stepsize_shrink if stepsize_shrink is not None else 1.0), int(bool(adaptive)),
         int(bool(backtrack)), int(window), int(max_backtracks), int(max_iters), _RULES[stop_rule],
-        int(bool(evaluate_objective)), _device.stream_ptr()), "fb200_resident_fbs")
+        int(bool(evaluate_objective)), int(bool(accelerate)), int(bool(restart)), *[_device.ptr(v) for v in fista],
+        _device.stream_ptr()), "fb200_resident_fbs")
     be.launches += 1
     out = out_d.cpu().numpy()                               # the one sync of the solve
     n = int(out[0])
@@ -97,12 +100,15 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     clk = clk_d.cpu().numpy().astype(np.float64)
     times = np.zeros(max_iters + 1)
     times[:n + 1] = t_launch + (clk[:n + 1] - clk[0]) * 1e-9     # %globaltimer stamps mapped onto the host clock
-    if verbose:                                             # ref :302-306, printed after the fact
+    if verbose:                                             # ref :235,302-306, printed after the fact
         bts = bt_d.cpu().numpy()
+        alphas = alpha_d.cpu().numpy() if accelerate else None
         for i in range(n):
+            if bts[i] & (1 << 30):
+                print("Restarted acceleration.")
             print("[{:<6}]\t{:e}\t{:e}\t{:e}\t{:6}\t{:e}".format(
-                i, residual_hist[i], tau_hist[i], 0.0, int(bts[i]) if backtrack else 0,
-                objective_hist[i] if evaluate_objective else 0))
+                i, residual_hist[i], tau_hist[i], alphas[i] if accelerate else 0.0,
+                int(bts[i] & 0xFFFFF) if backtrack else 0, objective_hist[i] if evaluate_objective else 0))
     res = Convergence(residual_hist, norm_residual_hist, tau_hist, int(out[1]), times, n, be.solution(),
                       objective_hist, None, None)
     res.resident = True

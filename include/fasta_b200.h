@@ -151,7 +151,9 @@ int fb200_dense_sweep_accel(const double* A, int64_t lda, int64_t M, int64_t N, 
                             double* scal, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- device-resident FBS loop for small dense problems (csrc/resident_loop.cu) -------------------------
- * The whole loop of reference __init__.py:172-313 (non-accelerated modes, built-in stop rules 0..3 =
+ * The whole loop of reference __init__.py:172-313 (plain, adaptive and FISTA modes; accelerate != 0 needs the prox
+ * point / image ping-pong buffers xa_*, za_* with xa_a = start point, za_a = A x0, and alpha_h; bit 30 of bt_h[i]
+ * flags a restart of the acceleration in iteration i; built-in stop rules 0..3 =
  * stopping.residual / norm_residual / ratio_residual / hybrid_residual, elementwise prox) in ONE cooperative
  * kernel: no host round trip per iteration.  x_a / g_a hold the start point and its gradient, f_h[0] (and
  * obj_h[0]) the start values; histories, per-iteration backtrack counts and %globaltimer stamps are device arrays
@@ -166,7 +168,9 @@ int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64_t N, const
                        double* resid_h, double* nresid_h, double* tau_h, double* f_h, double* obj_h, int* bt_h,
                        unsigned long long* clock_h, double* out, double tau_init, double g1_sq_init,
                        double tolerance, double shrink, int adaptive, int backtrack, int window,
-                       int max_backtracks, int max_iters, int stop_rule, int evaluate_objective, void* stream);
+                       int max_backtracks, int max_iters, int stop_rule, int evaluate_objective, int accelerate,
+                       int restart, double* xa_a, double* xa_b, double* za_a, double* za_b, double* alpha_h,
+                       void* stream);
 
 /* ---- K14: batched contractions (B columns, batch index fastest), fp64 DMMA GEMM -----------------
  * adjoint = 0:  C (Mg x Ng) = A (Mg x K) . B (K x Ng)         the per-column `A @ x`   of linalg.py:41

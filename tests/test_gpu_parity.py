@@ -40,7 +40,7 @@ def test_fused_path_matches_golden(case, mode):
 SMALL_DENSE = ("lasso_200x1000_k10", "lasso_200x1000_k50", "lasso_333x1414_k40", "nnls_200x1000", "logistic_1000x2000")
 
 
-@pytest.mark.parametrize("case,mode", [cm for cm in golden_cases(prefixes=SMALL_DENSE) if cm[1] != "accelerated"])
+@pytest.mark.parametrize("case,mode", golden_cases(prefixes=SMALL_DENSE))
 def test_device_resident_loop_matches_golden(case, mode):
     """Small dense problems run the whole loop in one cooperative kernel (csrc/resident_loop.cu)."""
     import fasta
@@ -54,7 +54,7 @@ def test_device_resident_loop_matches_golden(case, mode):
     assert np.all(np.diff(res.times[:n + 1]) >= 0) and res.times[n] > res.times[0]
 
 
-@pytest.mark.parametrize("case,mode", [cm for cm in golden_cases(prefixes=SMALL_DENSE) if cm[1] != "accelerated"])
+@pytest.mark.parametrize("case,mode", golden_cases(prefixes=SMALL_DENSE))
 def test_host_driven_loop_matches_golden_on_small_problems(case, mode, monkeypatch):
     """The same cases with the device-resident loop disabled (host loop + single-pass sweep)."""
     import fasta
@@ -169,12 +169,57 @@ def test_accelerated_without_the_fused_fista_sweep_matches_golden(case, monkeypa
     """Accelerated mode with the separate forward / extrapolate / adjoint kernels (the fused FISTA sweep is the default)."""
     import fasta
     monkeypatch.setenv("FASTA_B200_SWEEP_ACCEL", "0")
+    monkeypatch.setenv("FASTA_B200_RESIDENT", "0")
     gold = load_golden(case, "accelerated")
     p = problems.build(case, int(gold["seed"]))
     A, loss, pen = tagged(p)
     res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
-    assert not res.single_pass
+    assert not res.single_pass and not res.resident
     assert_trajectory(res, gold, label=f"accel-unfused/{case}")
+
+
+def test_device_resident_loop_fista_options(capsys, monkeypatch):
+    """FISTA in the device-resident loop: restart on/off, together with the adaptive step size, verbose lines."""
+    import fasta
+    p = problems.build("lasso_200x1000_k50", 0)
+    A, loss, pen = tagged(p)
+    f, gradf, g, proxg = problems.numpy_callables(p)
+    for opts in (dict(restart=False, max_iters=120), dict(adaptive=True, max_iters=80), dict(backtrack=False, max_iters=60),
+                 dict(evaluate_objective=False, max_iters=90)):
+        o = dict(verbose=False, evaluate_objective=True, accelerate=True, adaptive=False)
+        o.update(opts)
+        np.random.seed(7)
+        res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **o)
+        np.random.seed(7)
+        ref = fasta_oracle.solve(lambda x: p.A @ x, lambda y: p.A.T @ y, f, gradf, g, proxg, p.x0, **o)
+        assert res.resident
+        assert (res.iteration_count, res.backtracks) == (ref.iteration_count, ref.backtracks), opts
+        n = ref.iteration_count
+        assert np.linalg.norm(res.solution - ref.solution) <= 1e-9 * np.linalg.norm(ref.solution), opts
+        assert np.allclose(res.stepsizes[:n], ref.stepsizes[:n], rtol=1e-6, atol=0)
+        assert np.allclose(res.residuals[:n], ref.residuals[:n], rtol=1e-6, atol=0)
+        if o["evaluate_objective"]:
+            assert np.max(np.abs(res.objectives[:n + 1] - ref.objectives[:n + 1]) / np.abs(ref.objectives[:n + 1])) <= 1e-10
+    # verbose output is the host loop's (= the reference's format), line for line: alpha column, "Restarted acceleration."
+    o = dict(accelerate=True, adaptive=False, max_iters=200, evaluate_objective=True)
+    capsys.readouterr()
+    np.random.seed(7)
+    assert fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **o).resident
+    got = capsys.readouterr().out
+    monkeypatch.setenv("FASTA_B200_RESIDENT", "0")
+    np.random.seed(7)
+    assert not fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **o).resident
+    want = capsys.readouterr().out
+    assert "Restarted acceleration." in want
+    gl, wl = got.splitlines(), want.splitlines()
+    assert len(gl) == len(wl)
+    for a, b in zip(gl, wl):
+        if a.startswith("["):
+            fa, fb = a.split("\t"), b.split("\t")
+            assert fa[0] == fb[0] and fa[4] == fb[4]
+            assert np.allclose([float(v) for v in fa[1:4] + fa[5:]], [float(v) for v in fb[1:4] + fb[5:]], rtol=1e-5)
+        else:
+            assert a == b
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
