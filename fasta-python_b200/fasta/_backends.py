@@ -285,17 +285,20 @@ class FusedBackend:
         self.m = int(np.prod(driver.zshape))
         self.ws = _device.acquire_workspace(*driver.workspace_dims(), device=dev)
         new = lambda k: t.empty(k, dtype=t.float64, device=dev)
-        self.X = [new(self.n), new(self.n)]
+        # three iterate buffers: current, previous and the best iterate so far -- the best iterate (reference :298-300)
+        # is kept by INDEX, never copied: a new trial is written to the buffer that is neither x0 nor the best
+        self.X = [new(self.n), new(self.n), new(self.n)]
         # gradient buffers carry 8 spare doubles: a sharded driver packs the loss partial behind the
         # gradient so that ONE all-reduce per iteration moves both
         self._Gbuf = [new(self.n + 8), new(self.n + 8)]
         self.G = [g[:self.n] for g in self._Gbuf]
-        self.XH, self.DX, self.BEST = new(self.n), new(self.n), new(self.n)
+        self.XH, self.DX = new(self.n), new(self.n)
         self.Z, self.R = new(self.m), new(self.m)
         if self.accelerate:
             self.XA = [new(self.n), new(self.n)]
             self.ZA = [new(self.m), new(self.m)]
         self.ic = self.ip = 0      # X[ic] current iterate, X[ip] previous
+        self.ib = 0                # X[ib] best iterate so far
         self.gc = self.gp = 0      # G[gc] current gradient, G[gp] previous
         self.ac = self.ap = 0      # XA/ZA[ac] current prox point, [ap] previous
         self.launches = 0          # kernels launched by this backend (vector kernels; + driver.launches)
@@ -330,7 +333,7 @@ class FusedBackend:
     def load(self):
         x0d = _device.to_device(self.x0_in, self.X[0].device).reshape(-1)
         self.X[self.ic].copy_(x0d)
-        self.BEST.copy_(x0d)
+        self.ib = self.ic
         if self.accelerate:
             self.XA[self.ac].copy_(x0d)
 
@@ -346,7 +349,7 @@ class FusedBackend:
 
     def _probe_outputs(self):
         # X[other] and G[other] are free until the first advance(); Z / R are scratch here
-        return self.X[1 - self.ic], self.G[1 - self.gc]
+        return self.X[(self.ic + 1) % 3], self.G[1 - self.gc]
 
     def lipschitz_push(self, k, v):
         """Upload probe k (0/1) and queue d_k = A^H gradf(A v_k)."""
@@ -408,7 +411,8 @@ class FusedBackend:
         return Scalars(f=self.loss.finalize(s[S.S_F]), pen=self.pen.value(s[S.S_PEN]), g_sq=s[S.S_G1_SQ])
 
     def advance(self):
-        self.ip, self.ic = self.ic, 1 - self.ic
+        self.ip = self.ic
+        self.ic = next(k for k in (0, 1, 2) if k != self.ip and k != self.ib)
         self.gp, self.gc = self.gc, 1 - self.gc
         if self.accelerate:
             self.ap, self.ac = self.ac, 1 - self.ac
@@ -542,15 +546,15 @@ class FusedBackend:
         return self.X[self.ip] if self._ahead else self.X[self.ic]
 
     def keep_best(self):
-        self.BEST.copy_(self._current())
+        self.ib = self.ip if self._ahead else self.ic      # by index: no copy (advance() never hands out X[ib])
 
     def iterate(self):
         return _device.like_input(self._current().view(self.shape), self.x0_in)
 
     def solution(self):
-        # BEST belongs to this backend alone and the backend ends with the solve: hand the buffer over
+        # X[ib] belongs to this backend alone and the backend ends with the solve: hand the buffer over
         # instead of cloning it (no allocation at the end of a solve)
-        return _device.like_input(self.BEST.view(self.shape), self.x0_in)
+        return _device.like_input(self.X[self.ib].view(self.shape), self.x0_in)
 
 
 # =================================================================================================

@@ -76,14 +76,16 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     pen = be.pen
     mu = float(pen.mu) if pen.tag == S.PROX_SHRINK else 0.0
     lo, hi = (float(pen.lo), float(pen.hi)) if pen.tag == S.PROX_BOX else (0.0, 0.0)
-    xa, xb = be.X[be.ic], be.X[1 - be.ic]
+    ia, ib_, ibest = be.ic, (be.ic + 1) % 3, (be.ic + 2) % 3
+    xa, xb, best = be.X[ia], be.X[ib_], be.X[ibest]
+    best.copy_(xa)                                          # stays the answer if no iterate ever improves (nan quality)
     ga, gb = be.G[be.gc], be.G[1 - be.gc]
     alpha_d = f64(max_iters) if accelerate else None
     fista = [be.XA[be.ac], be.XA[1 - be.ac], be.ZA[be.ac], be.ZA[1 - be.ac], alpha_d] if accelerate else [None] * 5
     t_launch = time()
     _cabi.check(lib.fb200_resident_fbs(
         be.drv.A.data_ptr(), be.drv.lda, be.drv.M, be.drv.N, be.loss.b.data_ptr(), be.loss.tag, pen.tag, mu, lo, hi,
-        xa.data_ptr(), xb.data_ptr(), ga.data_ptr(), gb.data_ptr(), be.XH.data_ptr(), be.DX.data_ptr(), be.BEST.data_ptr(),
+        xa.data_ptr(), xb.data_ptr(), ga.data_ptr(), gb.data_ptr(), be.XH.data_ptr(), be.DX.data_ptr(), best.data_ptr(),
         be.Z.data_ptr(), be.R.data_ptr(), part.data_ptr(), resid_d.data_ptr(), nresid_d.data_ptr(), tau_d.data_ptr(),
         f_d.data_ptr(), obj_d.data_ptr(), bt_d.data_ptr(), clk_d.data_ptr(), out_d.data_ptr(), float(tau0), float(s.g_sq),
         float(tolerance), float(stepsize_shrink if stepsize_shrink is not None else 1.0), int(bool(adaptive)),
@@ -93,8 +95,8 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     be.launches += 1
     out = out_d.cpu().numpy()                               # the one sync of the solve
     n = int(out[0])
-    if int(out[2]) != 0:                                    # the kernel rotated the buffers an odd number of times
-        be.ic, be.ip = 1 - be.ic, be.ic
+    be.ic, be.ip = (ib_, ia) if int(out[2]) != 0 else (ia, ib_)      # which buffer holds the last iterate
+    be.ib = ibest                                           # the kernel copies an improving iterate there (N is small)
     residual_hist, norm_residual_hist, tau_hist = (v.cpu().numpy() for v in (resid_d, nresid_d, tau_d))
     objective_hist = obj_d.cpu().numpy() if evaluate_objective else None
     clk = clk_d.cpu().numpy().astype(np.float64)
