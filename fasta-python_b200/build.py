@@ -31,6 +31,7 @@ UNITS = [
     ("ozaki_gemm.cu", []),
     ("batched_vector.cu", ["-fmad=false"]),
     ("resident_loop.cu", ["-fmad=false"]),
+    ("jacobi_svd.cu", []),
 ]
 
 

@@ -18,7 +18,7 @@ namespace fb200 {
 //   [DENSE_OFF, ...)               split partials of the dense maps: zp[S][ldz] then gp[S][ldg]
 // ------------------------------------------------------------------------------------------------
 constexpr int    MAX_RED_BLOCKS = 8192;
-constexpr int    MAX_RED_K      = 8;
+constexpr int    MAX_RED_K      = 12;
 constexpr size_t CTR_BYTES      = 2048;
 constexpr int    FPART_MAX      = 160;
 constexpr size_t RED_BYTES      = size_t(MAX_RED_BLOCKS) * MAX_RED_K * sizeof(double);

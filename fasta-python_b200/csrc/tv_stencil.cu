@@ -435,7 +435,18 @@ tv_iter_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, d
 // ---------------------------------------------------------------------------------------------------
 constexpr int TVM_THREADS = 128, TVM_COLS = 30;
 
-template <int LOSS, int TVM_UNROLL, int MINB>
+// v / tau with the reciprocal rt = 1 / tau formed once per thread: product, then two residual corrections
+// (Markstein: a faithful quotient corrected with the correctly rounded reciprocal is the correctly rounded
+// quotient).  Only the BB sums consume this quotient.
+template <bool FD>
+__device__ __forceinline__ double tv_div_tau(double v, double tau, double rt) {
+    if (!FD) return v / tau;
+    const double q0 = v * rt;
+    const double q1 = fma(fma(-tau, q0, v), rt, q0);
+    return fma(fma(-tau, q1, v), rt, q1);
+}
+
+template <int LOSS, int TVM_UNROLL, int MINB, bool FD>
 __global__ void __launch_bounds__(TVM_THREADS, MINB)
 tv_iter_march_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, double tau, int n0, int n1,
                      const double* __restrict__ b, double2* __restrict__ x1, double2* __restrict__ g1, int warps_x, int strip,
@@ -448,6 +459,7 @@ tv_iter_march_kernel(const double2* __restrict__ x0, const double2* __restrict__
     const int i0 = wy * strip;
     const int i1 = min(n0, i0 + strip);
     const bool out_lane = lane >= 1 && lane <= TVM_COLS && j < n1;
+    const double rtau = 1.0 / tau;
     double s[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (i0 < n0) {
         auto point = [&](int i, double2& a, double2& gr) {    // x0, g0 at (wrapped) row i of this lane's column
@@ -506,8 +518,8 @@ tv_iter_march_kernel(const double2* __restrict__ x0, const double2* __restrict__
                     s[1] += dxx * dxx;   s[1] += dxy * dxy;
                     s[2] += ex * ex;     s[2] += ey * ey;
                     s[3] += fc;
-                    const double dg0 = gi.x + (hx - a_c.x) / tau;
-                    const double dg1 = gi.y + (hy - a_c.y) / tau;
+                    const double dg0 = gi.x + tv_div_tau<FD>(hx - a_c.x, tau, rtau);
+                    const double dg1 = gi.y + tv_div_tau<FD>(hy - a_c.y, tau, rtau);
                     s[4] += dxx * dg0;   s[4] += dxy * dg1;
                     s[5] += dg0 * dg0;   s[5] += dg1 * dg1;
                     s[6] += gi.x * gi.x; s[6] += gi.y * gi.y;
@@ -522,6 +534,120 @@ tv_iter_march_kernel(const double2* __restrict__ x0, const double2* __restrict__
     double* const out[7] = {scal + FB200_S_DX_G0, scal + FB200_S_DX_SQ, scal + FB200_S_XMXH_SQ, scal + FB200_S_F,
                             scal + FB200_S_DX_DG, scal + FB200_S_DG_SQ, scal + FB200_S_G1_SQ};
     grid_sum<7>(s, red, counter, out);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FISTA (accelerated) iteration, same marching scheme: forward step and ball projection give the prox point
+// x_accel1 (reference __init__.py:181-186), its image z_accel1 = div(x_accel1) and f there feed the line search
+// (:187-217); the extrapolation x1 = x_accel1 + c (x_accel1 - x_accel0), z1 = z_accel1 + c (z_accel1 - z_accel0)
+// (:242-243, by linearity no second div), f(z1) (:245), the gradient grad(gradf(z1)) (:248) and the BB / residual
+// sums (:254-274) follow in the same pass.  The weight c = (alpha0 - 1) / alpha1 depends on the restart test
+// <x0 - x_accel1, x_accel1 - x_accel0> > 1e-30 (:231) of THIS trial, which has only two outcomes: the host passes
+// the no-restart weight and repeats the launch with c = 0 in the (rare) iterations that restart.
+// Reads x0, g0, x_accel0 (2U each), b, z_accel0 (U each); writes x_accel1, x1, g1 (2U each), z_accel1 (U): 15U.
+// ---------------------------------------------------------------------------------------------------
+template <int LOSS, int TVM_UNROLL, int MINB, bool FD>
+__global__ void __launch_bounds__(TVM_THREADS, MINB)
+tv_fista_march_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, double tau, double c, int n0, int n1,
+                      const double* __restrict__ b, const double2* __restrict__ xa0, const double* __restrict__ za0,
+                      double2* __restrict__ xa1, double* __restrict__ za1, double2* __restrict__ x1,
+                      double2* __restrict__ g1, int warps_x, int strip, double* scal, double* red, unsigned* counter) {
+    const int lane = threadIdx.x & 31;
+    const int wid  = blockIdx.x * (TVM_THREADS / 32) + (threadIdx.x >> 5);
+    const int wx = wid % warps_x, wy = wid / warps_x;
+    const int j  = wx * TVM_COLS - 1 + lane;                  // unwrapped column of this lane
+    const int jw = tv_wrap(j, n1);
+    const int i0 = wy * strip;
+    const int i1 = min(n0, i0 + strip);
+    const bool out_lane = lane >= 1 && lane <= TVM_COLS && j < n1;
+    const double rtau = 1.0 / tau;
+    double s[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (i0 < n0) {
+        auto point = [&](int i, double2& a, double2& gr) {    // x0, g0 at (wrapped) row i of this lane's column
+            const int64_t o = int64_t(tv_wrap(i, n0)) * n1 + jw;
+            a = x0[o];
+            gr = g0[o];
+        };
+        double2 a_c, g_c, a_t, g_t, h;
+        point(i0 - 1, a_t, g_t);
+        const double2 y_m = tv_prox_point(a_t, g_t, tau, h);       // row i0-1
+        point(i0, a_c, g_c);
+        double2 y_c = tv_prox_point(a_c, g_c, tau, h);             // row i0
+        double r_up;                                               // gradf(z1)(i0-1, j) at the extrapolated z
+        {
+            const int64_t o = int64_t(tv_wrap(i0 - 1, n0)) * n1 + jw;
+            const double rty = __shfl_down_sync(0xffffffffu, y_m.y, 1);
+            const double zp = (y_c.x - y_m.x) + (rty - y_m.y);
+            const double ze = zp + c * (zp - za0[o]);
+            double fv;
+            loss_elem<LOSS>(ze, b[o], r_up, fv);
+        }
+        for (int ib = i0; ib < i1; ib += TVM_UNROLL) {
+            double2 an[TVM_UNROLL], gn[TVM_UNROLL], qa[TVM_UNROLL];
+            double bb[TVM_UNROLL], zq[TVM_UNROLL];
+#pragma unroll
+            for (int u = 0; u < TVM_UNROLL; ++u) {                 // x0, g0 of rows ib+1 ..; b, x_accel0, z_accel0 of rows ib ..
+                const int i = ib + u;
+                if (i < i1) {
+                    point(i + 1, an[u], gn[u]);
+                    const int64_t o = int64_t(i) * n1 + jw;
+                    bb[u] = b[o];
+                    zq[u] = za0[o];
+                    qa[u] = xa0[o];
+                } else {
+                    an[u] = gn[u] = qa[u] = make_double2(0.0, 0.0);
+                    bb[u] = zq[u] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < TVM_UNROLL; ++u) {
+                const int i = ib + u;
+                if (i >= i1) break;                                // warp-uniform
+                double2 hn;
+                const double2 y_n = tv_prox_point(an[u], gn[u], tau, hn);        // row i+1
+                const double rty = __shfl_down_sync(0xffffffffu, y_c.y, 1);
+                const double zp = (y_n.x - y_c.x) + (rty - y_c.y);               // z_accel1 = div(x_accel1)
+                const double ze = zp + c * (zp - zq[u]);                         // extrapolated z1
+                double rp, fp, rc, fc;
+                loss_elem<LOSS>(zp, bb[u], rp, fp);
+                loss_elem<LOSS>(ze, bb[u], rc, fc);
+                const double r_left = __shfl_up_sync(0xffffffffu, rc, 1);
+                if (out_lane) {
+                    const int64_t o = int64_t(i) * n1 + j;
+                    double2 gi, xe;
+                    gi.x = r_up - rc;
+                    gi.y = r_left - rc;
+                    xe.x = y_c.x + c * (y_c.x - qa[u].x);
+                    xe.y = y_c.y + c * (y_c.y - qa[u].y);
+                    xa1[o] = y_c;
+                    za1[o] = zp;
+                    x1[o] = xe;
+                    g1[o] = gi;
+                    const double hx = a_c.x - tau * g_c.x, hy = a_c.y - tau * g_c.y;
+                    const double dxx = y_c.x - a_c.x, dxy = y_c.y - a_c.y, ex = xe.x - hx, ey = xe.y - hy;
+                    s[0] += dxx * g_c.x; s[0] += dxy * g_c.y;
+                    s[1] += dxx * dxx;   s[1] += dxy * dxy;
+                    s[2] += ex * ex;     s[2] += ey * ey;
+                    s[3] += fp;
+                    const double dg0 = gi.x + tv_div_tau<FD>(hx - a_c.x, tau, rtau);
+                    const double dg1 = gi.y + tv_div_tau<FD>(hy - a_c.y, tau, rtau);
+                    s[4] += dxx * dg0;   s[4] += dxy * dg1;
+                    s[5] += dg0 * dg0;   s[5] += dg1 * dg1;
+                    s[6] += gi.x * gi.x; s[6] += gi.y * gi.y;
+                    s[7] += (a_c.x - y_c.x) * (y_c.x - qa[u].x); s[7] += (a_c.y - y_c.y) * (y_c.y - qa[u].y);
+                    s[8] += fc;
+                }
+                r_up = rc;
+                y_c = y_n;
+                a_c = an[u];
+                g_c = gn[u];
+            }
+        }
+    }
+    double* const out[9] = {scal + FB200_S_DX_G0, scal + FB200_S_DX_SQ, scal + FB200_S_XMXH_SQ, scal + FB200_S_F,
+                            scal + FB200_S_DX_DG, scal + FB200_S_DG_SQ, scal + FB200_S_G1_SQ, scal + FB200_S_RESTART,
+                            scal + FB200_S_AUX3};
+    grid_sum<9>(s, red, counter, out);
 }
 
 static int tv_grid(int64_t n0, int64_t n1, dim3* grid, int* strip) {
@@ -641,8 +767,9 @@ extern "C" int fb200_tv_iter_fused(const double* x0, const double* g0, double ta
         if (blocks > MAX_RED_BLOCKS || warps_x > (1 << 24)) { set_error("tv_iter_fused: image too large"); return 1; }
         static int mv = -1;                 // experiment knob: unroll depth / occupancy target of the marching kernel
         if (mv < 0) { const char* e = getenv("FASTA_B200_TVM_VARIANT"); mv = e ? atoi(e) : 0; }
-#define TVM_LAUNCH(L, U, B) tv_iter_march_kernel<L, U, B><<<unsigned(blocks), TVM_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, int(n0), int(n1), b, (double2*)x1, (double2*)g1, int(warps_x), int(strip), scal, w.red, w.counter)
-#define TVM_PICK(L) switch (mv) { case 1: TVM_LAUNCH(L, 4, 6); break; case 2: TVM_LAUNCH(L, 8, 4); break; case 3: TVM_LAUNCH(L, 2, 8); break; default: TVM_LAUNCH(L, 4, 4); }
+#define TVM_LAUNCH(L, U, B) TVM_LAUNCH_FD(L, U, B, false)
+#define TVM_LAUNCH_FD(L, U, B, FD) tv_iter_march_kernel<L, U, B, FD><<<unsigned(blocks), TVM_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, int(n0), int(n1), b, (double2*)x1, (double2*)g1, int(warps_x), int(strip), scal, w.red, w.counter)
+#define TVM_PICK(L) switch (mv) { case 1: TVM_LAUNCH(L, 4, 6); break; case 2: TVM_LAUNCH(L, 8, 4); break; case 3: TVM_LAUNCH(L, 2, 8); break; case 4: TVM_LAUNCH_FD(L, 4, 4, true); break; case 5: TVM_LAUNCH_FD(L, 4, 5, true); break; default: TVM_LAUNCH(L, 4, 4); }
         switch (loss) {
             case FB200_LOSS_LEAST_SQUARES: TVM_PICK(FB200_LOSS_LEAST_SQUARES) break;
             case FB200_LOSS_LOGISTIC: TVM_LAUNCH(FB200_LOSS_LOGISTIC, 4, 4); break;
@@ -650,6 +777,7 @@ extern "C" int fb200_tv_iter_fused(const double* x0, const double* g0, double ta
         }
 #undef TVM_PICK
 #undef TVM_LAUNCH
+#undef TVM_LAUNCH_FD
         return check_launch("tv_iter_march");
     }
     const int64_t tx = (n1 + TVI_TW - 1) / TVI_TW, ty = (n0 + TVI_TH - 1) / TVI_TH;
@@ -675,4 +803,35 @@ extern "C" int fb200_tv_iter_fused(const double* x0, const double* g0, double ta
         default: set_error("tv_iter_fused: unsupported loss tag %d", loss); return 1;
     }
     return check_launch("tv_iter_fused");
+}
+
+// FISTA trial in one kernel (tv_fista_march_kernel): scal[S_F] = raw f at the prox point's image (line search),
+// scal[S_AUX3] = raw f at the extrapolated z, scal[S_RESTART] = the restart dot, the remaining sums as fb200_tv_iter_fused.
+extern "C" int fb200_tv_fista_fused(const double* x0, const double* g0, double tau, double c, int64_t n0, int64_t n1, int loss,
+                                    const double* b, const double* xa0, const double* za0, double* xa1, double* za1,
+                                    double* x1, double* g1, double* scal, void* ws, void* stream) {
+    Workspace w(ws);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n0 < 1 || n1 < 1 || n0 > (1 << 30) || n1 > (1 << 30)) { set_error("tv_fista_fused: bad shape"); return 1; }
+    const int64_t warps_x = (n1 + TVM_COLS - 1) / TVM_COLS;
+    int64_t strip = 64;
+    while ((warps_x * ((n0 + strip - 1) / strip) + 3) / 4 > MAX_RED_BLOCKS) strip *= 2;
+    const int64_t warps = warps_x * ((n0 + strip - 1) / strip);
+    const int64_t blocks = (warps + TVM_THREADS / 32 - 1) / (TVM_THREADS / 32);
+    if (blocks > MAX_RED_BLOCKS || warps_x > (1 << 24)) { set_error("tv_fista_fused: image too large"); return 1; }
+    static int mv = -1;                     // experiment knob: unroll depth / occupancy target
+    if (mv < 0) { const char* e = getenv("FASTA_B200_TVF_VARIANT"); mv = e ? atoi(e) : 0; }
+#define TVF_LAUNCH(L, U, B) TVF_LAUNCH_FD(L, U, B, false)
+#define TVF_LAUNCH_FD(L, U, B, FD) tv_fista_march_kernel<L, U, B, FD><<<unsigned(blocks), TVM_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, c, int(n0), int(n1), b, (const double2*)xa0, za0, (double2*)xa1, za1, (double2*)x1, (double2*)g1, int(warps_x), int(strip), scal, w.red, w.counter)
+    switch (loss) {
+        case FB200_LOSS_LEAST_SQUARES:
+            switch (mv) { case 1: TVF_LAUNCH(FB200_LOSS_LEAST_SQUARES, 4, 3); break; case 2: TVF_LAUNCH(FB200_LOSS_LEAST_SQUARES, 2, 3); break;
+                          case 3: TVF_LAUNCH_FD(FB200_LOSS_LEAST_SQUARES, 2, 4, true); break; default: TVF_LAUNCH(FB200_LOSS_LEAST_SQUARES, 2, 4); }
+            break;
+        case FB200_LOSS_LOGISTIC: TVF_LAUNCH(FB200_LOSS_LOGISTIC, 2, 4); break;
+        default: set_error("tv_fista_fused: unsupported loss tag %d", loss); return 1;
+    }
+#undef TVF_LAUNCH
+#undef TVF_LAUNCH_FD
+    return check_launch("tv_fista_march");
 }

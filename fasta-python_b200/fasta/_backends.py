@@ -132,6 +132,16 @@ class TVDriver:
                                                  ws.buf.data_ptr(), _device.stream_ptr()), "fb200_tv_iter_fused")
         self.launches += 1
 
+    # the whole accelerated (FISTA) trial in one kernel (15U bytes), extrapolation weight c speculated by the caller
+    fista_fused_ok = os.environ.get("FASTA_B200_TV_FISTA", "1") != "0"
+
+    def fista_fused(self, x0, g0, tau, c, loss_tag, b, xa0, za0, xa1, za1, x1, g1, ws):
+        _cabi.check(self.lib.fb200_tv_fista_fused(x0.data_ptr(), g0.data_ptr(), float(tau), float(c), self.n0, self.n1,
+                                                  loss_tag, b.data_ptr(), xa0.data_ptr(), za0.data_ptr(), xa1.data_ptr(),
+                                                  za1.data_ptr(), x1.data_ptr(), g1.data_ptr(), ws.scal.data_ptr(),
+                                                  ws.buf.data_ptr(), _device.stream_ptr()), "fb200_tv_fista_fused")
+        self.launches += 1
+
     def sync_point(self, v1, v2):
         pass
 
@@ -317,6 +327,10 @@ class FusedBackend:
         # TV: one fused kernel per half-iteration (see TVDriver.step_forward)
         self.use_tv_fused = ((not self.accelerate) and isinstance(driver, TVDriver) and driver.fused_step_ok
                              and penalty.tag == S.PROX_TV_BALL and loss.tag != S.LOSS_NONE)
+        # TV + FISTA: the whole accelerated trial in one kernel (see trial_accel)
+        self.use_tv_accel = (self.accelerate and isinstance(driver, TVDriver) and driver.fused_step_ok
+                             and driver.fista_fused_ok and penalty.tag == S.PROX_TV_BALL
+                             and loss.tag in (S.LOSS_LEAST_SQUARES, S.LOSS_LOGISTIC))
 
     # -- helpers --------------------------------------------------------------------------------
     def _st(self):
@@ -472,6 +486,8 @@ class FusedBackend:
         the x extrapolation and the sweep (z_accel1 = A x_accel1, extrapolated z, f at both, gradient, BB sums)."""
         x0, g0 = self.X[self.ip], self.G[self.gp]
         xa1, xa0 = self.XA[self.ac], self.XA[self.ap]
+        if self.use_tv_accel:
+            return self._trial_accel_tv(tau, alpha_prev, restart)
         p0, p1 = self.pen.params(tau)
         st = self._st()
         if self.pen.tag == S.PROX_L1BALL:
@@ -505,6 +521,26 @@ class FusedBackend:
         extrap = Scalars(f=self.loss.finalize(s[S.S_AUX3]), xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]))
         return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=step.dx_g0, dx_sq=step.dx_sq, xmxh_sq=s[S.S_XMXH_SQ],
                        pen=self.pen.value(s[S.S_PEN]), restart=step.restart, extrap=extrap)
+
+    def _trial_accel_tv(self, tau, alpha_prev, restart):
+        """TV + FISTA: ONE kernel per trial.  The extrapolation weight has two possible values -- the regular
+        (alpha0 - 1) / alpha1 with alpha0 = alpha_prev, or 0 when the restart test of reference :231 fires -- so the
+        kernel is launched with the regular one and repeated with c = 0 in the rare iterations that restart."""
+        alpha1 = (1 + np.sqrt(1 + 4 * alpha_prev ** 2)) / 2           # reference :238-240 with alpha0 = alpha_prev
+        c = (alpha_prev - 1) / alpha1
+        args = (self.X[self.ip], self.G[self.gp], tau)
+        bufs = (self.loss.tag, self.loss.b, self.XA[self.ap], self.ZA[self.ap], self.XA[self.ac], self.ZA[self.ac],
+                self.X[self.ic], self.G[self.gc], self.ws)
+        self.drv.fista_fused(*args, c, *bufs)
+        s = self.ws.fetch()
+        if restart and s[S.S_RESTART] > 1E-30 and c != 0.0:
+            self.drv.fista_fused(*args, 0.0, *bufs)
+            s = self.ws.fetch()
+        self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
+        zero = self.pen.value(0.0)
+        extrap = Scalars(f=self.loss.finalize(s[S.S_AUX3]), xmxh_sq=s[S.S_XMXH_SQ], pen=zero)
+        return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ], xmxh_sq=s[S.S_XMXH_SQ],
+                       pen=zero, restart=s[S.S_RESTART], extrap=extrap)
 
     def trial_launch(self, tau):
         """Queue the next iteration's first trial; until trial_finish() the 'current' iterate is X[ip]."""

@@ -50,6 +50,8 @@ SIGNATURES = {
     "fb200_resident_scratch_doubles": (_sz, [_i64, _i64]),
     "fb200_resident_fbs": (_int, [_p, _i64, _i64, _i64, _p, _int, _int, _dbl, _dbl, _dbl] + [_p] * 18 +
                            [_dbl, _dbl, _dbl, _dbl, _int, _int, _int, _int, _int, _int, _int, _int, _int, _p, _p, _p, _p, _p, _p]),
+    "fb200_prox_nuclear_scratch_doubles": (_sz, [_i64, _i64]),
+    "fb200_prox_nuclear": (_int, [_p, _i64, _i64, _i64, _dbl, _p, _i64, _p, _p, _p, _p]),
     "fb200_gemm_f64": (_int, [_int, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _int, _i64, _p]),
     "fb200_gemm_splits": (_int, [_i64, _i64, _i64]),
     "fb200_ozaki_pad": (_i64, [_i64, _int]),
@@ -67,6 +69,7 @@ SIGNATURES = {
     "fb200_tv_grad_bb": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),
     "fb200_tv_step_div_loss": (_int, [_p, _p, _dbl, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_tv_grad_bb_fused": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),
+    "fb200_tv_fista_fused": (_int, [_p, _p, _dbl, _dbl, _i64, _i64, _int] + [_p] * 10),
     "fb200_tv_iter_fused": (_int, [_p, _p, _dbl, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_peer_allreduce_bb": (_int, [_p, _int, _i64, _p, _int, _p, _p, _p, _dbl, _int, _p, _p, _p]),
     "fb200_prox_rows": (_int, [_p, _i64, _i64, _int, _dbl, _p, _p, _p]),

@@ -125,7 +125,8 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     # Back-ends that can queue a trial without waiting for it get the NEXT iteration's trial queued as soon as the
     # new step size is known (end of the loop body); histories, best-iterate copy and stop rule then run on the host
     # while the device works.  A trial queued before a stop is simply never collected.
-    fused_accel = accelerate and getattr(be, "use_sweep_accel", False)     # FISTA trial incl. extrapolation in one pass
+    # FISTA trial incl. extrapolation in one pass (dense single-pass sweep / TV whole-iteration kernel)
+    fused_accel = accelerate and (getattr(be, "use_sweep_accel", False) or getattr(be, "use_tv_accel", False))
     run_ahead = hasattr(be, "trial_launch") and not fused_accel and os.environ.get("FASTA_B200_RUN_AHEAD", "1") != "0"
     queued = False
 

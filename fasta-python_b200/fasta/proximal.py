@@ -64,17 +64,33 @@ def project_Linf_ball(x, t):
     return x - project_L1_ball(x, t)
 
 
+def _nuclear(X, t, want_out):
+    tt = _device.torch()
+    lib = _cabi.load()
+    assert X.ndim == 2
+    Xd = _device.to_device(X).contiguous()
+    M, N = Xd.shape
+    out = tt.empty_like(Xd) if want_out else None
+    sv = tt.empty(min(M, N), dtype=tt.float64, device=Xd.device)
+    need = int(lib.fb200_prox_nuclear_scratch_doubles(M, N))
+    scratch = tt.empty(need, dtype=tt.float64, device=Xd.device) if need else None
+    _cabi.check(lib.fb200_prox_nuclear(Xd.data_ptr(), M, N, N, float(t), _device.ptr(out), N, sv.data_ptr(),
+                                       _device.ptr(scratch), None, _device.stream_ptr()), "fb200_prox_nuclear")
+    return out, sv
+
+
 def project_Lnuc_ball(X, t):
     """The reference's function of this name: singular-value soft threshold U diag(shrink(s,t)) V
-    (reference proximal.py:44-55).  SVD via torch.linalg on the GPU (library call; this prox is in
-    no BASELINE config)."""
-    tt = _device.torch()
-    Xd = _device.to_device(X)
-    U, s, Vh = tt.linalg.svd(Xd, full_matrices=True)
-    S = tt.zeros_like(Xd)
-    k = s.numel()
-    S[:k, :k] = tt.diag(shrink(s, t))
-    return _device.like_input(U @ S @ Vh, X)
+    (reference proximal.py:44-55), by the one-sided Jacobi kernel of csrc/jacobi_svd.cu (no library SVD)."""
+    out, _ = _nuclear(X, t, True)
+    return _device.like_input(out, X)
+
+
+def singular_values(X):
+    """Singular values of a matrix iterate, descending (what `la.svd(X)[1]` gives the nuclear-norm penalty of
+    reference logistic_matrix_completion.py:43), from the same Jacobi kernel."""
+    _, sv = _nuclear(X, 0.0, False)
+    return _device.like_input(_device.torch().sort(sv, descending=True).values, X)
 
 
 def _rows(X, mode, p, want_out=True, want_norms=False):

@@ -257,6 +257,16 @@ int fb200_tv_grad_bb_fused(const double* R, int64_t n0, int64_t n1, double* g, i
 int fb200_tv_iter_fused(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, int loss,
                         const double* b, double* x1, double* g1, double* scal, void* ws, void* stream);
 
+/* whole accelerated (FISTA) TV trial in one pass (reference __init__.py:181-188,220-260 with tv_denoising.py:26-63,
+ * 85-96): prox point xa1 and its image za1 = div(xa1), extrapolation x1 = xa1 + c (xa1 - xa0), z1 = za1 + c (za1 - za0),
+ * g1 = grad(gradf(z1)); scal[S_F] = raw f(za1) (line search, :200), scal[S_AUX3] = raw f(z1) (:245),
+ * scal[S_RESTART] = <x0 - xa1, xa1 - xa0> (:231), scal[S_XMXH_SQ] with the extrapolated x1 (:274), BB sums as above.
+ * c is the extrapolation weight (alpha0 - 1) / alpha1 the caller expects; if the restart test of this trial says
+ * otherwise the caller repeats the call with c = 0.  15U bytes.                                                    */
+int fb200_tv_fista_fused(const double* x0, const double* g0, double tau, double c, int64_t n0, int64_t n1, int loss,
+                         const double* b, const double* xa0, const double* za0, double* xa1, double* za1,
+                         double* x1, double* g1, double* scal, void* ws, void* stream);
+
 /* ---- multi-GPU (A row-partitioned): all-reduce of the A^T r partials over NVLink peer memory fused
  * with the BB epilogue.  peer_ptrs[k] (host array, P entries) is the address, in THIS process, of rank k's partial:
  * n doubles of gradient partial followed by one double of raw loss partial.  g = sum_k partial_k in rank order
@@ -274,6 +284,16 @@ int fb200_peer_allreduce_bb(const uint64_t* peer_ptrs, int P, int64_t n, double*
  * out == NULL skips the prox; norms (optional, rows doubles) receives |X_i|_2                              */
 int fb200_prox_rows(const double* x, int64_t rows, int64_t cols, int mode, double p, double* out, double* norms,
                     void* stream);
+
+/* singular-value soft threshold  out = U diag(max(s - t, 0)) V  of an M x N row-major matrix: the reference's
+ * proximal.project_Lnuc_ball (proximal.py:44-55, la.svd + shrink + U @ S @ V; used by
+ * examples/logistic_matrix_completion.py:42-45), by one-sided Jacobi in one CTA -- no library SVD.
+ * svals (optional, min(M,N) doubles) receives the singular values, unsorted; out == NULL computes them only.
+ * scratch: fb200_prox_nuclear_scratch_doubles(M, N) doubles (0 = the matrix fits shared memory, pass NULL).
+ * info (optional, 2 ints, device): sweeps used, converged flag.                                              */
+size_t fb200_prox_nuclear_scratch_doubles(int64_t M, int64_t N);
+int fb200_prox_nuclear(const double* X, int64_t M, int64_t N, int64_t ldx, double t, double* out, int64_t ldo,
+                       double* svals, double* scratch, int* info, void* stream);
 
 /* ---- small reductions used by the prologue and the generic (untagged-callable) path ---------
  * out (device) receives: dot = <a,b>; diff_nrm2sq = |a-b|^2; asum = sum |a|                   */

@@ -64,7 +64,7 @@ def _solve(case, opts):
         f = lambda Z: t.sum(t.log(1 + t.exp(Z)) - (B == 1) * Z)
         gradf = lambda Z: -B / (1 + t.exp(B * Z))
         # la.norm(np.diag(s), 1) of the reference is the MATRIX 1-norm of diag(s), i.e. the largest singular value
-        g = lambda X: mu * t.linalg.svdvals(X).max()
+        g = lambda X: mu * fasta.proximal.singular_values(X).max()
         proxg = lambda X, tt: fasta.proximal.project_Lnuc_ball(X, tt * mu)
         return fasta.fasta(None, None, f, gradf, g, proxg, x0, **opts)
     raise ValueError(e.name)

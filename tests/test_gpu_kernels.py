@@ -127,6 +127,31 @@ def test_l1_ball_projection_large_and_penalties():
     assert np.array_equal(fasta.proximal.TVBall().prox(Y, 0.1), Y / nrm[..., None])
 
 
+@pytest.mark.parametrize("M,N", [(40, 60), (60, 40), (7, 7), (1, 5), (5, 1), (33, 90), (120, 300), (300, 120)])
+def test_nuclear_prox_jacobi_svd(M, N):
+    """Singular-value soft threshold by the one-sided Jacobi kernel vs numpy's SVD (reference proximal.py:44-55);
+    the two larger shapes take the global-scratch path, (M > N) the transposed one; one case is rank deficient."""
+    import fasta
+    import torch
+    rng = np.random.default_rng(M * 1000 + N)
+    X = rng.standard_normal((M, N))
+    if M > 5:
+        X[3] = 2 * X[2]
+    for t in (0.0, 1.5, 1e3):
+        U, s, V = np.linalg.svd(X, full_matrices=False)
+        want = U @ np.diag(np.maximum(s - t, 0)) @ V
+        got = fasta.proximal.project_Lnuc_ball(X, t)
+        assert isinstance(got, np.ndarray) and got.shape == X.shape
+        assert np.abs(got - want).max() <= 1e-12 * max(s[0], 1.0)
+    sv = fasta.proximal.singular_values(X)
+    assert np.abs(sv - s).max() <= 1e-12 * s[0]
+    Xd = torch.from_numpy(X).cuda()
+    a, b = fasta.proximal.project_Lnuc_ball(Xd, 1.5), fasta.proximal.project_Lnuc_ball(Xd, 1.5)
+    assert a.is_cuda and torch.equal(a, b)                 # bit-reproducible run to run
+    # non-contiguous input (a transposed view) is handled
+    assert np.abs(fasta.proximal.project_Lnuc_ball(Xd.t(), 1.5).cpu().numpy() - a.cpu().numpy().T).max() <= 1e-12 * s[0]
+
+
 def test_losses():
     import fasta
     rng = np.random.RandomState(5)
@@ -185,6 +210,50 @@ def test_tv_whole_iteration_kernel(n0, n1):
     for slot, want in ((_cabi.S_DX_G0, dot(dx, g0)), (_cabi.S_DX_SQ, dot(dx, dx)), (_cabi.S_XMXH_SQ, dot(y - h, y - h)),
                        (_cabi.S_F, dot(r, r)), (_cabi.S_DX_DG, dot(dx, dg)), (_cabi.S_DG_SQ, dot(dg, dg)),
                        (_cabi.S_G1_SQ, dot(g, g))):
+        assert abs(s[slot] - want) <= 1e-12 * max(abs(want), 1e-3), (n0, n1, slot, s[slot], want)
+
+
+@pytest.mark.parametrize("c", [0.0, 0.4375, 0.83])
+@pytest.mark.parametrize("n0,n1", [(64, 64), (33, 130), (1, 7), (5, 1), (2, 2), (300, 257), (70, 64)])
+def test_tv_fista_iteration_kernel(n0, n1, c):
+    """fb200_tv_fista_fused: prox point, its image, the extrapolated x1 and the gradient at the extrapolated z are
+    bit-identical to the numpy expressions of the reference lines (__init__.py:181-188,242-248), the nine sums to
+    reduction rounding."""
+    from fasta import _cabi, _device
+    from oracle import problems
+    torch = _t()
+    lib = _cabi.load()
+    rng = np.random.RandomState(5 * n0 + n1)
+    x0, g0, xa0 = (rng.randn(n0, n1, 2) for _ in range(3))
+    b, za0 = rng.randn(n0, n1), rng.randn(n0, n1)
+    tau = 0.3
+    d = {k: torch.from_numpy(v).cuda() for k, v in dict(x0=x0, g0=g0, b=b, xa0=xa0, za0=za0).items()}
+    xa1, x1, g1 = (torch.full((n0, n1, 2), np.nan, dtype=torch.float64, device="cuda") for _ in range(3))
+    za1 = torch.full((n0, n1), np.nan, dtype=torch.float64, device="cuda")
+    ws = _device.Workspace(1, 1)
+    _cabi.check(lib.fb200_tv_fista_fused(d["x0"].data_ptr(), d["g0"].data_ptr(), tau, c, n0, n1, _cabi.LOSS_LEAST_SQUARES,
+                                         d["b"].data_ptr(), d["xa0"].data_ptr(), d["za0"].data_ptr(), xa1.data_ptr(),
+                                         za1.data_ptr(), x1.data_ptr(), g1.data_ptr(), ws.scal.data_ptr(),
+                                         ws.buf.data_ptr(), _device.stream_ptr()))
+    s = ws.fetch().copy()
+    h = x0 - tau * g0
+    nrm = np.maximum(np.sqrt(h[..., 0] * h[..., 0] + h[..., 1] * h[..., 1]), 1.0)
+    y = h / nrm[..., None]
+    zp = problems.tv_div(y)
+    xe = y + c * (y - xa0)
+    ze = zp + c * (zp - za0)
+    r = ze - b
+    g = problems.tv_grad(r)
+    assert np.array_equal(xa1.cpu().numpy(), y)
+    assert np.array_equal(za1.cpu().numpy(), zp)
+    assert np.array_equal(x1.cpu().numpy(), xe)
+    assert np.array_equal(g1.cpu().numpy(), g)
+    dx = y - x0
+    dg = g + (h - x0) / tau
+    dot = lambda u, v: float(np.sum(u * v))
+    for slot, want in ((_cabi.S_DX_G0, dot(dx, g0)), (_cabi.S_DX_SQ, dot(dx, dx)), (_cabi.S_XMXH_SQ, dot(xe - h, xe - h)),
+                       (_cabi.S_F, dot(zp - b, zp - b)), (_cabi.S_AUX3, dot(r, r)), (_cabi.S_DX_DG, dot(dx, dg)),
+                       (_cabi.S_DG_SQ, dot(dg, dg)), (_cabi.S_G1_SQ, dot(g, g)), (_cabi.S_RESTART, dot(x0 - y, y - xa0))):
         assert abs(s[slot] - want) <= 1e-12 * max(abs(want), 1e-3), (n0, n1, slot, s[slot], want)
 
 

@@ -143,12 +143,29 @@ def test_tv_two_kernel_iteration_matches_golden(case, mode, monkeypatch):
     assert_trajectory(res, gold, label=f"tv-two-kernel/{case}/{mode}")
 
 
-def test_tv_fused_is_default_for_non_accelerated():
+def test_tv_fused_is_default(monkeypatch):
     import fasta
     p = problems.build("tv_64", 0)
     A, loss, pen = tagged(p)
     assert fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3).tv_fused
-    assert not fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3, accelerate=True).tv_fused
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3, accelerate=True)
+    assert res.tv_fused
+    monkeypatch.setattr(fasta._backends.TVDriver, "fista_fused_ok", False)
+    ref = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, verbose=False, max_iters=3, accelerate=True)
+    assert not ref.tv_fused and ref.kernel_launches >= res.kernel_launches + 3 * 3     # one kernel per trial instead of four
+
+
+@pytest.mark.parametrize("case", ["tv_64", "tv_128"])
+def test_tv_accelerated_without_the_fista_kernel_matches_golden(case, monkeypatch):
+    """Accelerated TV with the separate step / div / extrapolate / grad kernels (the fused FISTA kernel is the default)."""
+    import fasta
+    monkeypatch.setattr(fasta._backends.TVDriver, "fista_fused_ok", False)
+    gold = load_golden(case, "accelerated")
+    p = problems.build(case, int(gold["seed"]))
+    A, loss, pen = tagged(p)
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert not res.tv_fused
+    assert_trajectory(res, gold, label=f"tv-accel-unfused/{case}")
 
 
 def test_single_pass_is_default_for_dense_solves(monkeypatch):
