@@ -769,10 +769,10 @@ extern "C" int fb200_tv_iter_fused(const double* x0, const double* g0, double ta
         if (mv < 0) { const char* e = getenv("FASTA_B200_TVM_VARIANT"); mv = e ? atoi(e) : 0; }
 #define TVM_LAUNCH(L, U, B) TVM_LAUNCH_FD(L, U, B, false)
 #define TVM_LAUNCH_FD(L, U, B, FD) tv_iter_march_kernel<L, U, B, FD><<<unsigned(blocks), TVM_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, int(n0), int(n1), b, (double2*)x1, (double2*)g1, int(warps_x), int(strip), scal, w.red, w.counter)
-#define TVM_PICK(L) switch (mv) { case 1: TVM_LAUNCH(L, 4, 6); break; case 2: TVM_LAUNCH(L, 8, 4); break; case 3: TVM_LAUNCH(L, 2, 8); break; case 4: TVM_LAUNCH_FD(L, 4, 4, true); break; case 5: TVM_LAUNCH_FD(L, 4, 5, true); break; default: TVM_LAUNCH(L, 4, 4); }
+#define TVM_PICK(L) switch (mv) { case 1: TVM_LAUNCH(L, 4, 6); break; case 2: TVM_LAUNCH(L, 8, 4); break; case 3: TVM_LAUNCH(L, 2, 8); break; case 4: TVM_LAUNCH(L, 4, 4); break; case 5: TVM_LAUNCH_FD(L, 4, 5, true); break; default: TVM_LAUNCH_FD(L, 4, 4, true); }
         switch (loss) {
             case FB200_LOSS_LEAST_SQUARES: TVM_PICK(FB200_LOSS_LEAST_SQUARES) break;
-            case FB200_LOSS_LOGISTIC: TVM_LAUNCH(FB200_LOSS_LOGISTIC, 4, 4); break;
+            case FB200_LOSS_LOGISTIC: TVM_LAUNCH_FD(FB200_LOSS_LOGISTIC, 4, 4, true); break;
             default: set_error("tv_iter_fused: unsupported loss tag %d", loss); return 1;
         }
 #undef TVM_PICK
@@ -825,10 +825,10 @@ extern "C" int fb200_tv_fista_fused(const double* x0, const double* g0, double t
 #define TVF_LAUNCH_FD(L, U, B, FD) tv_fista_march_kernel<L, U, B, FD><<<unsigned(blocks), TVM_THREADS, 0, st>>>((const double2*)x0, (const double2*)g0, tau, c, int(n0), int(n1), b, (const double2*)xa0, za0, (double2*)xa1, za1, (double2*)x1, (double2*)g1, int(warps_x), int(strip), scal, w.red, w.counter)
     switch (loss) {
         case FB200_LOSS_LEAST_SQUARES:
-            switch (mv) { case 1: TVF_LAUNCH(FB200_LOSS_LEAST_SQUARES, 4, 3); break; case 2: TVF_LAUNCH(FB200_LOSS_LEAST_SQUARES, 2, 3); break;
-                          case 3: TVF_LAUNCH_FD(FB200_LOSS_LEAST_SQUARES, 2, 4, true); break; default: TVF_LAUNCH(FB200_LOSS_LEAST_SQUARES, 2, 4); }
+            switch (mv) { case 1: TVF_LAUNCH_FD(FB200_LOSS_LEAST_SQUARES, 4, 3, true); break; case 2: TVF_LAUNCH(FB200_LOSS_LEAST_SQUARES, 4, 3); break;
+                          case 3: TVF_LAUNCH(FB200_LOSS_LEAST_SQUARES, 2, 4); break; default: TVF_LAUNCH_FD(FB200_LOSS_LEAST_SQUARES, 2, 4, true); }
             break;
-        case FB200_LOSS_LOGISTIC: TVF_LAUNCH(FB200_LOSS_LOGISTIC, 2, 4); break;
+        case FB200_LOSS_LOGISTIC: TVF_LAUNCH_FD(FB200_LOSS_LOGISTIC, 2, 4, true); break;
         default: set_error("tv_fista_fused: unsupported loss tag %d", loss); return 1;
     }
 #undef TVF_LAUNCH
