@@ -17,6 +17,10 @@ fbs_step_kernel(const double* __restrict__ x0, const double* __restrict__ g0, do
                 double* __restrict__ x1, double* __restrict__ dx, double* scal, double* red,
                 unsigned* counter) {
     if (PROX == FB200_PROX_L1BALL) p0 = scal[FB200_S_THETA];
+    if (isnan(tau)) {                                       // step size left on the device by fb200_stepsize_next
+        tau = __ldcg(&scal[FB200_S_TAU]);
+        if (PROX == FB200_PROX_SHRINK) p0 = tau * p1;       // proxg(x, t) = shrink(x, t * mu), mu passed in p1
+    }
     double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -286,6 +290,7 @@ __global__ void __launch_bounds__(VEC_THREADS)
 bb_kernel(const double* __restrict__ gsrc, int nsplit, int64_t ld, int64_t n, double* __restrict__ g,
           const double* __restrict__ x0, const double* __restrict__ xhat, const double* __restrict__ dx,
           double tau, double* scal, double* red, unsigned* counter) {
+    if (BB >= 2 && isnan(tau)) tau = __ldcg(&scal[FB200_S_TAU]);
     double s[3] = {0.0, 0.0, 0.0};
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -347,6 +352,7 @@ __global__ void __launch_bounds__(VEC_THREADS)
 peer_allreduce_bb_kernel(PeerParts parts, int P, int64_t n, double* __restrict__ g, const double* __restrict__ x0,
                          const double* __restrict__ xhat, const double* __restrict__ dx, double tau, int with_loss,
                          double* scal, double* red, unsigned* counter) {
+    if (BB >= 2 && isnan(tau)) tau = __ldcg(&scal[FB200_S_TAU]);
     double s[3] = {0.0, 0.0, 0.0};
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -370,6 +376,28 @@ peer_allreduce_bb_kernel(PeerParts parts, int P, int64_t n, double* __restrict__
                                 BB >= 2 ? scal + FB200_S_DG_SQ : nullptr, scal + FB200_S_G1_SQ};
         grid_sum<3>(s, red, counter, out);
     }
+}
+
+// =================================================================================================
+// Barzilai-Borwein step size on the device (reference __init__.py:253-270), the np.float64 algebra of the host loop:
+// la.norm(.)**2 is sqrt(.)**2, Python max(q, 0) keeps a nan q.  One thread; queued behind the trial's kernels.
+// =================================================================================================
+__global__ void stepsize_next_kernel(double* scal, double tau, int adaptive) {
+    const double tau0 = isnan(tau) ? scal[FB200_S_TAU] : tau;
+    double tau1 = tau0;
+    if (adaptive) {
+        const double dx_norm = sqrt(scal[FB200_S_DX_SQ]);
+        const double dotprod = scal[FB200_S_DX_DG];
+        const double tau_s = (dx_norm * dx_norm) / dotprod;
+        const double dg_norm = sqrt(scal[FB200_S_DG_SQ]);
+        const double q = dotprod / (dg_norm * dg_norm);
+        const double tau_m = (0.0 > q) ? 0.0 : q;
+        if (2 * tau_m > tau_s) tau1 = tau_m;
+        else tau1 = tau_s - .5 * tau_m;
+        if (tau1 <= 0 || isinf(tau1) || isnan(tau1)) tau1 = tau0 * 1.5;
+    }
+    scal[FB200_S_TAU_USED] = tau0;
+    scal[FB200_S_TAU] = tau1;
 }
 
 // =================================================================================================
@@ -546,6 +574,12 @@ extern "C" int fb200_accel_step(double c, const double* xa1, const double* xa0, 
     }
 #undef FB200_ACCEL
     return check_launch("accel_step");
+}
+
+extern "C" int fb200_stepsize_next(double* scal, double tau, int adaptive, void* stream) {
+    if (!scal) { set_error("stepsize_next: null scalar block"); return 1; }
+    stepsize_next_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(scal, tau, adaptive);
+    return check_launch("stepsize_next");
 }
 
 extern "C" int fb200_loss_eval(int loss, const double* z, const double* b, int64_t m, double* r, double* scal,

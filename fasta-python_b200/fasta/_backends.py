@@ -295,12 +295,14 @@ class FusedBackend:
         self.m = int(np.prod(driver.zshape))
         self.ws = _device.acquire_workspace(*driver.workspace_dims(), device=dev)
         new = lambda k: t.empty(k, dtype=t.float64, device=dev)
-        # three iterate buffers: current, previous and the best iterate so far -- the best iterate (reference :298-300)
-        # is kept by INDEX, never copied: a new trial is written to the buffer that is neither x0 nor the best
-        self.X = [new(self.n), new(self.n), new(self.n)]
+        # four iterate buffers: the best iterate so far (reference :298-300) is kept by INDEX, never copied, and a trial
+        # queued ahead of the line-search decision must not overwrite the x0 of the trial it speculates on: a new trial
+        # is written to the buffer that is none of {its x0, the previous x0, the best}
+        self.X = [new(self.n) for _ in range(4)]
         # gradient buffers carry 8 spare doubles: a sharded driver packs the loss partial behind the
         # gradient so that ONE all-reduce per iteration moves both
-        self._Gbuf = [new(self.n + 8), new(self.n + 8)]
+        # (three of them: a trial queued ahead of the line-search decision must not overwrite the gradient at x0)
+        self._Gbuf = [new(self.n + 8), new(self.n + 8), new(self.n + 8)]
         self.G = [g[:self.n] for g in self._Gbuf]
         self.XH, self.DX = new(self.n), new(self.n)
         self.Z, self.R = new(self.m), new(self.m)
@@ -324,9 +326,18 @@ class FusedBackend:
         self._spec = None
         self._ahead = False
         self._pending = None
+        self._spec_mode = False
+        self._spec_adaptive = 0
         # TV: one fused kernel per half-iteration (see TVDriver.step_forward)
         self.use_tv_fused = ((not self.accelerate) and isinstance(driver, TVDriver) and driver.fused_step_ok
                              and penalty.tag == S.PROX_TV_BALL and loss.tag != S.LOSS_NONE)
+        # Speculative run-ahead: the step size of the next trial stays on the device (fb200_stepsize_next), so the next
+        # iteration's trial is queued BEFORE the host has seen this trial's sums; see _loop.run
+        tv_iter = self.use_tv_fused and driver.iter_fused_ok
+        elementwise = penalty.tag in (S.PROX_NONNEG, S.PROX_BOX, S.PROX_IDENTITY) or \
+            (penalty.tag == S.PROX_SHRINK and np.ndim(getattr(penalty, "mu", 0.0)) == 0)
+        self.speculate_ok = ((tv_iter or (self.use_sweep and elementwise))
+                             and os.environ.get("FASTA_B200_SPECULATE", "1") != "0")
         # TV + FISTA: the whole accelerated trial in one kernel (see trial_accel)
         self.use_tv_accel = (self.accelerate and isinstance(driver, TVDriver) and driver.fused_step_ok
                              and driver.fista_fused_ok and penalty.tag == S.PROX_TV_BALL
@@ -363,7 +374,7 @@ class FusedBackend:
 
     def _probe_outputs(self):
         # X[other] and G[other] are free until the first advance(); Z / R are scratch here
-        return self.X[(self.ic + 1) % 3], self.G[1 - self.gc]
+        return self.X[(self.ic + 1) % 4], self.G[(self.gc + 1) % 3]
 
     def lipschitz_push(self, k, v):
         """Upload probe k (0/1) and queue d_k = A^H gradf(A v_k)."""
@@ -425,57 +436,87 @@ class FusedBackend:
         return Scalars(f=self.loss.finalize(s[S.S_F]), pen=self.pen.value(s[S.S_PEN]), g_sq=s[S.S_G1_SQ])
 
     def advance(self):
+        prev = self.ip
         self.ip = self.ic
-        self.ic = next(k for k in (0, 1, 2) if k != self.ip and k != self.ib)
-        self.gp, self.gc = self.gc, 1 - self.gc
+        self.ic = next(k for k in (0, 1, 2, 3) if k != self.ip and k != self.ib and k != prev)
+        self.gp, self.gc = self.gc, (self.gc + 1) % 3
         if self.accelerate:
             self.ap, self.ac = self.ac, 1 - self.ac
 
     # A trial is queued (all kernels asynchronous) and collected (one fetch).  The host loop uses the split to queue
     # the NEXT iteration's trial as soon as the new step size is known and to do its bookkeeping (histories, best
     # iterate, stop rule) while the device already works; trial() is queue + collect.
+    def rotation(self):
+        return self.ic, self.ip, self.gc, self.gp, self._ahead
+
+    def restore(self, state):
+        self.ic, self.ip, self.gc, self.gp, self._ahead = state
+
+    def speculate_begin(self, adaptive):
+        """From now on every trial is followed by fb200_stepsize_next (the next step size stays on the device) and an
+        in-stream snapshot of its sums, so trials can be queued with tau=None before the previous one was collected."""
+        self._spec_mode = True
+        self._spec_adaptive = 1 if adaptive else 0
+
     def _queue_trial(self, tau):
+        """Queue one trial (reference :181-188, plus the speculative gradient of the single-pass kernels).  tau=None:
+        the kernels read the step size fb200_stepsize_next left in scal[S_TAU].  Returns a handle for _collect_trial."""
         x0, g0 = self.X[self.ip], self.G[self.gp]
         x1 = self.XA[self.ac] if self.accelerate else self.X[self.ic]
         z1 = self.ZA[self.ac] if self.accelerate else self.Z
         xa_prev = self.XA[self.ap] if self.accelerate else None
-        p0, p1 = self.pen.params(tau)
+        if tau is None:
+            tau = float("nan")
+            p0, p1 = (0.0, float(self.pen.mu)) if self.pen.tag == S.PROX_SHRINK else self.pen.params(1.0)
+        else:
+            p0, p1 = self.pen.params(tau)
         st = self._st()
+        kind = None
         if self.use_tv_fused and self.drv.iter_fused_ok:
             # one kernel per trial; the gradient of an accepted trial is already in G[gc] (speculative, like the sweep)
             self.drv.iterate_fused(x0, g0, tau, self.loss.tag, self.loss.b, x1, self.G[self.gc], self.ws)
-            return "tv_iter"
-        if self.use_tv_fused:
+            kind = "tv_iter"
+        elif self.use_tv_fused:
             self.drv.step_forward(x0, g0, tau, self.loss.tag, self.loss.b, x1, self.R, self.ws)
-            return "tv_step"
-        if self.pen.tag == S.PROX_L1BALL:
-            _cabi.check(self.lib.fb200_forward_step(x0.data_ptr(), g0.data_ptr(), float(tau), self.n,
-                                                    self.XH.data_ptr(), st), "fb200_forward_step")
-            _cabi.check(self.lib.fb200_l1ball_threshold(self.XH.data_ptr(), self.n, float(self.pen.radius),
-                                                        self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
-                        "fb200_l1ball_threshold")
-            self.launches += 2
-        _cabi.check(self.lib.fb200_fbs_step(x0.data_ptr(), g0.data_ptr(), float(tau), self.pen.tag, float(p0), float(p1),
-                                            _device.ptr(xa_prev), self.n, self.XH.data_ptr(), x1.data_ptr(),
-                                            self.DX.data_ptr(), self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
-                    "fb200_fbs_step")
+            kind = "tv_step"
+        else:
+            if self.pen.tag == S.PROX_L1BALL:
+                _cabi.check(self.lib.fb200_forward_step(x0.data_ptr(), g0.data_ptr(), float(tau), self.n,
+                                                        self.XH.data_ptr(), st), "fb200_forward_step")
+                _cabi.check(self.lib.fb200_l1ball_threshold(self.XH.data_ptr(), self.n, float(self.pen.radius),
+                                                            self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
+                            "fb200_l1ball_threshold")
+                self.launches += 2
+            _cabi.check(self.lib.fb200_fbs_step(x0.data_ptr(), g0.data_ptr(), float(tau), self.pen.tag, float(p0),
+                                                float(p1), _device.ptr(xa_prev), self.n, self.XH.data_ptr(), x1.data_ptr(),
+                                                self.DX.data_ptr(), self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
+                        "fb200_fbs_step")
+            self.launches += 1
+            if self.use_sweep:
+                self.drv.sweep(x1, self.loss.tag, self.loss.b, z1, self.R, self.G[self.gc], 2, x0, self.XH, self.DX, tau,
+                               self.ws)
+                kind = "sweep"
+            else:
+                self.drv.forward(x1, self.loss.tag, self.loss.b, z1, self.R, self.ws)
+                kind = "forward"
+        if not self._spec_mode:
+            return kind, None
+        _cabi.check(self.lib.fb200_stepsize_next(self.ws.scal.data_ptr(), float(tau), self._spec_adaptive, st),
+                    "fb200_stepsize_next")
         self.launches += 1
-        if self.use_sweep:
-            self.drv.sweep(x1, self.loss.tag, self.loss.b, z1, self.R, self.G[self.gc], 2, x0, self.XH, self.DX, tau,
-                           self.ws)
-            return "sweep"
-        self.drv.forward(x1, self.loss.tag, self.loss.b, z1, self.R, self.ws)
-        return "forward"
+        return kind, self.ws.snapshot()
 
-    def _collect_trial(self, kind):
-        s = self.ws.fetch()
+    def _collect_trial(self, handle):
+        kind, ticket = handle
+        s = self.ws.fetch() if ticket is None else self.ws.collect(ticket)
         if kind in ("tv_iter", "sweep"):
             self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
+        tau_next = s[S.S_TAU] if ticket is not None else None
         if kind in ("tv_iter", "tv_step"):
             return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
-                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0))
+                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0), tau_next=tau_next)
         return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
-                       xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART])
+                       xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART], tau_next=tau_next)
 
     def trial(self, tau):
         return self._collect_trial(self._queue_trial(tau))

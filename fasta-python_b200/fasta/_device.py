@@ -63,6 +63,12 @@ class Workspace:
         self._np = self.host.numpy()
         self.scal_saved = t.zeros(_cabi.NSCAL, dtype=t.float64, device=self.device)   # snapshot of the start() sums
         self._stage = None                                                            # pinned upload staging (2 vectors)
+        # in-stream snapshots of the scalar block: a trial queued ahead overwrites `scal` before the host has read the
+        # previous trial's sums, so each trial's sums are copied to their own pinned slot, fenced by an event
+        self._slots = t.zeros((4, _cabi.NSCAL), dtype=t.float64).pin_memory()
+        self._slots_np = self._slots.numpy()
+        self._events = [t.cuda.Event() for _ in range(4)]
+        self._ticket = 0
 
     def grow(self, M, N):
         need = int(self.lib.fb200_workspace_bytes(int(M), int(N)))
@@ -77,6 +83,18 @@ class Workspace:
         self.host.copy_(self.scal_saved if saved else self.scal, non_blocking=True)
         t.cuda.current_stream().synchronize()
         return self._np      # np.float64 elements
+
+    def snapshot(self):
+        """Queue a D2H copy of the scalar block into the next pinned slot; returns the ticket for collect()."""
+        k = self._ticket & 3
+        self._ticket += 1
+        self._slots[k].copy_(self.scal, non_blocking=True)
+        self._events[k].record()
+        return k
+
+    def collect(self, ticket):
+        self._events[ticket].synchronize()
+        return self._slots_np[ticket]
 
     def stage(self, slot, n):
         """Pinned host staging vector `slot` (0/1) of n doubles, so that an upload neither blocks the host

@@ -129,13 +129,36 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     fused_accel = accelerate and (getattr(be, "use_sweep_accel", False) or getattr(be, "use_tv_accel", False))
     run_ahead = hasattr(be, "trial_launch") and not fused_accel and os.environ.get("FASTA_B200_RUN_AHEAD", "1") != "0"
     queued = False
+    # Speculative run-ahead (back-ends with speculate_ok): the Barzilai-Borwein step size of a trial is formed on the
+    # device right behind it (fb200_stepsize_next, the algebra of :253-270), so the NEXT iteration's trial -- which in
+    # the common case differs from this one only in the step size and the buffer rotation -- is queued before the host
+    # has read this trial's sums.  The device never waits for the host.  If the line search rejects the trial, the
+    # speculated one is dropped (it only wrote scratch buffers) and the backtracking runs as usual.
+    speculate = run_ahead and not accelerate and getattr(be, "speculate_ok", False)
+    if speculate:
+        be.speculate_begin(adaptive)
+    pending = None            # handle of the trial queued for iteration i
+    ahead = None              # handle of the trial speculatively queued for iteration i + 1
 
     i = 0
     while i < max_iters:
         times[i] = time()                                   # ref :173
         g0_sq = g1_sq
         tau0 = tau1
-        if queued:
+        if speculate:
+            if pending is None:
+                be.advance()                                # ref :176-178
+                pending = be._queue_trial(tau0)             # ref :181-188
+            be._ahead = False
+            rot = be.rotation()
+            ahead = None
+            if i + 1 < max_iters:
+                be.advance()
+                be._ahead = True
+                ahead = be._queue_trial(None if adaptive else tau0)
+            t = be._collect_trial(pending)
+            pending = None
+        elif queued:
             t = be.trial_finish()
             queued = False
         else:
@@ -149,6 +172,9 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
             while f1 - (f_window_max + t.dx_g0 + _sq(t.dx_sq) / (2 * tau0)) > EPSILON \
                     and backtrack_count < max_backtracks:
                 tau0 *= stepsize_shrink
+                if ahead is not None:                       # the speculated trial assumed acceptance: drop it
+                    be.restore(rot)
+                    ahead = None
                 t = be.trial_accel(tau0, alpha1, restart) if fused_accel else be.trial(tau0)
                 f1 = t.f
                 backtrack_count += 1
@@ -182,6 +208,8 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
                 tau1 = tau_s - .5 * tau_m
             if tau1 <= 0 or np.isinf(tau1) or np.isnan(tau1):
                 tau1 = tau0 * 1.5
+            if speculate:
+                tau1 = t.tau_next                           # the device's value of the same algebra: the one trial i+1 uses
 
         residual_hist[i] = dx_norm / tau0                   # ref :272-281
         normalizer = max(np.sqrt(g0_sq), np.sqrt(xmxh_sq) / tau0) + EPSILON
@@ -192,7 +220,13 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
 
         # ref :308 -- evaluated here (it depends only on the residuals above) so that no trial is queued past the end
         stop = stop_rule(i, residual_hist[i], norm_residual_hist[i], max_residual, tolerance)
-        if run_ahead and not stop and i + 1 < max_iters:
+        if speculate:
+            if ahead is None and not stop and i + 1 < max_iters:
+                be.advance()                                # after a backtracked iteration: queue the next trial now
+                be._ahead = True
+                ahead = be._queue_trial(tau1)
+            pending, ahead = ahead, None
+        elif run_ahead and not stop and i + 1 < max_iters:
             be.advance()                                    # next iteration's ref :176-188, queued now
             be.trial_launch(tau1)
             queued = True

@@ -76,10 +76,10 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     pen = be.pen
     mu = float(pen.mu) if pen.tag == S.PROX_SHRINK else 0.0
     lo, hi = (float(pen.lo), float(pen.hi)) if pen.tag == S.PROX_BOX else (0.0, 0.0)
-    ia, ib_, ibest = be.ic, (be.ic + 1) % 3, (be.ic + 2) % 3
+    ia, ib_, ibest = be.ic, (be.ic + 1) % 4, (be.ic + 2) % 4
     xa, xb, best = be.X[ia], be.X[ib_], be.X[ibest]
     best.copy_(xa)                                          # stays the answer if no iterate ever improves (nan quality)
-    ga, gb = be.G[be.gc], be.G[1 - be.gc]
+    ga, gb = be.G[be.gc], be.G[(be.gc + 1) % 3]
     alpha_d = f64(max_iters) if accelerate else None
     fista = [be.XA[be.ac], be.XA[1 - be.ac], be.ZA[be.ac], be.ZA[1 - be.ac], alpha_d] if accelerate else [None] * 5
     t_launch = time()

@@ -47,7 +47,9 @@ enum {
     FB200_S_AUX0     = 10, /* dot / norm helpers write here by default */
     FB200_S_AUX1     = 11,
     FB200_S_AUX2     = 12,
-    FB200_S_AUX3     = 13
+    FB200_S_AUX3     = 13,
+    FB200_S_TAU      = 14, /* step size for the NEXT trial, written by fb200_stepsize_next (__init__.py:253-270) */
+    FB200_S_TAU_USED = 15  /* step size the last trial ran with, written by fb200_stepsize_next */
 };
 
 /* loss tags: f and gradf evaluated on z = A x */
@@ -256,6 +258,16 @@ int fb200_tv_grad_bb_fused(const double* R, int64_t n0, int64_t n1, double* g, i
  * (9U bytes, U = n0*n1*8; reference __init__.py:181-188,248-260 with tv_denoising.py:26-63,85-96)        */
 int fb200_tv_iter_fused(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, int loss,
                         const double* b, double* x1, double* g1, double* scal, void* ws, void* stream);
+
+/* ---- device-side step size (run-ahead without a host round trip) ------------------------------------------
+ * fb200_stepsize_next forms the Barzilai-Borwein step size of reference __init__.py:253-270 from the sums of the
+ * trial just queued (scal[S_DX_SQ, S_DX_DG, S_DG_SQ]; adaptive = 0: tau1 = tau0) with the np.float64 algebra of the
+ * host loop and stores it in scal[FB200_S_TAU] (and the step size the trial ran with in scal[FB200_S_TAU_USED]).
+ * Every entry point that takes `double tau` (fb200_fbs_step, fb200_dense_sweep, fb200_bb_reduce,
+ * fb200_peer_allreduce_bb, fb200_tv_iter_fused, fb200_stepsize_next) accepts tau = NaN, meaning "read the step size
+ * from scal[FB200_S_TAU]": the host can queue the next iteration's trial before it has seen this one's sums.
+ * With tau = NaN fb200_fbs_step forms the shrink threshold as scal[FB200_S_TAU] * p1 (pass mu in p1).        */
+int fb200_stepsize_next(double* scal, double tau, int adaptive, void* stream);
 
 /* whole accelerated (FISTA) TV trial in one pass (reference __init__.py:181-188,220-260 with tv_denoising.py:26-63,
  * 85-96): prox point xa1 and its image za1 = div(xa1), extrapolation x1 = xa1 + c (xa1 - xa0), z1 = za1 + c (za1 - za0),

@@ -224,6 +224,72 @@ class CpuFusedBackend:
         return self.best.numpy().reshape(self.shape).copy()
 
 
+class CpuSpeculatingBackend(CpuFusedBackend):
+    """The speculative run-ahead protocol of fasta._backends.FusedBackend (speculate_ok, _queue_trial(tau or None),
+    _collect_trial, rotation / restore) with eager CPU arithmetic: a queued trial is computed at once, its sums are
+    kept in its handle, and 'the step size on the device' is whatever the most recently QUEUED trial left there --
+    including trials the loop later drops -- exactly as the stream order makes it on the GPU."""
+
+    speculate_ok = True
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._ahead = False
+        self._spec = None
+        self.dev_tau = None
+        self.dropped = 0
+        self.queued = 0
+
+    def trial_launch(self, tau):               # presence enables run-ahead in _loop.run
+        raise AssertionError("the speculative protocol does not use trial_launch")
+
+    def speculate_begin(self, adaptive):
+        self.adaptive = bool(adaptive)
+
+    def rotation(self):
+        return self.x0, self.g0, self.x1, self.g1, self._ahead
+
+    def restore(self, state):
+        self.x0, self.g0, self.x1, self.g1, self._ahead = state
+        self.dropped += 1
+
+    def _queue_trial(self, tau):
+        self.queued += 1
+        tau0 = np.float64(self.dev_tau if tau is None else tau)
+        t = CpuFusedBackend.trial(self, tau0)
+        g = CpuFusedBackend.gradient(self, tau0, self.adaptive)
+        tau1 = tau0
+        if self.adaptive:                      # fb200_stepsize_next
+            with np.errstate(all="ignore"):
+                dx_norm = np.sqrt(t.dx_sq)
+                tau_s = dx_norm ** 2 / g.dx_dg
+                tau_m = max(g.dx_dg / np.sqrt(g.dg_sq) ** 2, 0)
+                tau1 = tau_m if 2 * tau_m > tau_s else tau_s - .5 * tau_m
+                if tau1 <= 0 or np.isinf(tau1) or np.isnan(tau1):
+                    tau1 = tau0 * 1.5
+        self.dev_tau = tau1
+        t.tau_next = tau1
+        return "sweep", (t, g)
+
+    def _collect_trial(self, handle):
+        t, g = handle[1]
+        self._spec = g
+        return t
+
+    def trial(self, tau):
+        return self._collect_trial(self._queue_trial(tau))
+
+    def gradient(self, tau, adaptive):
+        g, self._spec = self._spec, None
+        return g
+
+    def keep_best(self):
+        self.best = (self.x0 if self._ahead else self.x1).clone()
+
+    def iterate(self):
+        return (self.x0 if self._ahead else self.x1).numpy().reshape(self.shape)
+
+
 class HostPenalty:
     """params()/value() of fasta.proximal penalties without touching the GPU."""
 
@@ -240,9 +306,10 @@ class HostPenalty:
         return self.mu * raw if self.kind == "l1" else 0
 
 
-def backend_for(problem, accelerate, driver=None):
+def backend_for(problem, accelerate, driver=None, speculate=False):
     """CPU test-double back-end for an oracle.problems.Problem."""
     tag = S.LOSS_LEAST_SQUARES if problem.loss == "least_squares" else S.LOSS_LOGISTIC
     if driver is None:
         driver = CpuDenseDriver(problem.A) if problem.kind == "dense" else CpuTVDriver(*problem.x0.shape[:2])
-    return CpuFusedBackend(driver, tag, problem.b, HostPenalty(problem.penalty, problem.mu), problem.x0, accelerate)
+    cls = CpuSpeculatingBackend if speculate else CpuFusedBackend
+    return cls(driver, tag, problem.b, HostPenalty(problem.penalty, problem.mu), problem.x0, accelerate)

@@ -21,6 +21,33 @@ def test_host_loop_matches_golden(case, mode):
     assert_trajectory(res, gold, label=f"{case}/{mode}")
 
 
+@pytest.mark.parametrize("case,mode", [cm for cm in CASES if cm[1] != "accelerated"])
+def test_speculative_run_ahead_matches_golden(case, mode):
+    """The loop's speculative run-ahead (next trial queued with the step size 'left on the device' before this
+    trial's sums are read; dropped when the line search rejects) reproduces the same trajectories."""
+    gold = load_golden(case, mode)
+    p = problems.build(case, int(gold["seed"]))
+    be = backend_for(p, False, speculate=True)
+    be.load()
+    res = _loop.run(be, p.x0.shape, **gold["opts"])
+    assert_trajectory(res, gold, label=f"speculative/{case}/{mode}")
+    n = res.iteration_count
+    assert be.queued >= n and (be.dropped > 0 or res.backtracks == 0)
+    # with record_iterates / func the hooks must see the accepted iterate, not the speculated one
+    be = backend_for(p, False, speculate=True)
+    be.load()
+    opts = dict(gold["opts"], record_iterates=True, func=lambda x: float(np.abs(x).sum()), max_iters=min(n, 12))
+    np.random.seed(int(gold["seed"]) + 100)
+    res2 = _loop.run(be, p.x0.shape, **opts)
+    be = backend_for(p, False)
+    be.load()
+    np.random.seed(int(gold["seed"]) + 100)
+    ref2 = _loop.run(be, p.x0.shape, **opts)
+    assert res2.iteration_count == ref2.iteration_count and res2.backtracks == ref2.backtracks
+    assert np.array_equal(res2.iterates, ref2.iterates) and np.array_equal(res2.function_hist, ref2.function_hist)
+    assert np.array_equal(res2.solution, ref2.solution) and np.array_equal(res2.stepsizes, ref2.stepsizes)
+
+
 def test_verbose_output_format(capsys):
     gold = load_golden("lasso_200x1000_k10", "accelerated")
     p = problems.build("lasso_200x1000_k10", 0)
