@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
 dense_sweep_kernel(const double* __restrict__ A, int64_t lda, int M, int N, int Nc, const double* __restrict__ x,
                    const double* __restrict__ b, double* __restrict__ z, double* __restrict__ r,
                    double* __restrict__ gpart, int64_t ldg, double* __restrict__ fpart, int nstage,
-                   const double* __restrict__ za0, double* __restrict__ za1, double cacc, double* __restrict__ fpart2) {
+                   const double* __restrict__ za0, double* __restrict__ za1, double cacc, double* __restrict__ fpart2,
+                   const double* __restrict__ skip) {
+    if (skip && __ldcg(skip) != 0.0) return;       // speculative trial that must not run (fb200_trial_decide): whole grid
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int STAGE_BYTES = CPT * SW_GROUP * 16;
     double*   recv  = reinterpret_cast<double*>(smem + size_t(nstage) * STAGE_BYTES);     // [NSLOT][MAXCS]
@@ -239,7 +241,8 @@ dense_sweep_kernel(const double* __restrict__ A, int64_t lda, int M, int N, int 
 }
 
 // sum of the per-cluster loss partials in index order -> scal[S_F]
-__global__ void sweep_fsum_kernel(const double* __restrict__ fpart, int n, double* out) {
+__global__ void sweep_fsum_kernel(const double* __restrict__ fpart, int n, double* out, const double* skip) {
+    if (skip && __ldcg(skip) != 0.0) return;
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int i = 0; i < n; ++i) s += fpart[i];
@@ -253,7 +256,7 @@ struct SweepPlan {
 };
 
 typedef void (*SweepKernel)(const double*, int64_t, int, int, int, const double*, const double*, double*, double*,
-                            double*, int64_t, double*, int, const double*, double*, double, double*);
+                            double*, int64_t, double*, int, const double*, double*, double, double*, const double*);
 
 template <int LOSS>
 static SweepKernel pick_kernel(int cpt) {
@@ -383,15 +386,16 @@ static int sweep_launch(const double* A, int64_t lda, int64_t M, int64_t N, cons
     fill_launch(&cfg, attr, p, ncl, st);
     double* fpart = w.fpart;
     double* fpart2 = w.fpart + FPART_MAX / 2;
+    const double* skip = isnan(tau) ? scal + FB200_S_SKIP : nullptr;      // speculative trial: see fb200_trial_decide
     cudaError_t e = cudaLaunchKernelEx(&cfg, k, A, lda, int(M), int(N), p.nc, x, b, z, r, w.dense, ldg, fpart, p.nstage, za0, za1,
-                                       c, fpart2);
+                                       c, fpart2, skip);
     if (e != cudaSuccess) { set_error("dense_sweep: launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 1; }
     if (loss != FB200_LOSS_NONE) {
         if (za0) {
-            sweep_fsum_kernel<<<1, 32, 0, st>>>(fpart2, ncl, scal + FB200_S_F);       // prox point: the line-search value
-            sweep_fsum_kernel<<<1, 32, 0, st>>>(fpart, ncl, scal + FB200_S_AUX3);     // extrapolated point
+            sweep_fsum_kernel<<<1, 32, 0, st>>>(fpart2, ncl, scal + FB200_S_F, skip);       // prox point: the line-search value
+            sweep_fsum_kernel<<<1, 32, 0, st>>>(fpart, ncl, scal + FB200_S_AUX3, skip);     // extrapolated point
         } else {
-            sweep_fsum_kernel<<<1, 32, 0, st>>>(fpart, ncl, scal + FB200_S_F);
+            sweep_fsum_kernel<<<1, 32, 0, st>>>(fpart, ncl, scal + FB200_S_F, skip);
         }
         if (check_launch("sweep_fsum_kernel")) return 1;
     }

@@ -17,7 +17,8 @@ fbs_step_kernel(const double* __restrict__ x0, const double* __restrict__ g0, do
                 double* __restrict__ x1, double* __restrict__ dx, double* scal, double* red,
                 unsigned* counter) {
     if (PROX == FB200_PROX_L1BALL) p0 = scal[FB200_S_THETA];
-    if (isnan(tau)) {                                       // step size left on the device by fb200_stepsize_next
+    if (isnan(tau)) {                                       // speculative trial: see fb200_trial_decide
+        if (__ldcg(&scal[FB200_S_SKIP]) != 0.0) return;
         tau = __ldcg(&scal[FB200_S_TAU]);
         if (PROX == FB200_PROX_SHRINK) p0 = tau * p1;       // proxg(x, t) = shrink(x, t * mu), mu passed in p1
     }
@@ -290,7 +291,10 @@ __global__ void __launch_bounds__(VEC_THREADS)
 bb_kernel(const double* __restrict__ gsrc, int nsplit, int64_t ld, int64_t n, double* __restrict__ g,
           const double* __restrict__ x0, const double* __restrict__ xhat, const double* __restrict__ dx,
           double tau, double* scal, double* red, unsigned* counter) {
-    if (BB >= 2 && isnan(tau)) tau = __ldcg(&scal[FB200_S_TAU]);
+    if (isnan(tau)) {                                       // speculative trial: see fb200_trial_decide
+        if (__ldcg(&scal[FB200_S_SKIP]) != 0.0) return;
+        tau = __ldcg(&scal[FB200_S_TAU]);
+    }
     double s[3] = {0.0, 0.0, 0.0};
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -352,7 +356,10 @@ __global__ void __launch_bounds__(VEC_THREADS)
 peer_allreduce_bb_kernel(PeerParts parts, int P, int64_t n, double* __restrict__ g, const double* __restrict__ x0,
                          const double* __restrict__ xhat, const double* __restrict__ dx, double tau, int with_loss,
                          double* scal, double* red, unsigned* counter) {
-    if (BB >= 2 && isnan(tau)) tau = __ldcg(&scal[FB200_S_TAU]);
+    if (isnan(tau)) {                                       // speculative trial: see fb200_trial_decide
+        if (__ldcg(&scal[FB200_S_SKIP]) != 0.0) return;
+        tau = __ldcg(&scal[FB200_S_TAU]);
+    }
     double s[3] = {0.0, 0.0, 0.0};
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -379,25 +386,76 @@ peer_allreduce_bb_kernel(PeerParts parts, int P, int64_t n, double* __restrict__
 }
 
 // =================================================================================================
-// Barzilai-Borwein step size on the device (reference __init__.py:253-270), the np.float64 algebra of the host loop:
-// la.norm(.)**2 is sqrt(.)**2, Python max(q, 0) keeps a nan q.  One thread; queued behind the trial's kernels.
+// The host loop's decisions on the device (see fb200_trial_decide in the header): line search (:195-201), step size
+// (:253-270), residuals (:272-281), stop rule (:308).  la.norm(.)**2 is sqrt(.)**2; Python max(a, b) is (b > a ? b : a).
+// One thread, queued behind the trial's kernels.
 // =================================================================================================
-__global__ void stepsize_next_kernel(double* scal, double tau, int adaptive) {
-    const double tau0 = isnan(tau) ? scal[FB200_S_TAU] : tau;
+__device__ __forceinline__ double dd_sq(double v) { const double n = sqrt(v); return n * n; }
+__device__ __forceinline__ double dd_pymax(double a, double b) { return (b > a) ? b : a; }
+
+__global__ void decide_init_kernel(double* scal, double f0, double g0_sq) {
+    scal[FB200_S_SKIP] = 0.0;
+    scal[FB200_S_SKIPPED] = 0.0;
+    scal[FB200_S_IT] = 0.0;
+    scal[FB200_S_MAXRES] = -INFINITY;
+    scal[FB200_S_G0SQ] = g0_sq;
+    scal[FB200_S_FRING] = f0;
+}
+
+__global__ void trial_decide_kernel(double* scal, double tau, int loss, int adaptive, int backtrack, int bt,
+                                    int max_backtracks, int window, int stop_rule, double tolerance) {
+    const bool speculative = isnan(tau);
+    if (speculative && scal[FB200_S_SKIP] != 0.0) { scal[FB200_S_SKIPPED] = 1.0; return; }
+    scal[FB200_S_SKIPPED] = 0.0;
+    const double tau0 = speculative ? scal[FB200_S_TAU] : tau;
+    scal[FB200_S_TAU_USED] = tau0;
+    const double raw = scal[FB200_S_F];
+    const double f1 = (loss == FB200_LOSS_LEAST_SQUARES) ? .5 * dd_sq(raw) : raw;
+    const int it = int(scal[FB200_S_IT]);
+    const double dx_sq = scal[FB200_S_DX_SQ];
+    if (backtrack && bt < max_backtracks) {
+        double fmax_w = -INFINITY;
+        bool has_nan = false;
+        for (int k = (it - window + 1 > 0 ? it - window + 1 : 0); k <= it; ++k) {
+            const double v = scal[FB200_S_FRING + k % FB200_FRING];
+            if (isnan(v)) has_nan = true;
+            fmax_w = fmax(fmax_w, v);
+        }
+        if (has_nan) fmax_w = NAN;                                   // np.max propagates nan
+        if (f1 - (fmax_w + scal[FB200_S_DX_G0] + dd_sq(dx_sq) / (2 * tau0)) > 1E-12) {
+            scal[FB200_S_SKIP] = 1.0;                                // rejected: the host backtracks (by-value trials)
+            return;
+        }
+    }
+    const double dx_norm = sqrt(dx_sq);
     double tau1 = tau0;
     if (adaptive) {
-        const double dx_norm = sqrt(scal[FB200_S_DX_SQ]);
         const double dotprod = scal[FB200_S_DX_DG];
         const double tau_s = (dx_norm * dx_norm) / dotprod;
-        const double dg_norm = sqrt(scal[FB200_S_DG_SQ]);
-        const double q = dotprod / (dg_norm * dg_norm);
-        const double tau_m = (0.0 > q) ? 0.0 : q;
+        const double q = dotprod / dd_sq(scal[FB200_S_DG_SQ]);
+        const double tau_m = (0.0 > q) ? 0.0 : q;                    // Python max(q, 0): a nan q stays
         if (2 * tau_m > tau_s) tau1 = tau_m;
         else tau1 = tau_s - .5 * tau_m;
         if (tau1 <= 0 || isinf(tau1) || isnan(tau1)) tau1 = tau0 * 1.5;
     }
-    scal[FB200_S_TAU_USED] = tau0;
+    const double resid = dx_norm / tau0;
+    const double normalizer = dd_pymax(sqrt(scal[FB200_S_G0SQ]), sqrt(scal[FB200_S_XMXH_SQ]) / tau0) + 1E-12;
+    const double nresid = resid / normalizer;
+    const double max_residual = dd_pymax(scal[FB200_S_MAXRES], resid);
+    bool stop = false;
+    switch (stop_rule) {
+        case 0: stop = resid < tolerance; break;
+        case 1: stop = nresid < tolerance; break;
+        case 2: stop = resid / max_residual < tolerance; break;
+        case 3: stop = (resid / max_residual < tolerance) || (nresid < tolerance); break;
+        default: break;
+    }
+    scal[FB200_S_FRING + (it + 1) % FB200_FRING] = f1;
+    scal[FB200_S_IT] = double(it + 1);
+    scal[FB200_S_MAXRES] = max_residual;
+    scal[FB200_S_G0SQ] = scal[FB200_S_G1_SQ];
     scal[FB200_S_TAU] = tau1;
+    scal[FB200_S_SKIP] = stop ? 1.0 : 0.0;
 }
 
 // =================================================================================================
@@ -576,10 +634,19 @@ extern "C" int fb200_accel_step(double c, const double* xa1, const double* xa0, 
     return check_launch("accel_step");
 }
 
-extern "C" int fb200_stepsize_next(double* scal, double tau, int adaptive, void* stream) {
-    if (!scal) { set_error("stepsize_next: null scalar block"); return 1; }
-    stepsize_next_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(scal, tau, adaptive);
-    return check_launch("stepsize_next");
+extern "C" int fb200_decide_init(double* scal, double f0, double g0_sq, void* stream) {
+    if (!scal) { set_error("decide_init: null scalar block"); return 1; }
+    decide_init_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(scal, f0, g0_sq);
+    return check_launch("decide_init");
+}
+
+extern "C" int fb200_trial_decide(double* scal, double tau, int loss, int adaptive, int backtrack, int bt,
+                                  int max_backtracks, int window, int stop_rule, double tolerance, void* stream) {
+    if (!scal) { set_error("trial_decide: null scalar block"); return 1; }
+    if (window < 1 || window > FB200_FRING) { set_error("trial_decide: window %d not in 1..%d", window, FB200_FRING); return 1; }
+    trial_decide_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(scal, tau, loss, adaptive, backtrack, bt,
+                                                                        max_backtracks, window, stop_rule, tolerance);
+    return check_launch("trial_decide");
 }
 
 extern "C" int fb200_loss_eval(int loss, const double* z, const double* b, int64_t m, double* r, double* scal,

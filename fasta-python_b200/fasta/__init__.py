@@ -172,6 +172,7 @@ def fasta(*args, **kwargs) -> Convergence:
     result.single_pass = bool(getattr(be, "use_sweep", False) or getattr(be, "use_sweep_accel", False))
     result.tv_fused = bool(getattr(be, "use_tv_fused", False) or getattr(be, "use_tv_accel", False))
     result.resident = bool(getattr(result, "resident", False))
+    result.speculative = bool(getattr(be, "_spec_mode", False))
     result.kernel_launches = be.total_launches()
     result.peer_reductions = int(getattr(getattr(be, "drv", None), "peer_reductions", 0))   # fused NVLink all-reduce + BB calls
     return result

@@ -216,7 +216,8 @@ class ShardedDriver:
             slot = peer["calls"] & 1
             peer["calls"] += 1
             part = peer["buf"][slot * peer["pitch"]: slot * peer["pitch"] + n + 1]
-            self.local.sweep(x, loss_tag, b, z, r, part[:n], 0, None, None, None, 0.0, ws)
+            # (a speculative trial, tau = NaN, must reach the sweep as such: it returns at once when it should not run)
+            self.local.sweep(x, loss_tag, b, z, r, part[:n], 0, None, None, None, tau if tau != tau else 0.0, ws)
             with_loss = 1 if loss_tag != S.LOSS_NONE else 0
             if with_loss:
                 part[n:n + 1].copy_(ws.scal[S.S_F:S.S_F + 1])
@@ -229,7 +230,7 @@ class ShardedDriver:
             self.collectives += 1
             self.peer_reductions += 1
             return
-        self.local.sweep(x, loss_tag, b, z, r, g, 0, None, None, None, 0.0, ws)
+        self.local.sweep(x, loss_tag, b, z, r, g, 0, None, None, None, tau if tau != tau else 0.0, ws)
         base = getattr(g, "_base", None)
         packed = None
         if loss_tag != S.LOSS_NONE and base is not None and base.numel() > n and base.data_ptr() == g.data_ptr():
@@ -327,7 +328,7 @@ class FusedBackend:
         self._ahead = False
         self._pending = None
         self._spec_mode = False
-        self._spec_adaptive = 0
+        self._decide = None
         # TV: one fused kernel per half-iteration (see TVDriver.step_forward)
         self.use_tv_fused = ((not self.accelerate) and isinstance(driver, TVDriver) and driver.fused_step_ok
                              and penalty.tag == S.PROX_TV_BALL and loss.tag != S.LOSS_NONE)
@@ -452,13 +453,18 @@ class FusedBackend:
     def restore(self, state):
         self.ic, self.ip, self.gc, self.gp, self._ahead = state
 
-    def speculate_begin(self, adaptive):
-        """From now on every trial is followed by fb200_stepsize_next (the next step size stays on the device) and an
-        in-stream snapshot of its sums, so trials can be queued with tau=None before the previous one was collected."""
+    def speculate_begin(self, f0, g0_sq, adaptive, backtrack, max_backtracks, window, stop_rule_id, tolerance):
+        """From now on every trial is followed by fb200_trial_decide (the loop's decisions repeated on the device: the
+        next step size stays there, a rejected trial or a fired stop rule makes speculative successors return at once)
+        and an in-stream snapshot of its sums, so trials can be queued with tau=None before the previous one was read."""
         self._spec_mode = True
-        self._spec_adaptive = 1 if adaptive else 0
+        self._decide = (self.loss.tag, 1 if adaptive else 0, 1 if backtrack else 0, int(max_backtracks), int(window),
+                        int(stop_rule_id), float(tolerance))
+        _cabi.check(self.lib.fb200_decide_init(self.ws.scal.data_ptr(), float(f0), float(g0_sq), self._st()),
+                    "fb200_decide_init")
+        self.launches += 1
 
-    def _queue_trial(self, tau):
+    def _queue_trial(self, tau, bt=0):
         """Queue one trial (reference :181-188, plus the speculative gradient of the single-pass kernels).  tau=None:
         the kernels read the step size fb200_stepsize_next left in scal[S_TAU].  Returns a handle for _collect_trial."""
         x0, g0 = self.X[self.ip], self.G[self.gp]
@@ -501,8 +507,9 @@ class FusedBackend:
                 kind = "forward"
         if not self._spec_mode:
             return kind, None
-        _cabi.check(self.lib.fb200_stepsize_next(self.ws.scal.data_ptr(), float(tau), self._spec_adaptive, st),
-                    "fb200_stepsize_next")
+        loss_tag, adaptive, backtrack, max_bt, window, rule, tol = self._decide
+        _cabi.check(self.lib.fb200_trial_decide(self.ws.scal.data_ptr(), float(tau), loss_tag, adaptive, backtrack, int(bt),
+                                                max_bt, window, rule, tol, st), "fb200_trial_decide")
         self.launches += 1
         return kind, self.ws.snapshot()
 
@@ -512,14 +519,17 @@ class FusedBackend:
         if kind in ("tv_iter", "sweep"):
             self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
         tau_next = s[S.S_TAU] if ticket is not None else None
+        skipped = ticket is not None and s[S.S_SKIPPED] != 0
         if kind in ("tv_iter", "tv_step"):
             return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
-                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0), tau_next=tau_next)
+                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0), tau_next=tau_next,
+                           skipped=skipped)
         return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
-                       xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART], tau_next=tau_next)
+                       xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART], tau_next=tau_next,
+                       skipped=skipped)
 
-    def trial(self, tau):
-        return self._collect_trial(self._queue_trial(tau))
+    def trial(self, tau, bt=0):
+        return self._collect_trial(self._queue_trial(tau, bt))
 
     def trial_accel(self, tau, alpha_prev, restart):
         """One FISTA trial with the contractions in a single pass (reference :181-188 and :220-249): forward step and

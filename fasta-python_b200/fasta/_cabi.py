@@ -11,12 +11,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfasta_b200.so")
 
 ABI_VERSION = 1
-NSCAL = 32
+NSCAL = 64
 
 # scalar-block slots (FB200_S_*)
 S_F, S_DX_G0, S_DX_SQ, S_XMXH_SQ, S_PEN, S_RESTART, S_DX_DG, S_DG_SQ, S_G1_SQ, S_THETA = range(10)
 S_AUX0, S_AUX1, S_AUX2, S_AUX3 = 10, 11, 12, 13
-S_TAU, S_TAU_USED = 14, 15
+S_TAU, S_TAU_USED, S_SKIP, S_SKIPPED, S_IT, S_MAXRES, S_G0SQ = 14, 15, 16, 17, 18, 19, 20
+S_FRING, FRING = 24, 40
 
 LOSS_NONE, LOSS_LEAST_SQUARES, LOSS_LOGISTIC = 0, 1, 2
 PROX_IDENTITY, PROX_SHRINK, PROX_NONNEG, PROX_BOX, PROX_L1BALL, PROX_TV_BALL = range(6)
@@ -70,7 +71,8 @@ SIGNATURES = {
     "fb200_tv_grad_bb": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),
     "fb200_tv_step_div_loss": (_int, [_p, _p, _dbl, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_tv_grad_bb_fused": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),
-    "fb200_stepsize_next": (_int, [_p, _dbl, _int, _p]),
+    "fb200_decide_init": (_int, [_p, _dbl, _dbl, _p]),
+    "fb200_trial_decide": (_int, [_p, _dbl, _int, _int, _int, _int, _int, _int, _int, _dbl, _p]),
     "fb200_tv_fista_fused": (_int, [_p, _p, _dbl, _dbl, _i64, _i64, _int] + [_p] * 10),
     "fb200_tv_iter_fused": (_int, [_p, _p, _dbl, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_peer_allreduce_bb": (_int, [_p, _int, _i64, _p, _int, _p, _p, _p, _dbl, _int, _p, _p, _p]),

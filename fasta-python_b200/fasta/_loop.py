@@ -61,6 +61,10 @@ class Convergence:
         self.function_hist = function_hist
 
 
+_BUILTIN_RULES = {stopping.residual: 0, stopping.norm_residual: 1, stopping.ratio_residual: 2,
+                  stopping.hybrid_residual: 3}
+
+
 def _sq(norm_squared):
     """la.norm(v)**2 the way the reference forms it: sqrt of the dot, then squared."""
     return np.sqrt(norm_squared) ** 2
@@ -134,9 +138,11 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     # the common case differs from this one only in the step size and the buffer rotation -- is queued before the host
     # has read this trial's sums.  The device never waits for the host.  If the line search rejects the trial, the
     # speculated one is dropped (it only wrote scratch buffers) and the backtracking runs as usual.
-    speculate = run_ahead and not accelerate and getattr(be, "speculate_ok", False)
+    speculate = run_ahead and not accelerate and getattr(be, "speculate_ok", False) and 1 <= window <= 40
     if speculate:
-        be.speculate_begin(adaptive)
+        rule_id = _BUILTIN_RULES.get(stop_rule, -1)          # a user's rule is evaluated by the host only
+        be.speculate_begin(f1, g1_sq, adaptive, backtrack, max_backtracks, window, rule_id, tolerance)
+    spec_stats = dict(speculated=0, dropped=0, mismatched=0)
     pending = None            # handle of the trial queued for iteration i
     ahead = None              # handle of the trial speculatively queued for iteration i + 1
 
@@ -155,9 +161,16 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
             if i + 1 < max_iters:
                 be.advance()
                 be._ahead = True
-                ahead = be._queue_trial(None if adaptive else tau0)
+                ahead = be._queue_trial(None)               # step size and go / no-go are on the device
+                spec_stats["speculated"] += 1
             t = be._collect_trial(pending)
             pending = None
+            if t.skipped:                                   # the device's decision differed from the host's (it never
+                spec_stats["mismatched"] += 1
+                if ahead is not None:                       # should): run the trial now, by value
+                    be.restore(rot)
+                    ahead = None
+                t = be.trial(tau0)
         elif queued:
             t = be.trial_finish()
             queued = False
@@ -173,9 +186,13 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
                     and backtrack_count < max_backtracks:
                 tau0 *= stepsize_shrink
                 if ahead is not None:                       # the speculated trial assumed acceptance: drop it
-                    be.restore(rot)
+                    be.restore(rot)                         # (on the device it returned at once)
                     ahead = None
-                t = be.trial_accel(tau0, alpha1, restart) if fused_accel else be.trial(tau0)
+                    spec_stats["dropped"] += 1
+                if speculate:
+                    t = be.trial(tau0, backtrack_count + 1)
+                else:
+                    t = be.trial_accel(tau0, alpha1, restart) if fused_accel else be.trial(tau0)
                 f1 = t.f
                 backtrack_count += 1
             total_backtracks += backtrack_count
@@ -255,8 +272,10 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
         i += 1
 
     times[i] = time()                                       # ref :315
-    return Convergence(residual_hist, norm_residual_hist, tau_hist, total_backtracks, times, i, be.solution(),
-                       objective_hist, iterate_hist, function_hist)
+    res = Convergence(residual_hist, norm_residual_hist, tau_hist, total_backtracks, times, i, be.solution(),
+                      objective_hist, iterate_hist, function_hist)
+    res.speculation = spec_stats if speculate else None
+    return res
 
 
 def _host(a):

@@ -30,7 +30,8 @@ extern "C" {
 #endif
 
 #define FB200_ABI_VERSION 1
-#define FB200_NSCAL 32
+#define FB200_NSCAL 64
+#define FB200_FRING 40
 
 /* slots of the device scalar block */
 enum {
@@ -48,8 +49,15 @@ enum {
     FB200_S_AUX1     = 11,
     FB200_S_AUX2     = 12,
     FB200_S_AUX3     = 13,
-    FB200_S_TAU      = 14, /* step size for the NEXT trial, written by fb200_stepsize_next (__init__.py:253-270) */
-    FB200_S_TAU_USED = 15  /* step size the last trial ran with, written by fb200_stepsize_next */
+    FB200_S_TAU      = 14, /* step size for the NEXT trial, written by fb200_trial_decide (__init__.py:253-270) */
+    FB200_S_TAU_USED = 15, /* step size the last trial ran with */
+    FB200_S_SKIP     = 16, /* != 0: trials queued with tau = NaN return at once (the trial before them was rejected by
+                              the line search, or the stop rule fired) */
+    FB200_S_SKIPPED  = 17, /* != 0: THIS trial was skipped (its other slots are stale) */
+    FB200_S_IT       = 18, /* accepted trials so far (the loop index i of __init__.py:172) */
+    FB200_S_MAXRES   = 19, /* running maximum of the residuals (__init__.py:281) */
+    FB200_S_G0SQ     = 20, /* |gradf0|^2 of the next trial = |gradf1|^2 of the last accepted one (__init__.py:274) */
+    FB200_S_FRING    = 24  /* ring of the last FB200_FRING values of f_hist, index k at slot FB200_S_FRING + k % FB200_FRING */
 };
 
 /* loss tags: f and gradf evaluated on z = A x */
@@ -259,15 +267,23 @@ int fb200_tv_grad_bb_fused(const double* R, int64_t n0, int64_t n1, double* g, i
 int fb200_tv_iter_fused(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, int loss,
                         const double* b, double* x1, double* g1, double* scal, void* ws, void* stream);
 
-/* ---- device-side step size (run-ahead without a host round trip) ------------------------------------------
- * fb200_stepsize_next forms the Barzilai-Borwein step size of reference __init__.py:253-270 from the sums of the
- * trial just queued (scal[S_DX_SQ, S_DX_DG, S_DG_SQ]; adaptive = 0: tau1 = tau0) with the np.float64 algebra of the
- * host loop and stores it in scal[FB200_S_TAU] (and the step size the trial ran with in scal[FB200_S_TAU_USED]).
+/* ---- device-side trial decision (run-ahead without a host round trip) --------------------------------------
+ * fb200_trial_decide, queued behind the kernels of a trial, repeats on the device what the host loop does with the
+ * trial's sums, in the same np.float64 algebra: the non-monotone line-search test of reference __init__.py:195-201
+ * (bt = backtracks already spent on this iteration), and for an accepted trial the Barzilai-Borwein step size
+ * (:253-270; adaptive = 0: tau1 = tau0), the residuals (:272-281) and a built-in stop rule (stop_rule 0..3 =
+ * stopping.residual / norm_residual / ratio_residual / hybrid_residual, -1 = decided by the host only).  It leaves
+ * the next step size in scal[FB200_S_TAU] and sets scal[FB200_S_SKIP] when the trial was rejected or the rule fired.
  * Every entry point that takes `double tau` (fb200_fbs_step, fb200_dense_sweep, fb200_bb_reduce,
- * fb200_peer_allreduce_bb, fb200_tv_iter_fused, fb200_stepsize_next) accepts tau = NaN, meaning "read the step size
- * from scal[FB200_S_TAU]": the host can queue the next iteration's trial before it has seen this one's sums.
- * With tau = NaN fb200_fbs_step forms the shrink threshold as scal[FB200_S_TAU] * p1 (pass mu in p1).        */
-int fb200_stepsize_next(double* scal, double tau, int adaptive, void* stream);
+ * fb200_peer_allreduce_bb, fb200_tv_iter_fused, fb200_trial_decide) accepts tau = NaN, meaning "speculative trial":
+ * read the step size from scal[FB200_S_TAU], and return at once if scal[FB200_S_SKIP] is set.  The host can
+ * therefore queue the next iteration's trial before it has seen this one's sums; a trial that should not have run
+ * costs a few empty launches and reports scal[FB200_S_SKIPPED] = 1.  With tau = NaN fb200_fbs_step forms the shrink
+ * threshold as scal[FB200_S_TAU] * p1 (pass mu in p1).  fb200_decide_init arms the state before the first trial
+ * (f0 = f_hist[0], g0_sq = |gradf(x0)|^2).  window <= FB200_FRING.                                           */
+int fb200_decide_init(double* scal, double f0, double g0_sq, void* stream);
+int fb200_trial_decide(double* scal, double tau, int loss, int adaptive, int backtrack, int bt, int max_backtracks,
+                       int window, int stop_rule, double tolerance, void* stream);
 
 /* whole accelerated (FISTA) TV trial in one pass (reference __init__.py:181-188,220-260 with tv_denoising.py:26-63,
  * 85-96): prox point xa1 and its image za1 = div(xa1), extrapolation x1 = xa1 + c (xa1 - xa0), z1 = za1 + c (za1 - za0),

@@ -239,12 +239,16 @@ class CpuSpeculatingBackend(CpuFusedBackend):
         self.dev_tau = None
         self.dropped = 0
         self.queued = 0
+        self.skipped = 0
+        self.mismatch = 0
 
     def trial_launch(self, tau):               # presence enables run-ahead in _loop.run
         raise AssertionError("the speculative protocol does not use trial_launch")
 
-    def speculate_begin(self, adaptive):
+    def speculate_begin(self, f0, g0_sq, adaptive, backtrack, max_backtracks, window, stop_rule_id, tolerance):
         self.adaptive = bool(adaptive)
+        self.cfg = (bool(backtrack), max_backtracks, window, stop_rule_id, tolerance)
+        self.dev = dict(skip=False, it=0, maxres=-np.inf, g0sq=np.float64(g0_sq), f=[np.float64(f0)])
 
     def rotation(self):
         return self.x0, self.g0, self.x1, self.g1, self._ahead
@@ -253,31 +257,54 @@ class CpuSpeculatingBackend(CpuFusedBackend):
         self.x0, self.g0, self.x1, self.g1, self._ahead = state
         self.dropped += 1
 
-    def _queue_trial(self, tau):
+    def _queue_trial(self, tau, bt=0):
+        """Eager: the trial's kernels and fb200_trial_decide, with the device-side state in self.dev."""
         self.queued += 1
+        d = self.dev
+        if tau is None and d["skip"]:
+            self.skipped += 1
+            return "sweep", (Scalars(skipped=True), None)
         tau0 = np.float64(self.dev_tau if tau is None else tau)
         t = CpuFusedBackend.trial(self, tau0)
         g = CpuFusedBackend.gradient(self, tau0, self.adaptive)
-        tau1 = tau0
-        if self.adaptive:                      # fb200_stepsize_next
-            with np.errstate(all="ignore"):
-                dx_norm = np.sqrt(t.dx_sq)
+        t.skipped = False
+        backtrack, max_bt, window, rule, tol = self.cfg
+        with np.errstate(all="ignore"):
+            if backtrack and bt < max_bt:
+                fwin = np.max(d["f"][max(d["it"] - window + 1, 0):d["it"] + 1])
+                if t.f - (fwin + t.dx_g0 + np.sqrt(t.dx_sq) ** 2 / (2 * tau0)) > 1e-12:
+                    d["skip"] = True
+                    return "sweep", (t, g)
+            tau1 = tau0
+            dx_norm = np.sqrt(t.dx_sq)
+            if self.adaptive:
                 tau_s = dx_norm ** 2 / g.dx_dg
                 tau_m = max(g.dx_dg / np.sqrt(g.dg_sq) ** 2, 0)
                 tau1 = tau_m if 2 * tau_m > tau_s else tau_s - .5 * tau_m
                 if tau1 <= 0 or np.isinf(tau1) or np.isnan(tau1):
                     tau1 = tau0 * 1.5
+            resid = dx_norm / tau0
+            nres = resid / (max(np.sqrt(d["g0sq"]), np.sqrt(t.xmxh_sq) / tau0) + 1e-12)
+            d["maxres"] = max(d["maxres"], resid)
+            stop = {0: resid < tol, 1: nres < tol, 2: resid / d["maxres"] < tol,
+                    3: resid / d["maxres"] < tol or nres < tol}.get(rule, False)
+        d["f"].append(t.f)
+        d["it"] += 1
+        d["g0sq"] = g.g_sq
+        d["skip"] = bool(stop)
         self.dev_tau = tau1
         t.tau_next = tau1
         return "sweep", (t, g)
 
     def _collect_trial(self, handle):
         t, g = handle[1]
+        if t.skipped:
+            self.mismatch += 1                 # the host wants a trial the device skipped
         self._spec = g
         return t
 
-    def trial(self, tau):
-        return self._collect_trial(self._queue_trial(tau))
+    def trial(self, tau, bt=0):
+        return self._collect_trial(self._queue_trial(tau, bt))
 
     def gradient(self, tau, adaptive):
         g, self._spec = self._spec, None

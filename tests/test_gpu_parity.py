@@ -67,6 +67,32 @@ def test_host_driven_loop_matches_golden_on_small_problems(case, mode, monkeypat
     assert_trajectory(res, gold, label=f"host-loop/{case}/{mode}")
 
 
+@pytest.mark.parametrize("case,mode", [cm for cm in golden_cases(prefixes=("lasso_200x1000_k50", "logistic", "lasso_4000", "tv_64", "nnls"))
+                                       if cm[1] != "accelerated"])
+def test_without_speculative_run_ahead_matches_golden(case, mode, monkeypatch):
+    """Host loop with the speculation disabled (the next trial is queued only after this one's sums were read)."""
+    import fasta
+    monkeypatch.setenv("FASTA_B200_RESIDENT", "0")
+    gold = load_golden(case, mode)
+    p = problems.build(case, int(gold["seed"]))
+    A, loss, pen = tagged(p)
+    state = np.random.get_state()                        # both runs must draw the same Lipschitz probes
+    res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert res.speculative and not res.resident          # the default
+    assert res.speculation["mismatched"] == 0 and res.speculation["speculated"] >= res.iteration_count - 1
+    assert (res.speculation["dropped"] > 0) == (res.backtracks > 0)
+    assert_trajectory(res, gold, label=f"speculative/{case}/{mode}")
+    monkeypatch.setenv("FASTA_B200_SPECULATE", "0")
+    np.random.set_state(state)
+    ref = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert not ref.speculative
+    assert_trajectory(ref, gold, label=f"non-speculative/{case}/{mode}")
+    n = ref.iteration_count
+    # the device-side step-size algebra is the host's: identical step sizes, bit for bit
+    assert np.array_equal(res.stepsizes[:n], ref.stepsizes[:n])
+    assert np.array_equal(res.solution, ref.solution)
+
+
 def test_device_resident_loop_options(capsys):
     """Other stop rules, no backtracking, no objective, verbose lines, user-supplied L / tau0."""
     import fasta

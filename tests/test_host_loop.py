@@ -33,6 +33,8 @@ def test_speculative_run_ahead_matches_golden(case, mode):
     assert_trajectory(res, gold, label=f"speculative/{case}/{mode}")
     n = res.iteration_count
     assert be.queued >= n and (be.dropped > 0 or res.backtracks == 0)
+    assert be.mismatch == 0                      # host and 'device' always took the same decisions
+    assert be.skipped >= be.dropped              # every dropped speculation had returned at once on the 'device'
     # with record_iterates / func the hooks must see the accepted iterate, not the speculated one
     be = backend_for(p, False, speculate=True)
     be.load()
