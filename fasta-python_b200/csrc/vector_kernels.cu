@@ -403,10 +403,16 @@ __global__ void decide_init_kernel(double* scal, double f0, double g0_sq) {
 }
 
 __global__ void trial_decide_kernel(double* scal, double tau, int loss, int adaptive, int backtrack, int bt,
-                                    int max_backtracks, int window, int stop_rule, double tolerance) {
+                                    int max_backtracks, int window, int stop_rule, double tolerance, int host_it,
+                                    double host_max_residual, double host_g0_sq) {
     const bool speculative = isnan(tau);
     if (speculative && scal[FB200_S_SKIP] != 0.0) { scal[FB200_S_SKIPPED] = 1.0; return; }
     scal[FB200_S_SKIPPED] = 0.0;
+    if (!speculative) {                                     // a trial queued by value carries the host's loop state
+        scal[FB200_S_IT] = double(host_it);
+        scal[FB200_S_MAXRES] = host_max_residual;
+        scal[FB200_S_G0SQ] = host_g0_sq;
+    }
     const double tau0 = speculative ? scal[FB200_S_TAU] : tau;
     scal[FB200_S_TAU_USED] = tau0;
     const double raw = scal[FB200_S_F];
@@ -641,11 +647,13 @@ extern "C" int fb200_decide_init(double* scal, double f0, double g0_sq, void* st
 }
 
 extern "C" int fb200_trial_decide(double* scal, double tau, int loss, int adaptive, int backtrack, int bt,
-                                  int max_backtracks, int window, int stop_rule, double tolerance, void* stream) {
+                                  int max_backtracks, int window, int stop_rule, double tolerance, int host_it,
+                                  double host_max_residual, double host_g0_sq, void* stream) {
     if (!scal) { set_error("trial_decide: null scalar block"); return 1; }
     if (window < 1 || window > FB200_FRING) { set_error("trial_decide: window %d not in 1..%d", window, FB200_FRING); return 1; }
     trial_decide_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(scal, tau, loss, adaptive, backtrack, bt,
-                                                                        max_backtracks, window, stop_rule, tolerance);
+                                                                        max_backtracks, window, stop_rule, tolerance,
+                                                                        host_it, host_max_residual, host_g0_sq);
     return check_launch("trial_decide");
 }
 

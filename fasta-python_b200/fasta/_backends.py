@@ -464,7 +464,7 @@ class FusedBackend:
                     "fb200_decide_init")
         self.launches += 1
 
-    def _queue_trial(self, tau, bt=0):
+    def _queue_trial(self, tau, bt=0, host=(0, -np.inf, 0.0)):
         """Queue one trial (reference :181-188, plus the speculative gradient of the single-pass kernels).  tau=None:
         the kernels read the step size fb200_stepsize_next left in scal[S_TAU].  Returns a handle for _collect_trial."""
         x0, g0 = self.X[self.ip], self.G[self.gp]
@@ -509,7 +509,8 @@ class FusedBackend:
             return kind, None
         loss_tag, adaptive, backtrack, max_bt, window, rule, tol = self._decide
         _cabi.check(self.lib.fb200_trial_decide(self.ws.scal.data_ptr(), float(tau), loss_tag, adaptive, backtrack, int(bt),
-                                                max_bt, window, rule, tol, st), "fb200_trial_decide")
+                                                max_bt, window, rule, tol, int(host[0]), float(host[1]), float(host[2]),
+                                                st), "fb200_trial_decide")
         self.launches += 1
         return kind, self.ws.snapshot()
 
@@ -518,18 +519,18 @@ class FusedBackend:
         s = self.ws.fetch() if ticket is None else self.ws.collect(ticket)
         if kind in ("tv_iter", "sweep"):
             self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
-        tau_next = s[S.S_TAU] if ticket is not None else None
+        tau_used = s[S.S_TAU_USED] if ticket is not None else None
         skipped = ticket is not None and s[S.S_SKIPPED] != 0
         if kind in ("tv_iter", "tv_step"):
             return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
-                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0), tau_next=tau_next,
+                           xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(0.0), restart=np.float64(0.0), tau_used=tau_used,
                            skipped=skipped)
         return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ],
-                       xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART], tau_next=tau_next,
+                       xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART], tau_used=tau_used,
                        skipped=skipped)
 
-    def trial(self, tau, bt=0):
-        return self._collect_trial(self._queue_trial(tau, bt))
+    def trial(self, tau, bt=0, host=(0, -np.inf, 0.0)):
+        return self._collect_trial(self._queue_trial(tau, bt, host))
 
     def trial_accel(self, tau, alpha_prev, restart):
         """One FISTA trial with the contractions in a single pass (reference :181-188 and :220-249): forward step and

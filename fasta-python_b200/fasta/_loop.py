@@ -138,11 +138,12 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     # the common case differs from this one only in the step size and the buffer rotation -- is queued before the host
     # has read this trial's sums.  The device never waits for the host.  If the line search rejects the trial, the
     # speculated one is dropped (it only wrote scratch buffers) and the backtracking runs as usual.
-    speculate = run_ahead and not accelerate and getattr(be, "speculate_ok", False) and 1 <= window <= 40
+    speculate = run_ahead and not accelerate and getattr(be, "speculate_ok", False) and 1 <= window < 40
     if speculate:
         rule_id = _BUILTIN_RULES.get(stop_rule, -1)          # a user's rule is evaluated by the host only
         be.speculate_begin(f1, g1_sq, adaptive, backtrack, max_backtracks, window, rule_id, tolerance)
     spec_stats = dict(speculated=0, dropped=0, mismatched=0)
+    by_value = True           # whether `pending` was queued with the host's step size (else: the device's)
     pending = None            # handle of the trial queued for iteration i
     ahead = None              # handle of the trial speculatively queued for iteration i + 1
 
@@ -152,9 +153,11 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
         g0_sq = g1_sq
         tau0 = tau1
         if speculate:
+            host_state = (i, max_residual, g0_sq)           # re-arms the device's copy of the loop state (by-value trials)
             if pending is None:
                 be.advance()                                # ref :176-178
-                pending = be._queue_trial(tau0)             # ref :181-188
+                pending = be._queue_trial(tau0, 0, host_state)     # ref :181-188
+                by_value = True
             be._ahead = False
             rot = be.rotation()
             ahead = None
@@ -170,7 +173,10 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
                 if ahead is not None:                       # should): run the trial now, by value
                     be.restore(rot)
                     ahead = None
-                t = be.trial(tau0)
+                t = be.trial(tau0, 0, host_state)
+                by_value = True
+            if not by_value:
+                tau0 = t.tau_used                           # the device's value of the :253-270 algebra, the one it used
         elif queued:
             t = be.trial_finish()
             queued = False
@@ -190,7 +196,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
                     ahead = None
                     spec_stats["dropped"] += 1
                 if speculate:
-                    t = be.trial(tau0, backtrack_count + 1)
+                    t = be.trial(tau0, backtrack_count + 1, host_state)
                 else:
                     t = be.trial_accel(tau0, alpha1, restart) if fused_accel else be.trial(tau0)
                 f1 = t.f
@@ -225,8 +231,6 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
                 tau1 = tau_s - .5 * tau_m
             if tau1 <= 0 or np.isinf(tau1) or np.isnan(tau1):
                 tau1 = tau0 * 1.5
-            if speculate:
-                tau1 = t.tau_next                           # the device's value of the same algebra: the one trial i+1 uses
 
         residual_hist[i] = dx_norm / tau0                   # ref :272-281
         normalizer = max(np.sqrt(g0_sq), np.sqrt(xmxh_sq) / tau0) + EPSILON
@@ -241,7 +245,10 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
             if ahead is None and not stop and i + 1 < max_iters:
                 be.advance()                                # after a backtracked iteration: queue the next trial now
                 be._ahead = True
-                ahead = be._queue_trial(tau1)
+                ahead = be._queue_trial(tau1, 0, (i + 1, max_residual, g1_sq))
+                by_value = True
+            else:
+                by_value = False                            # the successor (if any) was queued speculatively
             pending, ahead = ahead, None
         elif run_ahead and not stop and i + 1 < max_iters:
             be.advance()                                    # next iteration's ref :176-188, queued now

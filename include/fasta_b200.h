@@ -280,10 +280,15 @@ int fb200_tv_iter_fused(const double* x0, const double* g0, double tau, int64_t 
  * therefore queue the next iteration's trial before it has seen this one's sums; a trial that should not have run
  * costs a few empty launches and reports scal[FB200_S_SKIPPED] = 1.  With tau = NaN fb200_fbs_step forms the shrink
  * threshold as scal[FB200_S_TAU] * p1 (pass mu in p1).  fb200_decide_init arms the state before the first trial
- * (f0 = f_hist[0], g0_sq = |gradf(x0)|^2).  window <= FB200_FRING.                                           */
+ * (f0 = f_hist[0], g0_sq = |gradf(x0)|^2).  window <= FB200_FRING.  A trial queued by value (tau not NaN) re-arms the
+ * device's loop state from the host's (host_it = loop index i, host_max_residual, host_g0_sq = |gradf0|^2), so a
+ * last-bit disagreement between the two algebras can cost a wasted or repeated trial but never a wrong result: the
+ * host decides from the sums it reads, uses scal[FB200_S_TAU_USED] as the step size of a speculative trial, and
+ * repeats by value a trial that reports FB200_S_SKIPPED.                                                      */
 int fb200_decide_init(double* scal, double f0, double g0_sq, void* stream);
 int fb200_trial_decide(double* scal, double tau, int loss, int adaptive, int backtrack, int bt, int max_backtracks,
-                       int window, int stop_rule, double tolerance, void* stream);
+                       int window, int stop_rule, double tolerance, int host_it, double host_max_residual,
+                       double host_g0_sq, void* stream);
 
 /* whole accelerated (FISTA) TV trial in one pass (reference __init__.py:181-188,220-260 with tv_denoising.py:26-63,
  * 85-96): prox point xa1 and its image za1 = div(xa1), extrapolation x1 = xa1 + c (xa1 - xa0), z1 = za1 + c (za1 - za0),

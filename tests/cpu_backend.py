@@ -257,10 +257,13 @@ class CpuSpeculatingBackend(CpuFusedBackend):
         self.x0, self.g0, self.x1, self.g1, self._ahead = state
         self.dropped += 1
 
-    def _queue_trial(self, tau, bt=0):
+    def _queue_trial(self, tau, bt=0, host=(0, -np.inf, 0.0)):
         """Eager: the trial's kernels and fb200_trial_decide, with the device-side state in self.dev."""
         self.queued += 1
         d = self.dev
+        if tau is not None:                    # by-value trials re-arm the device's loop state from the host's
+            d["it"], d["maxres"], d["g0sq"] = int(host[0]), np.float64(host[1]), np.float64(host[2])
+            del d["f"][d["it"] + 1:]
         if tau is None and d["skip"]:
             self.skipped += 1
             return "sweep", (Scalars(skipped=True), None)
@@ -274,6 +277,7 @@ class CpuSpeculatingBackend(CpuFusedBackend):
                 fwin = np.max(d["f"][max(d["it"] - window + 1, 0):d["it"] + 1])
                 if t.f - (fwin + t.dx_g0 + np.sqrt(t.dx_sq) ** 2 / (2 * tau0)) > 1e-12:
                     d["skip"] = True
+                    t.tau_used = tau0
                     return "sweep", (t, g)
             tau1 = tau0
             dx_norm = np.sqrt(t.dx_sq)
@@ -293,7 +297,7 @@ class CpuSpeculatingBackend(CpuFusedBackend):
         d["g0sq"] = g.g_sq
         d["skip"] = bool(stop)
         self.dev_tau = tau1
-        t.tau_next = tau1
+        t.tau_used = tau0
         return "sweep", (t, g)
 
     def _collect_trial(self, handle):
@@ -303,8 +307,8 @@ class CpuSpeculatingBackend(CpuFusedBackend):
         self._spec = g
         return t
 
-    def trial(self, tau, bt=0):
-        return self._collect_trial(self._queue_trial(tau, bt))
+    def trial(self, tau, bt=0, host=(0, -np.inf, 0.0)):
+        return self._collect_trial(self._queue_trial(tau, bt, host))
 
     def gradient(self, tau, adaptive):
         g, self._spec = self._spec, None
