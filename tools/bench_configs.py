@@ -49,7 +49,8 @@ def summarise(name, workload, outs, ms, steps, bytes_iter, bytes_bt, cpu, extra=
                               frac_of_nominal_8TBs=alg / loop / 1e9 / 8000.0,
                               algorithmic_bytes_per_iteration=bytes_iter, note="whole in-loop time, all kernels + host syncs"),
                 cpu_baseline=cpu, backend=outs[-1].backend, single_pass=outs[-1].single_pass,
-                gpu_launches=sum(r.kernel_launches for r in outs))
+                gpu_launches=sum(r.kernel_launches for r in outs),
+                speculation=getattr(outs[-1], "speculation", None))
     if extra:
         line.update(extra)
     print(json.dumps(line), flush=True)
