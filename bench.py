@@ -444,7 +444,6 @@ def main():
         if world > 1:
             line["collective"] = ("fused peer-memory all-reduce + BB epilogue kernel over NVLink (fb200_peer_allreduce_bb), "
                                   f"{peer_reductions} calls in the timed region" if peer_reductions else "ncclAllReduce + bb kernel")
-        line.pop("final_objective")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
