@@ -162,7 +162,7 @@ def clocks_summary(proc, f, device_index, t_begin, t_end):
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_arm(w, A_host, b_host, sample_iters=CPU_SAMPLE_ITERS):
+def cpu_arm(w, A_host, b_host, sample_iters=CPU_SAMPLE_ITERS, gpu_solve=None):
     """Bounded sample: Lipschitz prologue + `sample_iters` iterations of the same problem with numpy
     (all host threads).  Rate = iterations / in-loop time, the reference's own definition
     (examples/__init__.py:59-60), which EXCLUDES the prologue -- the most favourable reading."""
@@ -189,10 +189,25 @@ def cpu_arm(w, A_host, b_host, sample_iters=CPU_SAMPLE_ITERS):
     n = res.iteration_count
     loop = res.times[n] - res.times[0]
     cores = len(os.sched_getaffinity(0))
-    return dict(value=n / loop, unit="iterations/s", cores=cores, kind="port",
-                sample=(f"oracle/fasta_oracle.py (numpy {np.__version__}, BLAS pools {pools}) on the full "
-                        f"{w['M']}x{w['N']} problem, first {n} iterations (in-loop time {loop:.2f} s; whole call "
-                        f"incl. 6-pass prologue {wall:.2f} s); os.cpu_count()={os.cpu_count()}"))
+    out = dict(value=n / loop, unit="iterations/s", cores=cores, kind="port",
+               sample=(f"oracle/fasta_oracle.py (numpy {np.__version__}, BLAS pools {pools}) on the full "
+                       f"{w['M']}x{w['N']} problem, first {n} iterations (in-loop time {loop:.2f} s; whole call "
+                       f"incl. 6-pass prologue {wall:.2f} s); os.cpu_count()={os.cpu_count()}"))
+    if gpu_solve is not None:
+        # the oracle as the checker (not the thing measured): the same first iterations on the GPU, same seed
+        try:
+            np.random.seed(0)
+            got = gpu_solve(opts)
+            rel = lambda a, b_: float(np.max(np.abs(np.asarray(a) - np.asarray(b_)) / np.maximum(np.abs(np.asarray(b_)), 1e-300)))
+            sol = got.solution.detach().cpu().numpy() if hasattr(got.solution, "detach") else np.asarray(got.solution)
+            out["parity_full_size"] = dict(
+                iterations=[int(got.iteration_count), int(n)], backtracks=[int(got.backtracks), int(res.backtracks)],
+                stepsizes_rel_err=rel(got.stepsizes[:n], res.stepsizes[:n]),
+                residuals_rel_err=rel(got.residuals[:n], res.residuals[:n]),
+                iterate_rel_err=float(la.norm(sol - res.solution) / max(la.norm(res.solution), 1e-300)))
+        except Exception as exc:                             # never lose the bench line over the cross-check
+            out["parity_full_size"] = dict(error=repr(exc))
+    return out
 
 
 def reference_main(args):
@@ -428,7 +443,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         A_np = A_host.numpy() if e2e is not None else A.cpu().numpy()
-        cpu = cpu_arm(w, A_np, b.cpu().numpy())
+        cpu = cpu_arm(w, A_np, b.cpu().numpy(), gpu_solve=lambda o: fasta.fasta(op, loss.f, loss.gradf, pen.g, pen.prox, x0, **o))
 
     if rank == 0:
         line = dict(metric="lasso_fbs_iterations_per_sec", value=value, unit="iterations/s", n_gpus=world,
