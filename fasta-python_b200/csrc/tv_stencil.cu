@@ -672,6 +672,42 @@ static int tv_grid(int64_t n0, int64_t n1, dim3* grid, int* strip) {
     return 0;
 }
 
+// Strip length of the marching kernels: a warp owns TVM_COLS columns x `strip` rows.  The grid should fill a whole
+// number of waves of the resident capacity (4 blocks of 4 warps per SM), ending just BELOW a wave boundary, and strips
+// should be long enough to amortise the one recomputed halo row: among 1..16 waves pick the strip in [40, 160] rows
+// with the least (waves x (strip + halo)) cost.  FASTA_B200_TV_STRIP overrides (experiments).
+static int tvm_plan(int64_t n0, int64_t n1, int64_t* warps_x_out, int64_t* strip_out, int64_t* blocks_out) {
+    const int64_t warps_x = (n1 + TVM_COLS - 1) / TVM_COLS;
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("FASTA_B200_TV_STRIP"); forced = e ? atoi(e) : 0; }
+    int64_t strip = 64;
+    if (forced > 0) {
+        strip = forced;
+    } else {
+        const int64_t capacity = int64_t(sm_count()) * 4 * (TVM_THREADS / 32);       // resident warps
+        double best = 1e300;
+        for (int k = 1; k <= 16; ++k) {
+            const int64_t strips = (k * capacity) / warps_x;
+            if (strips < 1) continue;
+            const int64_t st = (n0 + strips - 1) / strips;
+            if (st < 40 || st > 160) continue;
+            const double cost = double(k) * (double(st) + 1.5);
+            if (cost < best - 1e-9) { best = cost; strip = st; }
+        }
+        if (best > 1e299) {                       // small image: less than one wave at 40 rows -- shorter strips, more warps
+            const int64_t strips = capacity / warps_x > 0 ? capacity / warps_x : 1;
+            strip = (n0 + strips - 1) / strips;
+            strip = strip < 8 ? 8 : (strip > 64 ? 64 : strip);
+        }
+    }
+    while ((warps_x * ((n0 + strip - 1) / strip) + 3) / 4 > MAX_RED_BLOCKS) strip *= 2;
+    const int64_t warps = warps_x * ((n0 + strip - 1) / strip);
+    const int64_t blocks = (warps + TVM_THREADS / 32 - 1) / (TVM_THREADS / 32);
+    if (blocks > MAX_RED_BLOCKS || warps_x > (1 << 24)) return 1;
+    *warps_x_out = warps_x; *strip_out = strip; *blocks_out = blocks;
+    return 0;
+}
+
 }  // namespace fb200
 
 using namespace fb200;
@@ -767,12 +803,8 @@ extern "C" int fb200_tv_iter_fused(const double* x0, const double* g0, double ta
         variant = (e && e[0] == '1') ? 1 : 0;
     }
     if (variant == 0) {
-        const int64_t warps_x = (n1 + TVM_COLS - 1) / TVM_COLS;
-        int64_t strip = 64;
-        while ((warps_x * ((n0 + strip - 1) / strip) + 3) / 4 > MAX_RED_BLOCKS) strip *= 2;
-        const int64_t warps = warps_x * ((n0 + strip - 1) / strip);
-        const int64_t blocks = (warps + TVM_THREADS / 32 - 1) / (TVM_THREADS / 32);
-        if (blocks > MAX_RED_BLOCKS || warps_x > (1 << 24)) { set_error("tv_iter_fused: image too large"); return 1; }
+        int64_t warps_x, strip, blocks;
+        if (tvm_plan(n0, n1, &warps_x, &strip, &blocks)) { set_error("tv_iter_fused: image too large"); return 1; }
         static int mv = -1;                 // experiment knob: unroll depth / occupancy target of the marching kernel
         if (mv < 0) { const char* e = getenv("FASTA_B200_TVM_VARIANT"); mv = e ? atoi(e) : 0; }
 #define TVM_LAUNCH(L, U, B) TVM_LAUNCH_FD(L, U, B, false)
@@ -821,12 +853,8 @@ extern "C" int fb200_tv_fista_fused(const double* x0, const double* g0, double t
     Workspace w(ws);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n0 < 1 || n1 < 1 || n0 > (1 << 30) || n1 > (1 << 30)) { set_error("tv_fista_fused: bad shape"); return 1; }
-    const int64_t warps_x = (n1 + TVM_COLS - 1) / TVM_COLS;
-    int64_t strip = 64;
-    while ((warps_x * ((n0 + strip - 1) / strip) + 3) / 4 > MAX_RED_BLOCKS) strip *= 2;
-    const int64_t warps = warps_x * ((n0 + strip - 1) / strip);
-    const int64_t blocks = (warps + TVM_THREADS / 32 - 1) / (TVM_THREADS / 32);
-    if (blocks > MAX_RED_BLOCKS || warps_x > (1 << 24)) { set_error("tv_fista_fused: image too large"); return 1; }
+    int64_t warps_x, strip, blocks;
+    if (tvm_plan(n0, n1, &warps_x, &strip, &blocks)) { set_error("tv_fista_fused: image too large"); return 1; }
     static int mv = -1;                     // experiment knob: unroll depth / occupancy target
     if (mv < 0) { const char* e = getenv("FASTA_B200_TVF_VARIANT"); mv = e ? atoi(e) : 0; }
 #define TVF_LAUNCH(L, U, B) TVF_LAUNCH_FD(L, U, B, false)
