@@ -377,6 +377,11 @@ peer_allreduce_bb_kernel(PeerParts parts, int P, int64_t n, double* __restrict__
         double f = __ldcg(&parts.p[0][n]);
         for (int k = 1; k < P; ++k) f += __ldcg(&parts.p[k][n]);
         scal[FB200_S_F] = f;
+        if (with_loss >= 2) {                               // FISTA sweep: second loss partial (extrapolated point)
+            double f2 = __ldcg(&parts.p[0][n + 1]);
+            for (int k = 1; k < P; ++k) f2 += __ldcg(&parts.p[k][n + 1]);
+            scal[FB200_S_AUX3] = f2;
+        }
     }
     if (BB >= 1) {
         double* const out[3] = {BB >= 2 ? scal + FB200_S_DX_DG : nullptr,

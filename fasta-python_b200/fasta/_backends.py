@@ -247,6 +247,45 @@ class ShardedDriver:
         if bb:
             self.local.bb_reduce(g, x0, xhat, dx, tau, bb >= 2, ws)
 
+    def sweep_accel(self, xa1, loss_tag, b, za0, c, za1, z, r, g, bb, x0, xhat, dx, tau, ws):
+        """FISTA mode of the single pass on the row shard (see DenseDriver.sweep_accel): the partial gradient and BOTH
+        loss partials (prox point: line search; extrapolated point) are summed over the ranks in one exchange."""
+        n = g.numel()
+        peer = self._peer(n, g.device) if g.is_cuda else None
+        if peer is not None:
+            slot = peer["calls"] & 1
+            peer["calls"] += 1
+            part = peer["buf"][slot * peer["pitch"]: slot * peer["pitch"] + n + 2]
+            self.local.sweep_accel(xa1, loss_tag, b, za0, c, za1, z, r, part[:n], 0, None, None, None, 0.0, ws)
+            part[n:n + 1].copy_(ws.scal[S.S_F:S.S_F + 1])
+            part[n + 1:n + 2].copy_(ws.scal[S.S_AUX3:S.S_AUX3 + 1])
+            peer["hdl"].barrier(channel=0)
+            _cabi.check(self.local.lib.fb200_peer_allreduce_bb(peer["ptrs"][slot], peer["P"], n, g.data_ptr(), int(bb),
+                                                               _device.ptr(x0), _device.ptr(xhat), _device.ptr(dx),
+                                                               float(tau), 2, ws.scal.data_ptr(), ws.buf.data_ptr(),
+                                                               _device.stream_ptr()), "fb200_peer_allreduce_bb")
+            self.local.launches += 1
+            self.collectives += 1
+            self.peer_reductions += 1
+            return
+        self.local.sweep_accel(xa1, loss_tag, b, za0, c, za1, z, r, g, 0, None, None, None, 0.0, ws)
+        base = getattr(g, "_base", None)
+        if base is not None and base.numel() >= n + 2 and base.data_ptr() == g.data_ptr():
+            packed = base[:n + 2]                       # [g ; f(prox point) ; f(extrapolated point)] in one message
+            packed[n:n + 1].copy_(ws.scal[S.S_F:S.S_F + 1])
+            packed[n + 1:n + 2].copy_(ws.scal[S.S_AUX3:S.S_AUX3 + 1])
+            self.dist.all_reduce(packed, group=self.group)
+            ws.scal[S.S_F:S.S_F + 1].copy_(packed[n:n + 1])
+            ws.scal[S.S_AUX3:S.S_AUX3 + 1].copy_(packed[n + 1:n + 2])
+            self.collectives += 1
+        else:
+            self.dist.all_reduce(g, group=self.group)
+            self.dist.all_reduce(ws.scal[S.S_F:S.S_F + 1], group=self.group)
+            self.dist.all_reduce(ws.scal[S.S_AUX3:S.S_AUX3 + 1], group=self.group)
+            self.collectives += 3
+        if bb:
+            self.local.bb_reduce(g, x0, xhat, dx, tau, bb >= 2, ws)
+
     def _root(self):
         return self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
 

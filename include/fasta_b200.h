@@ -303,7 +303,8 @@ int fb200_tv_fista_fused(const double* x0, const double* g0, double tau, double 
 /* ---- multi-GPU (A row-partitioned): all-reduce of the A^T r partials over NVLink peer memory fused
  * with the BB epilogue.  peer_ptrs[k] (host array, P entries) is the address, in THIS process, of rank k's partial:
  * n doubles of gradient partial followed by one double of raw loss partial.  g = sum_k partial_k in rank order
- * (bit-identical on every rank), scal[S_F] = sum of the loss partials (with_loss), BB sums as fb200_bb_reduce.
+ * (bit-identical on every rank), scal[S_F] = sum of the loss partials at element n (with_loss >= 1; with_loss = 2 also
+ * scal[S_AUX3] = sum of the second loss partials at element n + 1: the FISTA sweep), BB sums as fb200_bb_reduce.
  * The caller maps the buffers (torch symmetric memory / cudaIpc) and barriers the ranks before the call.
  * Replaces ncclAllReduce + fb200_bb_reduce for reference __init__.py:248,254-260 on the sharded map.       */
 #define FB200_MAX_PEERS 16

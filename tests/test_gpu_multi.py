@@ -42,7 +42,8 @@ def _worker(rank, world, port, case, mode, peer, out):
 
 @pytest.mark.parametrize("peer", [True, False])
 @pytest.mark.parametrize("case,mode", [("lasso_200x1000_k50", "adaptive"), ("lasso_4000x10000_k500", "adaptive"),
-                                       ("lasso_200x1000_k10", "plain")])
+                                       ("lasso_200x1000_k10", "plain"), ("lasso_200x1000_k50", "accelerated"),
+                                       ("lasso_4000x10000_k500", "accelerated")])
 def test_two_rank_sharded_solve_matches_golden(case, mode, peer, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
