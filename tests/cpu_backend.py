@@ -242,8 +242,14 @@ class CpuSpeculatingBackend(CpuFusedBackend):
         self.skipped = 0
         self.mismatch = 0
 
-    def trial_launch(self, tau):               # presence enables run-ahead in _loop.run
-        raise AssertionError("the speculative protocol does not use trial_launch")
+    def trial_launch(self, tau):               # the plain run-ahead protocol (used when speculation is not possible)
+        assert not hasattr(self, "dev"), "the speculative protocol does not use trial_launch"
+        self._pending_t = CpuFusedBackend.trial(self, tau)
+        self._ahead = True
+
+    def trial_finish(self):
+        self._ahead = False
+        return self._pending_t
 
     def speculate_begin(self, f0, g0_sq, adaptive, backtrack, max_backtracks, window, stop_rule_id, tolerance):
         self.adaptive = bool(adaptive)
@@ -308,9 +314,13 @@ class CpuSpeculatingBackend(CpuFusedBackend):
         return t
 
     def trial(self, tau, bt=0, host=(0, -np.inf, 0.0)):
+        if not hasattr(self, "dev"):
+            return CpuFusedBackend.trial(self, tau)
         return self._collect_trial(self._queue_trial(tau, bt, host))
 
     def gradient(self, tau, adaptive):
+        if not hasattr(self, "dev"):
+            return CpuFusedBackend.gradient(self, tau, adaptive)
         g, self._spec = self._spec, None
         return g
 

@@ -50,6 +50,37 @@ def test_speculative_run_ahead_matches_golden(case, mode):
     assert np.array_equal(res2.solution, ref2.solution) and np.array_equal(res2.stepsizes, ref2.stepsizes)
 
 
+def test_speculative_run_ahead_corner_cases():
+    """User stop rule (the device cannot evaluate it: rule id -1), a window too long for the device's ring (speculation
+    off), backtracking disabled, max_iters = 1 and a tolerance that stops at once."""
+    gold = load_golden("lasso_200x1000_k50", "adaptive")
+    p = problems.build("lasso_200x1000_k50", 0)
+
+    def both(**kw):
+        outs = []
+        for spec in (True, False):
+            be = backend_for(p, False, speculate=spec)
+            be.load()
+            np.random.seed(11)
+            outs.append((_loop.run(be, p.x0.shape, **dict(gold["opts"], **kw)), be))
+        (a, bea), (b, _) = outs
+        assert (a.iteration_count, a.backtracks) == (b.iteration_count, b.backtracks), kw
+        n = a.iteration_count
+        assert np.allclose(a.stepsizes[:n], b.stepsizes[:n], rtol=1e-12, atol=0) and np.allclose(a.solution, b.solution, rtol=1e-12, atol=1e-300)
+        return a, bea
+
+    res, be = both(stop_rule=lambda i, r, nr, mr, tol: i >= 6)
+    assert res.iteration_count == 7 and res.speculation is not None and be.mismatch == 0
+    res, be = both(window=45)
+    assert res.speculation is None and be.queued == 0          # ring too short: the plain run-ahead-free protocol
+    res, be = both(backtrack=False, max_iters=30)
+    assert res.backtracks == 0 and be.dropped == 0 and be.mismatch == 0
+    res, be = both(max_iters=1)
+    assert res.iteration_count == 1 and be.queued == 1
+    res, be = both(tolerance=1e9)
+    assert res.iteration_count == 1 and be.mismatch == 0
+
+
 def test_verbose_output_format(capsys):
     gold = load_golden("lasso_200x1000_k10", "accelerated")
     p = problems.build("lasso_200x1000_k10", 0)
