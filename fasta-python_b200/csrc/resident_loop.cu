@@ -82,17 +82,48 @@ __device__ __forceinline__ double rl_sq(double v) {          // la.norm(.)**2 = 
 }
 __device__ __forceinline__ double rl_pymax(double a, double b) { return (b > a) ? b : a; }   // Python max(a, b)
 
-template <int LOSS, int PROX, bool ACCEL>
+// CLUSTER variant (problems whose matrix fits the shared memory of one 16-CTA cluster TWICE -- BASELINE config 1 does):
+// the grid is a single thread-block cluster; every CTA keeps its band of rows of A (for A x) and its 32-column groups of
+// A (for A^T r) in shared memory, so after the one-time staging no phase touches A in L2 / HBM again, and the phases
+// are separated by the hardware cluster barrier (release / acquire at cluster scope) instead of a grid-wide barrier.
+// Same per-row and per-column summation order as the grid variant: identical z and g, bit for bit.
+constexpr int RL_CLUSTER = 16;
+
+template <bool CLUSTER>
+__device__ __forceinline__ void rl_barrier(cg::grid_group& grid) {
+    if (CLUSTER) cg::this_cluster().sync();
+    else grid.sync();
+}
+
+template <int LOSS, int PROX, bool ACCEL, bool CLUSTER>
 __global__ void __launch_bounds__(RL_THREADS)
 resident_fbs_kernel(ResidentArgs p) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[RL_MAXK * 32 + RL_MAXK];
     __shared__ double gsm[8][33];
+    extern __shared__ double rl_dyn[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = gridDim.x;
     const int gtid = blockIdx.x * RL_THREADS + tid, gthreads = nb * RL_THREADS;
     const int gwarp = blockIdx.x * (RL_THREADS / 32) + warp, gwarps = nb * (RL_THREADS / 32);
     const int M = p.M, N = p.N;
+    // CLUSTER: rows [row_lo, row_hi) of A as rows_sm[row - row_lo][N]; column groups as cols_sm[row][grp][32]
+    const int rpb = (M + nb - 1) / nb, ngrp = (N + nb * 32 - 1) / (nb * 32);
+    const int row_lo = min(M, int(blockIdx.x) * rpb), row_hi = min(M, row_lo + rpb);
+    double* rows_sm = rl_dyn;
+    double* cols_sm = rl_dyn + ((size_t(rpb) * N + 1) & ~size_t(1));
+    if (CLUSTER) {
+        for (int e = tid; e < (row_hi - row_lo) * N; e += RL_THREADS) {
+            const int rr = e / N, cc = e - rr * N;
+            rows_sm[e] = p.A[int64_t(row_lo + rr) * p.lda + cc];
+        }
+        for (int e = tid; e < M * ngrp * 32; e += RL_THREADS) {
+            const int rr = e / (ngrp * 32), rem = e - rr * (ngrp * 32), grp = rem >> 5;
+            const int col = int(blockIdx.x) * 32 + grp * nb * 32 + (rem & 31);
+            cols_sm[e] = (col < N) ? p.A[int64_t(rr) * p.lda + col] : 0.0;
+        }
+        __syncthreads();
+    }
     double* partA[2] = {p.part, p.part + size_t(nb) * RL_MAXK};
     double* partB[2] = {p.part + 2 * size_t(nb) * RL_MAXK, p.part + 3 * size_t(nb) * RL_MAXK};
     double* partC[2] = {p.part + 4 * size_t(nb) * RL_MAXK, p.part + 5 * size_t(nb) * RL_MAXK};
@@ -139,12 +170,12 @@ resident_fbs_kernel(ResidentArgs p) {
                 if (ACCEL) s[4] += (a - y) * (y - __ldcg(&p.XA[acur][i]));      // restart test, reference :231
             }
             rl_publish<5>(s, partA[ua & 1], sm);
-            grid.sync();
+            rl_barrier<CLUSTER>(grid);
             // ---- z = A x1, r = gradf(z), f (reference :187-188): one warp per row ----
             double fs[1] = {0.0};
             double* zp = ACCEL ? p.ZA[1 - acur] : p.z;
-            for (int row = gwarp; row < M; row += gwarps) {
-                const double* ar = p.A + int64_t(row) * p.lda;
+            for (int row = CLUSTER ? row_lo + warp : gwarp; row < (CLUSTER ? row_hi : M); row += CLUSTER ? RL_THREADS / 32 : gwarps) {
+                const double* ar = CLUSTER ? rows_sm + size_t(row - row_lo) * N : p.A + int64_t(row) * p.lda;
                 double acc = 0.0;
                 for (int j = lane; j < N; j += 32) acc = fma(ar[j], __ldcg(&xp[j]), acc);
                 acc = warp_sum(acc);
@@ -157,7 +188,7 @@ resident_fbs_kernel(ResidentArgs p) {
                 }
             }
             rl_publish<1>(fs, partB[ub & 1], sm);
-            grid.sync();
+            rl_barrier<CLUSTER>(grid);
             double ta[5], tb[1];
             rl_collect<5>(partA[ua & 1], nb, ta, sm);
             rl_collect<1>(partB[ub & 1], nb, tb, sm);
@@ -204,7 +235,7 @@ resident_fbs_kernel(ResidentArgs p) {
                 se[0] += fi;
             }
             rl_publish<3>(se, partE[ue & 1], sm);
-            grid.sync();
+            rl_barrier<CLUSTER>(grid);
             double te[3];
             rl_collect<3>(partE[ue & 1], nb, te, sm);
             ++ue;
@@ -215,11 +246,16 @@ resident_fbs_kernel(ResidentArgs p) {
         }
         // ---- g1 = A^T r (reference :248): 32 columns x 8 row lanes per block pass, + BB sums (:254-260) ----
         double sc[3] = {0.0, 0.0, 0.0};
-        for (int c0 = blockIdx.x * 32; c0 < N; c0 += nb * 32) {
+        int grp = 0;
+        for (int c0 = blockIdx.x * 32; c0 < N; c0 += nb * 32, ++grp) {
             const int col = c0 + lane;
             double acc = 0.0;
-            if (col < N)
-                for (int row = warp; row < M; row += 8) acc = fma(p.A[int64_t(row) * p.lda + col], __ldcg(&p.r[row]), acc);
+            if (col < N) {
+                if (CLUSTER)
+                    for (int row = warp; row < M; row += 8) acc = fma(cols_sm[(size_t(row) * ngrp + grp) * 32 + lane], __ldcg(&p.r[row]), acc);
+                else
+                    for (int row = warp; row < M; row += 8) acc = fma(p.A[int64_t(row) * p.lda + col], __ldcg(&p.r[row]), acc);
+            }
             gsm[warp][lane] = acc;
             __syncthreads();
             if (warp == 0 && col < N) {
@@ -237,7 +273,7 @@ resident_fbs_kernel(ResidentArgs p) {
             __syncthreads();
         }
         rl_publish<3>(sc, partC[uc & 1], sm);
-        grid.sync();
+        rl_barrier<CLUSTER>(grid);
         double tc[3];
         rl_collect<3>(partC[uc & 1], nb, tc, sm);
         ++uc;
@@ -284,7 +320,7 @@ resident_fbs_kernel(ResidentArgs p) {
         ++it;
         // f_h[it] must be visible to every block before the next window maximum; the partial buffers and
         // xhat / dx / z / r are protected by the two barriers of the next trial
-        grid.sync();
+        rl_barrier<CLUSTER>(grid);
         if (stop) break;
     }
     if (gtid == 0) {
@@ -292,20 +328,38 @@ resident_fbs_kernel(ResidentArgs p) {
         p.out[0] = double(it);
         p.out[1] = double(total_bt);
         p.out[2] = double(cur);
+        p.out[3] = CLUSTER ? 1.0 : 0.0;
     }
 }
 
 typedef void (*ResidentKernel)(ResidentArgs);
 
-template <int LOSS, bool ACCEL>
+template <int LOSS, bool ACCEL, bool CLUSTER>
 static ResidentKernel resident_pick(int prox) {
     switch (prox) {
-        case FB200_PROX_SHRINK: return resident_fbs_kernel<LOSS, FB200_PROX_SHRINK, ACCEL>;
-        case FB200_PROX_NONNEG: return resident_fbs_kernel<LOSS, FB200_PROX_NONNEG, ACCEL>;
-        case FB200_PROX_BOX: return resident_fbs_kernel<LOSS, FB200_PROX_BOX, ACCEL>;
-        case FB200_PROX_IDENTITY: return resident_fbs_kernel<LOSS, FB200_PROX_IDENTITY, ACCEL>;
+        case FB200_PROX_SHRINK: return resident_fbs_kernel<LOSS, FB200_PROX_SHRINK, ACCEL, CLUSTER>;
+        case FB200_PROX_NONNEG: return resident_fbs_kernel<LOSS, FB200_PROX_NONNEG, ACCEL, CLUSTER>;
+        case FB200_PROX_BOX: return resident_fbs_kernel<LOSS, FB200_PROX_BOX, ACCEL, CLUSTER>;
+        case FB200_PROX_IDENTITY: return resident_fbs_kernel<LOSS, FB200_PROX_IDENTITY, ACCEL, CLUSTER>;
         default: return nullptr;
     }
+}
+
+template <bool CLUSTER>
+static ResidentKernel resident_kernel(int loss, int prox, int accelerate) {
+    if (loss == FB200_LOSS_LEAST_SQUARES)
+        return accelerate ? resident_pick<FB200_LOSS_LEAST_SQUARES, true, CLUSTER>(prox) : resident_pick<FB200_LOSS_LEAST_SQUARES, false, CLUSTER>(prox);
+    if (loss == FB200_LOSS_LOGISTIC)
+        return accelerate ? resident_pick<FB200_LOSS_LOGISTIC, true, CLUSTER>(prox) : resident_pick<FB200_LOSS_LOGISTIC, false, CLUSTER>(prox);
+    return nullptr;
+}
+
+// dynamic shared memory of the cluster variant (0 = the matrix does not fit twice into one cluster's shared memory)
+static size_t resident_cluster_smem(int64_t M, int64_t N) {
+    const int64_t rpb = (M + RL_CLUSTER - 1) / RL_CLUSTER, ngrp = (N + RL_CLUSTER * 32 - 1) / (RL_CLUSTER * 32);
+    const int64_t doubles = ((rpb * N + 1) & ~int64_t(1)) + M * ngrp * 32;
+    const int64_t bytes = doubles * 8;
+    return bytes <= 220 * 1024 ? size_t(bytes) : 0;      // + 3.4 KB static, of the 227 KB a CTA may use
 }
 
 }  // namespace fb200
@@ -324,7 +378,14 @@ extern "C" int fb200_resident_blocks(int64_t M, int64_t N) {
 
 extern "C" size_t fb200_resident_scratch_doubles(int64_t M, int64_t N) {
     const int nb = fb200_resident_blocks(M, N);
-    return size_t(8) * size_t(nb > 0 ? nb : 1) * RL_MAXK;
+    return size_t(8) * size_t(nb > RL_CLUSTER ? nb : RL_CLUSTER) * RL_MAXK;
+}
+
+// 1 if the single-cluster variant (matrix resident in the cluster's shared memory) can run this problem
+extern "C" int fb200_resident_cluster_ok(int64_t M, int64_t N) {
+    if (fb200_resident_blocks(M, N) < 1 || resident_cluster_smem(M, N) == 0) return 0;
+    const char* e = getenv("FASTA_B200_RESIDENT_CLUSTER");
+    return (e && e[0] == '0') ? 0 : 1;
 }
 
 // One launch = the whole solve after the prologue.  Pointers as in ResidentArgs; stop_rule 0..3 = residual,
@@ -340,13 +401,31 @@ extern "C" int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64
                                   void* stream) {
     const int nb = fb200_resident_blocks(M, N);
     if (nb < 1) { set_error("resident_fbs: problem not eligible"); return 1; }
-    ResidentKernel k = nullptr;
     if (accelerate && (!xa_a || !xa_b || !za_a || !za_b || !alpha_h)) { set_error("resident_fbs: FISTA buffers missing"); return 1; }
-    if (loss == FB200_LOSS_LEAST_SQUARES) k = accelerate ? resident_pick<FB200_LOSS_LEAST_SQUARES, true>(prox) : resident_pick<FB200_LOSS_LEAST_SQUARES, false>(prox);
-    else if (loss == FB200_LOSS_LOGISTIC) k = accelerate ? resident_pick<FB200_LOSS_LOGISTIC, true>(prox) : resident_pick<FB200_LOSS_LOGISTIC, false>(prox);
+    ResidentKernel k = resident_kernel<false>(loss, prox, accelerate);
     if (!k) { set_error("resident_fbs: unsupported loss / prox tags %d / %d", loss, prox); return 1; }
+    // single-cluster variant: the matrix stays in the cluster's shared memory
+    ResidentKernel kc = nullptr;
+    size_t csmem = 0;
+    if (fb200_resident_cluster_ok(M, N)) {
+        kc = resident_kernel<true>(loss, prox, accelerate);
+        csmem = resident_cluster_smem(M, N);
+        cudaLaunchConfig_t probe{};
+        cudaLaunchAttribute pattr[1];
+        probe.gridDim = dim3(RL_CLUSTER); probe.blockDim = dim3(RL_THREADS); probe.dynamicSmemBytes = csmem;
+        pattr[0].id = cudaLaunchAttributeClusterDimension;
+        pattr[0].val.clusterDim.x = RL_CLUSTER; pattr[0].val.clusterDim.y = 1; pattr[0].val.clusterDim.z = 1;
+        probe.attrs = pattr; probe.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaFuncSetAttribute(reinterpret_cast<const void*>(kc), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+            cudaFuncSetAttribute(reinterpret_cast<const void*>(kc), cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem)) != cudaSuccess ||
+            cudaOccupancyMaxActiveClusters(&nclusters, reinterpret_cast<const void*>(kc), &probe) != cudaSuccess || nclusters < 1) {
+            cudaGetLastError();
+            kc = nullptr;                               // this device cannot place the cluster: grid variant
+        }
+    }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, RL_THREADS, 0) != cudaSuccess || per_sm < 1) {
+    if (!kc && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, RL_THREADS, 0) != cudaSuccess || per_sm < 1)) {
         cudaGetLastError();
         set_error("resident_fbs: occupancy query failed");
         return 1;
@@ -362,6 +441,18 @@ extern "C" int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64
     a.pen_mu = pen_mu; a.p_lo = p_lo; a.p_hi = p_hi;
     a.adaptive = adaptive; a.backtrack = backtrack; a.window = window; a.max_backtracks = max_backtracks;
     a.max_iters = max_iters; a.stop_rule = stop_rule; a.evaluate_objective = evaluate_objective;
+    if (kc) {
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        cfg.gridDim = dim3(RL_CLUSTER); cfg.blockDim = dim3(RL_THREADS); cfg.dynamicSmemBytes = csmem;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = RL_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t ec = cudaLaunchKernelEx(&cfg, kc, a);
+        if (ec != cudaSuccess) { set_error("resident_fbs: cluster launch failed: %s", cudaGetErrorString(ec)); cudaGetLastError(); return 1; }
+        return 0;
+    }
     void* params[1] = {&a};
     cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k), dim3(unsigned(nb)), dim3(RL_THREADS), params, 0,
                                                 static_cast<cudaStream_t>(stream));

@@ -50,6 +50,7 @@ SIGNATURES = {
                                       _p, _p, _sz, _p]),
     "fb200_resident_blocks": (_int, [_i64, _i64]),
     "fb200_resident_scratch_doubles": (_sz, [_i64, _i64]),
+    "fb200_resident_cluster_ok": (_int, [_i64, _i64]),
     "fb200_resident_fbs": (_int, [_p, _i64, _i64, _i64, _p, _int, _int, _dbl, _dbl, _dbl] + [_p] * 18 +
                            [_dbl, _dbl, _dbl, _dbl, _int, _int, _int, _int, _int, _int, _int, _int, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_prox_nuclear_scratch_doubles": (_sz, [_i64, _i64]),

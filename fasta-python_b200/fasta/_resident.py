@@ -114,4 +114,5 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     res = Convergence(residual_hist, norm_residual_hist, tau_hist, int(out[1]), times, n, be.solution(),
                       objective_hist, None, None)
     res.resident = True
+    res.resident_cluster = bool(out[3])                     # single-cluster variant: A stayed in shared memory
     return res

@@ -167,11 +167,16 @@ int fb200_dense_sweep_accel(const double* A, int64_t lda, int64_t M, int64_t N, 
  * stopping.residual / norm_residual / ratio_residual / hybrid_residual, elementwise prox) in ONE cooperative
  * kernel: no host round trip per iteration.  x_a / g_a hold the start point and its gradient, f_h[0] (and
  * obj_h[0]) the start values; histories, per-iteration backtrack counts and %globaltimer stamps are device arrays
- * of max_iters (+1) entries; out[0..2] = iterations, total backtracks, index of the buffer with the last iterate;
+ * of max_iters (+1) entries; out[0..3] = iterations, total backtracks, index of the buffer with the last iterate,
+ * 1 if the single-cluster variant ran;
  * best receives the best iterate.  fb200_resident_blocks returns 0 when the problem is not eligible (A must fit
  * the L2); part: fb200_resident_scratch_doubles(M, N) doubles.                                              */
 int fb200_resident_blocks(int64_t M, int64_t N);
 size_t fb200_resident_scratch_doubles(int64_t M, int64_t N);
+/* 1 if fb200_resident_fbs will run its single-cluster variant for an M x N problem: one 16-CTA thread-block cluster
+ * keeps the matrix in its shared memory (row bands for A x, column groups for A^T r), phases separated by the hardware
+ * cluster barrier; out[3] of fb200_resident_fbs reports which variant ran.  FASTA_B200_RESIDENT_CLUSTER=0 disables it. */
+int fb200_resident_cluster_ok(int64_t M, int64_t N);
 int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64_t N, const double* b, int loss, int prox,
                        double pen_mu, double p_lo, double p_hi, double* x_a, double* x_b, double* g_a, double* g_b,
                        double* xhat, double* dx, double* best, double* z, double* r, double* part,

@@ -41,7 +41,7 @@ SMALL_DENSE = ("lasso_200x1000_k10", "lasso_200x1000_k50", "lasso_333x1414_k40",
 
 
 @pytest.mark.parametrize("case,mode", golden_cases(prefixes=SMALL_DENSE))
-def test_device_resident_loop_matches_golden(case, mode):
+def test_device_resident_loop_matches_golden(case, mode, monkeypatch):
     """Small dense problems run the whole loop in one cooperative kernel (csrc/resident_loop.cu)."""
     import fasta
     gold = load_golden(case, mode)
@@ -52,6 +52,15 @@ def test_device_resident_loop_matches_golden(case, mode):
     assert_trajectory(res, gold, label=f"resident/{case}/{mode}")
     n = res.iteration_count
     assert np.all(np.diff(res.times[:n + 1]) >= 0) and res.times[n] > res.times[0]
+    # 200 x 1000 fits one cluster's shared memory twice: single-cluster variant; the larger cases take the grid variant
+    assert res.resident_cluster == (p.A.shape == (200, 1000))
+    if res.resident_cluster:
+        monkeypatch.setenv("FASTA_B200_RESIDENT_CLUSTER", "0")
+        p = problems.build(case, int(gold["seed"]))
+        A, loss, pen = tagged(p)
+        ref = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+        assert ref.resident and not ref.resident_cluster
+        assert_trajectory(ref, gold, label=f"resident-grid/{case}/{mode}")
 
 
 @pytest.mark.parametrize("case,mode", golden_cases(prefixes=SMALL_DENSE))

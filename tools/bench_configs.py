@@ -50,7 +50,8 @@ def summarise(name, workload, outs, ms, steps, bytes_iter, bytes_bt, cpu, extra=
                               algorithmic_bytes_per_iteration=bytes_iter, note="whole in-loop time, all kernels + host syncs"),
                 cpu_baseline=cpu, backend=outs[-1].backend, single_pass=outs[-1].single_pass,
                 gpu_launches=sum(r.kernel_launches for r in outs),
-                speculation=getattr(outs[-1], "speculation", None))
+                speculation=getattr(outs[-1], "speculation", None),
+                resident=bool(getattr(outs[-1], "resident", False)), resident_cluster=bool(getattr(outs[-1], "resident_cluster", False)))
     if extra:
         line.update(extra)
     print(json.dumps(line), flush=True)
