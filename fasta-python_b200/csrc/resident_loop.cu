@@ -112,6 +112,8 @@ resident_fbs_kernel(ResidentArgs p) {
     const int row_lo = min(M, int(blockIdx.x) * rpb), row_hi = min(M, row_lo + rpb);
     double* rows_sm = rl_dyn;
     double* cols_sm = rl_dyn + ((size_t(rpb) * N + 1) & ~size_t(1));
+    double* xv_sm = cols_sm + size_t(M) * ngrp * 32;     // [N] the vector of the current A x      (staged from L2 once per phase)
+    double* rv_sm = xv_sm + ((N + 1) & ~1);              // [M] the vector of the current A^T r
     if (CLUSTER) {
         for (int e = tid; e < (row_hi - row_lo) * N; e += RL_THREADS) {
             const int rr = e / N, cc = e - rr * N;
@@ -132,6 +134,12 @@ resident_fbs_kernel(ResidentArgs p) {
     double alpha1 = 1.0;                 // reference :157
     int acur = 0;                        // XA[acur] / ZA[acur]: previous prox point and its image
 
+    // the last 64 values of f_hist, kept per block (every block computes the same f1): the non-monotone window needs no
+    // grid-wide visibility of f_h, which saves the fourth barrier of an iteration (window > 64: global history + barrier)
+    __shared__ double fwin[64];
+    const bool local_win = p.window <= 64;
+    if (tid == 0) fwin[0] = p.f_h[0];
+    __syncthreads();
     double tau1 = p.tau_init, g1_sq = p.g1_sq_init;
     double max_residual = -INFINITY, best_q = INFINITY;
     int cur = 0, it = 0;
@@ -147,7 +155,8 @@ resident_fbs_kernel(ResidentArgs p) {
         double tau0 = tau1;
         int bt = 0;
         double f_window_max = -INFINITY;
-        for (int k = (it - p.window + 1 > 0 ? it - p.window + 1 : 0); k <= it; ++k) f_window_max = fmax(f_window_max, __ldcg(&p.f_h[k]));
+        for (int k = (it - p.window + 1 > 0 ? it - p.window + 1 : 0); k <= it; ++k)
+            f_window_max = fmax(f_window_max, local_win ? fwin[k & 63] : __ldcg(&p.f_h[k]));
         double dx_g0, dx_sq, xmxh_sq, pen_raw, f1, restart_dot = 0.0;
         while (true) {
             // ---- forward step, prox, Dx and their sums (reference :181-186) ----
@@ -174,10 +183,17 @@ resident_fbs_kernel(ResidentArgs p) {
             // ---- z = A x1, r = gradf(z), f (reference :187-188): one warp per row ----
             double fs[1] = {0.0};
             double* zp = ACCEL ? p.ZA[1 - acur] : p.z;
+            if (CLUSTER) {
+                for (int j = tid; j < N; j += RL_THREADS) xv_sm[j] = __ldcg(&xp[j]);
+                __syncthreads();
+            }
             for (int row = CLUSTER ? row_lo + warp : gwarp; row < (CLUSTER ? row_hi : M); row += CLUSTER ? RL_THREADS / 32 : gwarps) {
                 const double* ar = CLUSTER ? rows_sm + size_t(row - row_lo) * N : p.A + int64_t(row) * p.lda;
                 double acc = 0.0;
-                for (int j = lane; j < N; j += 32) acc = fma(ar[j], __ldcg(&xp[j]), acc);
+                if (CLUSTER)
+                    for (int j = lane; j < N; j += 32) acc = fma(ar[j], xv_sm[j], acc);
+                else
+                    for (int j = lane; j < N; j += 32) acc = fma(ar[j], __ldcg(&xp[j]), acc);
                 acc = warp_sum(acc);
                 if (lane == 0) {
                     double ri, fi;
@@ -247,12 +263,16 @@ resident_fbs_kernel(ResidentArgs p) {
         // ---- g1 = A^T r (reference :248): 32 columns x 8 row lanes per block pass, + BB sums (:254-260) ----
         double sc[3] = {0.0, 0.0, 0.0};
         int grp = 0;
+        if (CLUSTER) {
+            for (int j = tid; j < M; j += RL_THREADS) rv_sm[j] = __ldcg(&p.r[j]);
+            __syncthreads();
+        }
         for (int c0 = blockIdx.x * 32; c0 < N; c0 += nb * 32, ++grp) {
             const int col = c0 + lane;
             double acc = 0.0;
             if (col < N) {
                 if (CLUSTER)
-                    for (int row = warp; row < M; row += 8) acc = fma(cols_sm[(size_t(row) * ngrp + grp) * 32 + lane], __ldcg(&p.r[row]), acc);
+                    for (int row = warp; row < M; row += 8) acc = fma(cols_sm[(size_t(row) * ngrp + grp) * 32 + lane], rv_sm[row], acc);
                 else
                     for (int row = warp; row < M; row += 8) acc = fma(p.A[int64_t(row) * p.lda + col], __ldcg(&p.r[row]), acc);
             }
@@ -318,9 +338,14 @@ resident_fbs_kernel(ResidentArgs p) {
         }
         cur = 1 - cur;
         ++it;
-        // f_h[it] must be visible to every block before the next window maximum; the partial buffers and
-        // xhat / dx / z / r are protected by the two barriers of the next trial
-        rl_barrier<CLUSTER>(grid);
+        // f_h[it] must be visible to every block before the next window maximum (kept per block when the window fits
+        // the local ring); the partial buffers and xhat / dx / z / r are protected by the two barriers of the next trial
+        if (local_win) {
+            if (tid == 0) fwin[it & 63] = f1;       // it was incremented: this is f_hist[it]
+            __syncthreads();
+        } else {
+            rl_barrier<CLUSTER>(grid);
+        }
         if (stop) break;
     }
     if (gtid == 0) {
@@ -357,7 +382,7 @@ static ResidentKernel resident_kernel(int loss, int prox, int accelerate) {
 // dynamic shared memory of the cluster variant (0 = the matrix does not fit twice into one cluster's shared memory)
 static size_t resident_cluster_smem(int64_t M, int64_t N) {
     const int64_t rpb = (M + RL_CLUSTER - 1) / RL_CLUSTER, ngrp = (N + RL_CLUSTER * 32 - 1) / (RL_CLUSTER * 32);
-    const int64_t doubles = ((rpb * N + 1) & ~int64_t(1)) + M * ngrp * 32;
+    const int64_t doubles = ((rpb * N + 1) & ~int64_t(1)) + M * ngrp * 32 + ((N + 1) & ~int64_t(1)) + M;
     const int64_t bytes = doubles * 8;
     return bytes <= 220 * 1024 ? size_t(bytes) : 0;      // + 3.4 KB static, of the 227 KB a CTA may use
 }
@@ -410,19 +435,31 @@ extern "C" int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64
     if (fb200_resident_cluster_ok(M, N)) {
         kc = resident_kernel<true>(loss, prox, accelerate);
         csmem = resident_cluster_smem(M, N);
-        cudaLaunchConfig_t probe{};
-        cudaLaunchAttribute pattr[1];
-        probe.gridDim = dim3(RL_CLUSTER); probe.blockDim = dim3(RL_THREADS); probe.dynamicSmemBytes = csmem;
-        pattr[0].id = cudaLaunchAttributeClusterDimension;
-        pattr[0].val.clusterDim.x = RL_CLUSTER; pattr[0].val.clusterDim.y = 1; pattr[0].val.clusterDim.z = 1;
-        probe.attrs = pattr; probe.numAttrs = 1;
-        int nclusters = 0;
-        if (cudaFuncSetAttribute(reinterpret_cast<const void*>(kc), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-            cudaFuncSetAttribute(reinterpret_cast<const void*>(kc), cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem)) != cudaSuccess ||
-            cudaOccupancyMaxActiveClusters(&nclusters, reinterpret_cast<const void*>(kc), &probe) != cudaSuccess || nclusters < 1) {
-            cudaGetLastError();
-            kc = nullptr;                               // this device cannot place the cluster: grid variant
+        // attributes and the placement query once per kernel and shared-memory size
+        static ResidentKernel ok_kernel[64];
+        static size_t ok_smem[64];
+        static int ok_state[64], ok_count = 0;
+        int state = -1;
+        for (int i = 0; i < ok_count; ++i)
+            if (ok_kernel[i] == kc && ok_smem[i] == csmem) state = ok_state[i];
+        if (state < 0) {
+            cudaLaunchConfig_t probe{};
+            cudaLaunchAttribute pattr[1];
+            probe.gridDim = dim3(RL_CLUSTER); probe.blockDim = dim3(RL_THREADS); probe.dynamicSmemBytes = csmem;
+            pattr[0].id = cudaLaunchAttributeClusterDimension;
+            pattr[0].val.clusterDim.x = RL_CLUSTER; pattr[0].val.clusterDim.y = 1; pattr[0].val.clusterDim.z = 1;
+            probe.attrs = pattr; probe.numAttrs = 1;
+            int nclusters = 0;
+            state = 1;
+            if (cudaFuncSetAttribute(reinterpret_cast<const void*>(kc), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                cudaFuncSetAttribute(reinterpret_cast<const void*>(kc), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+                cudaOccupancyMaxActiveClusters(&nclusters, reinterpret_cast<const void*>(kc), &probe) != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                state = 0;                              // this device cannot place the cluster: grid variant
+            }
+            if (ok_count < 64) { ok_kernel[ok_count] = kc; ok_smem[ok_count] = csmem; ok_state[ok_count] = state; ++ok_count; }
         }
+        if (!state) kc = nullptr;
     }
     int per_sm = 0;
     if (!kc && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, RL_THREADS, 0) != cudaSuccess || per_sm < 1)) {

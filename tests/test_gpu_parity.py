@@ -111,7 +111,8 @@ def test_device_resident_loop_options(capsys):
     f, gradf, g, proxg = problems.numpy_callables(p)
     for opts in (dict(stop_rule_name="residual", tolerance=1e-3), dict(stop_rule_name="norm_residual", tolerance=1e-4),
                  dict(stop_rule_name="ratio_residual", tolerance=1e-4), dict(backtrack=False, adaptive=False, max_iters=50),
-                 dict(L=1.3, tau0=0.11, max_iters=40, evaluate_objective=False), dict(window=3, stepsize_shrink=0.5, max_iters=60)):
+                 dict(L=1.3, tau0=0.11, max_iters=40, evaluate_objective=False), dict(window=3, stepsize_shrink=0.5, max_iters=60),
+                 dict(window=70, max_iters=90)):
         o = dict(verbose=False, evaluate_objective=True)
         o.update(opts)
         name = o.pop("stop_rule_name", None)
