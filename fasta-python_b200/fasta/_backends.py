@@ -573,8 +573,8 @@ class FusedBackend:
 
     def trial_accel(self, tau, alpha_prev, restart):
         """One FISTA trial with the contractions in a single pass (reference :181-188 and :220-249): forward step and
-        prox, fetch the restart dot, form alpha / the extrapolation weight exactly as the host loop does, then queue
-        the x extrapolation and the sweep (z_accel1 = A x_accel1, extrapolated z, f at both, gradient, BB sums)."""
+        prox, the x extrapolation and the sweep (z_accel1 = A x_accel1, extrapolated z, f at both, gradient, BB sums)
+        queued back to back with the extrapolation weight the host loop will form, one fetch per trial."""
         x0, g0 = self.X[self.ip], self.G[self.gp]
         xa1, xa0 = self.XA[self.ac], self.XA[self.ap]
         if self.use_tv_accel:
@@ -593,25 +593,30 @@ class FusedBackend:
                                             self.DX.data_ptr(), self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
                     "fb200_fbs_step")
         self.launches += 1
-        s = self.ws.fetch()
-        step = Scalars(dx_g0=s[S.S_DX_G0].copy(), dx_sq=s[S.S_DX_SQ].copy(), restart=s[S.S_RESTART].copy())
-        alpha0 = alpha_prev                                          # reference :224-240
-        if restart and step.restart > 1E-30:
-            alpha0 = 1.0
-        alpha1 = (1 + np.sqrt(1 + 4 * alpha0 ** 2)) / 2
-        c = (alpha0 - 1) / alpha1
-        # x1 = x_accel1 + c (x_accel1 - x_accel0), |x1 - x1hat|^2, sum |x1|   (m = 0: the z part is the sweep's)
-        _cabi.check(self.lib.fb200_accel_step(float(c), xa1.data_ptr(), xa0.data_ptr(), self.XH.data_ptr(), self.n,
-                                              self.X[self.ic].data_ptr(), 0, 0, 0, 0, S.LOSS_NONE, self.pen.tag, 0, 0,
-                                              self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st), "fb200_accel_step")
-        self.launches += 1
-        self.drv.sweep_accel(xa1, self.loss.tag, self.loss.b, self.ZA[self.ap], c, self.ZA[self.ac], self.Z, self.R,
-                             self.G[self.gc], 2, x0, self.XH, self.DX, tau, self.ws)
-        s = self.ws.fetch()
+        # The extrapolation weight has two possible values: the regular (alpha0 - 1) / alpha1 with alpha0 = alpha_prev, or 0
+        # when the restart test of reference :231 -- a sum of this very forward step -- fires.  Queue the extrapolation and
+        # the sweep with the regular one behind the step, fetch ONCE, and repeat the two with c = 0 in the rare iterations
+        # that restart (the step's own sums stay in the scalar block).
+        alpha1 = (1 + np.sqrt(1 + 4 * alpha_prev ** 2)) / 2          # reference :238-240 with alpha0 = alpha_prev
+        c = (alpha_prev - 1) / alpha1
+
+        def extrapolate_and_sweep(weight):
+            # x1 = x_accel1 + c (x_accel1 - x_accel0), |x1 - x1hat|^2, sum |x1|   (m = 0: the z part is the sweep's)
+            _cabi.check(self.lib.fb200_accel_step(float(weight), xa1.data_ptr(), xa0.data_ptr(), self.XH.data_ptr(), self.n,
+                                                  self.X[self.ic].data_ptr(), 0, 0, 0, 0, S.LOSS_NONE, self.pen.tag, 0, 0,
+                                                  self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st), "fb200_accel_step")
+            self.launches += 1
+            self.drv.sweep_accel(xa1, self.loss.tag, self.loss.b, self.ZA[self.ap], weight, self.ZA[self.ac], self.Z, self.R,
+                                 self.G[self.gc], 2, x0, self.XH, self.DX, tau, self.ws)
+            return self.ws.fetch()
+
+        s = extrapolate_and_sweep(c)
+        if restart and s[S.S_RESTART] > 1E-30 and c != 0.0:
+            s = extrapolate_and_sweep(0.0)
         self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
         extrap = Scalars(f=self.loss.finalize(s[S.S_AUX3]), xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]))
-        return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=step.dx_g0, dx_sq=step.dx_sq, xmxh_sq=s[S.S_XMXH_SQ],
-                       pen=self.pen.value(s[S.S_PEN]), restart=step.restart, extrap=extrap)
+        return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ], xmxh_sq=s[S.S_XMXH_SQ],
+                       pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART], extrap=extrap)
 
     def _trial_accel_tv(self, tau, alpha_prev, restart):
         """TV + FISTA: ONE kernel per trial.  The extrapolation weight has two possible values -- the regular

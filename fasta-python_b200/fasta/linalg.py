@@ -164,6 +164,56 @@ class DenseMap(LinearMap):
                                        g_dev.data_ptr(), 0, 0, 0, 0, 0.0, ws.scal.data_ptr(), ws.buf.data_ptr(),
                                        ws.nbytes, _device.stream_ptr()), "fb200_gemvT_bb")
 
+    def gram_norm(self, iters: int = 500, tol: float = 1e-12, check_every: int = 8):
+        """Largest eigenvalue of A^T A, i.e. |A|_2^2 -- the Lipschitz constant of the least-squares gradient that the
+        reference only ESTIMATES from two random probes (``fasta/__init__.py:100-113``) -- by power iteration on the
+        device (exact constant, no dependence on the global RNG).  An iteration is ONE pass over A:
+        the single-pass sweep with a zero right-hand side gives ``g = A^T (A x)`` and ``|A x|^2`` (the Rayleigh
+        quotient of the normalised x) together; matrices the sweep cannot take use the two streaming contractions.
+        The start vector is fixed, the reductions are fixed-order: the result is reproducible bit for bit.
+
+            L = A.gram_norm();  fasta.fasta(A, f, gradf, g, proxg, x0, L=L, tau0=(2 / L) / 10)   # reference :113
+        """
+        t = _device.torch()
+        lib = _cabi.load()
+        S = _cabi
+        dev = self.matrix.device
+        M, N, A, lda = self.M, self.N, self.matrix, self.lda
+        ws = _device.shared_workspace(M, N)
+        new = lambda k: t.empty(k, dtype=t.float64, device=dev)
+        x, g, z, r = new(N), new(N), new(M), new(M)
+        zero_n, zero_m = t.zeros(N, dtype=t.float64, device=dev), t.zeros(M, dtype=t.float64, device=dev)
+        k = t.arange(N, dtype=t.float64, device=dev)
+        g.copy_(t.cos(0.7 * k + 0.3) + 1.5)                   # fixed start: positive mean, no symmetry
+        st = _device.stream_ptr
+        sweep = bool(lib.fb200_sweep_supported(A.data_ptr(), lda, M, N))
+        lam_prev, lam = 0.0, 0.0
+        g_sq = float((g * g).sum().item())
+        for it in range(1, iters + 1):
+            # x = g / |g|  (xhat = x0 - tau * g0 with x0 = 0, tau = -1 / |g|)
+            _cabi.check(lib.fb200_forward_step(zero_n.data_ptr(), g.data_ptr(), -1.0 / np.sqrt(g_sq), N, x.data_ptr(), st()),
+                        "fb200_forward_step")
+            if sweep:
+                _cabi.check(lib.fb200_dense_sweep(A.data_ptr(), lda, M, N, x.data_ptr(), S.LOSS_LEAST_SQUARES,
+                                                  zero_m.data_ptr(), z.data_ptr(), r.data_ptr(), g.data_ptr(), 1, 0, 0, 0,
+                                                  0.0, ws.scal.data_ptr(), ws.buf.data_ptr(), ws.nbytes, st()),
+                            "fb200_dense_sweep")
+            else:
+                _cabi.check(lib.fb200_gemv_loss(A.data_ptr(), lda, M, N, x.data_ptr(), S.LOSS_LEAST_SQUARES,
+                                                zero_m.data_ptr(), z.data_ptr(), r.data_ptr(), ws.scal.data_ptr(),
+                                                ws.buf.data_ptr(), ws.nbytes, st()), "fb200_gemv_loss")
+                _cabi.check(lib.fb200_gemvT_bb(A.data_ptr(), lda, M, N, r.data_ptr(), g.data_ptr(), 1, 0, 0, 0, 0.0,
+                                               ws.scal.data_ptr(), ws.buf.data_ptr(), ws.nbytes, st()), "fb200_gemvT_bb")
+            s = ws.fetch()                                    # |A x|^2 = x^T A^T A x (Rayleigh quotient), |A^T A x|^2
+            lam, g_sq = float(s[S.S_F]), float(s[S.S_G1_SQ])
+            if g_sq == 0.0:
+                return 0.0
+            if it % check_every == 0:
+                if abs(lam - lam_prev) <= tol * lam:
+                    break
+                lam_prev = lam
+        return lam
+
     def _gemm(self, v, transposed):
         """A @ V or A.T @ V for a matrix V with the fp64 DMMA kernel (csrc/batched_gemm.cu); shapes the kernel
         cannot take directly (odd N, L or leading dimension) go through zero-padded copies."""

@@ -152,6 +152,36 @@ def test_nuclear_prox_jacobi_svd(M, N):
     assert np.abs(fasta.proximal.project_Lnuc_ball(Xd.t(), 1.5).cpu().numpy() - a.cpu().numpy().T).max() <= 1e-12 * s[0]
 
 
+@pytest.mark.parametrize("M,N", [(300, 800), (301, 803), (64, 32)])
+def test_gram_norm_power_iteration(M, N):
+    """|A|_2^2 by power iteration on the device (one single-pass sweep per iteration when the matrix is eligible, the two
+    streaming contractions otherwise) against numpy's SVD; reproducible bit for bit; usable as the exact Lipschitz
+    constant in place of the reference's randomized estimate (fasta/__init__.py:100-113) without touching the RNG."""
+    import fasta
+    rng = np.random.RandomState(M + N)
+    u, v = rng.randn(M), rng.randn(N)
+    A = rng.randn(M, N) + 3.0 * np.outer(u, v) / np.sqrt(M * N) * np.sqrt(M + N)      # a clear spectral gap
+    op = fasta.linalg.LinearMap.from_matrix(A)
+    want = np.linalg.norm(A, 2) ** 2
+    got = op.gram_norm()
+    assert abs(got - want) <= 1e-9 * want
+    assert op.gram_norm() == got
+    # a plain Gaussian matrix (tiny gap): the Rayleigh quotient is a lower bound that converges from below
+    B = rng.randn(M, N)
+    lam = fasta.linalg.LinearMap.from_matrix(B).gram_norm(iters=3000)
+    assert 0.999 * np.linalg.norm(B, 2) ** 2 <= lam <= (1 + 1e-12) * np.linalg.norm(B, 2) ** 2
+    if (M, N) == (300, 800):
+        b = A @ (rng.rand(N) < 0.02) + 0.01 * rng.randn(M)
+        loss, pen = fasta.losses.LeastSquares(b), fasta.proximal.L1Norm(0.5)
+        state = np.random.get_state()[1].copy()
+        res = fasta.fasta(op, loss.f, loss.gradf, pen.g, pen.prox, np.zeros(N), L=got, tau0=(2 / got) / 10, verbose=False,
+                          evaluate_objective=True)
+        assert np.array_equal(np.random.get_state()[1], state)                 # no draws from the global RNG
+        ref = fasta.fasta(op, loss.f, loss.gradf, pen.g, pen.prox, np.zeros(N), verbose=False, evaluate_objective=True)
+        fa, fb = res.objectives[res.iteration_count], ref.objectives[ref.iteration_count]
+        assert abs(fa - fb) <= 1e-6 * abs(fb)
+
+
 def test_losses():
     import fasta
     rng = np.random.RandomState(5)
