@@ -102,6 +102,26 @@ def test_without_speculative_run_ahead_matches_golden(case, mode, monkeypatch):
     assert np.allclose(res.stepsizes[:k], ref.stepsizes[:k], rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("case,mode", golden_cases(prefixes=("lasso_200x1000_k50", "lasso_333", "tv_64", "lasso_4000")))
+def test_two_probe_lipschitz_estimate_matches_golden(case, mode, monkeypatch):
+    """Least-squares problems estimate L from ONE contraction pair on v1 - v2 (the gradient is affine); with
+    FASTA_B200_AFFINE_PROBE=0 the two terms of reference :106-110 are evaluated separately.  Same trajectory, and the
+    two estimates agree to rounding."""
+    import fasta
+    monkeypatch.setenv("FASTA_B200_RESIDENT", "0")
+    gold = load_golden(case, mode)
+    p = problems.build(case, int(gold["seed"]))
+    A, loss, pen = tagged(p)
+    state = np.random.get_state()
+    one = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    monkeypatch.setenv("FASTA_B200_AFFINE_PROBE", "0")
+    np.random.set_state(state)
+    two = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
+    assert_trajectory(two, gold, label=f"two-probe/{case}/{mode}")
+    assert abs(one.stepsizes[0] - two.stepsizes[0]) <= 1e-13 * two.stepsizes[0]
+    assert one.kernel_launches < two.kernel_launches
+
+
 def test_device_resident_loop_options(capsys):
     """Other stop rules, no backtracking, no objective, verbose lines, user-supplied L / tau0."""
     import fasta
