@@ -347,8 +347,10 @@ class FusedBackend:
         self.XH, self.DX = new(self.n), new(self.n)
         self.Z, self.R = new(self.m), new(self.m)
         if self.accelerate:
-            self.XA = [new(self.n), new(self.n)]
-            self.ZA = [new(self.m), new(self.m)]
+            # three each: a FISTA trial queued ahead must not overwrite the x_accel0 / z_accel0 of the trial before it,
+            # which is repeated with weight 0 when its restart test fires
+            self.XA = [new(self.n) for _ in range(3)]
+            self.ZA = [new(self.m) for _ in range(3)]
         self.ic = self.ip = 0      # X[ic] current iterate, X[ip] previous
         self.ib = 0                # X[ib] best iterate so far
         self.gc = self.gp = 0      # G[gc] current gradient, G[gp] previous
@@ -363,6 +365,8 @@ class FusedBackend:
         self.use_sweep_accel = (self.accelerate and bool(getattr(driver, "sweep_ok", False))
                                 and hasattr(driver, "sweep_accel") and loss.tag != S.LOSS_NONE
                                 and os.environ.get("FASTA_B200_SWEEP_ACCEL", "1") != "0")
+        self.accel_speculate_ok = ((self.use_tv_accel or self.use_sweep_accel)
+                                   and os.environ.get("FASTA_B200_SPECULATE", "1") != "0")
         # Lipschitz prologue: one probe pass instead of two when the gradient of the loss is affine (see lipschitz_push)
         self.affine_probe = (loss.tag == S.LOSS_LEAST_SQUARES
                              and os.environ.get("FASTA_B200_AFFINE_PROBE", "1") != "0")
@@ -381,7 +385,7 @@ class FusedBackend:
             (penalty.tag == S.PROX_SHRINK and np.ndim(getattr(penalty, "mu", 0.0)) == 0)
         self.speculate_ok = ((tv_iter or (self.use_sweep and elementwise))
                              and os.environ.get("FASTA_B200_SPECULATE", "1") != "0")
-        # TV + FISTA: the whole accelerated trial in one kernel (see trial_accel)
+        # TV + FISTA: the whole accelerated trial in one kernel (see _queue_accel)
         self.use_tv_accel = (self.accelerate and isinstance(driver, TVDriver) and driver.fused_step_ok
                              and driver.fista_fused_ok and penalty.tag == S.PROX_TV_BALL
                              and loss.tag in (S.LOSS_LEAST_SQUARES, S.LOSS_LOGISTIC))
@@ -509,16 +513,16 @@ class FusedBackend:
         self.ic = next(k for k in (0, 1, 2, 3) if k != self.ip and k != self.ib and k != prev)
         self.gp, self.gc = self.gc, (self.gc + 1) % 3
         if self.accelerate:
-            self.ap, self.ac = self.ac, 1 - self.ac
+            self.ap, self.ac = self.ac, (self.ac + 1) % 3
 
     # A trial is queued (all kernels asynchronous) and collected (one fetch).  The host loop uses the split to queue
     # the NEXT iteration's trial as soon as the new step size is known and to do its bookkeeping (histories, best
     # iterate, stop rule) while the device already works; trial() is queue + collect.
     def rotation(self):
-        return self.ic, self.ip, self.gc, self.gp, self._ahead
+        return self.ic, self.ip, self.gc, self.gp, self.ac, self.ap, self._ahead
 
     def restore(self, state):
-        self.ic, self.ip, self.gc, self.gp, self._ahead = state
+        self.ic, self.ip, self.gc, self.gp, self.ac, self.ap, self._ahead = state
 
     def speculate_begin(self, f0, g0_sq, adaptive, backtrack, max_backtracks, window, stop_rule_id, tolerance):
         """From now on every trial is followed by fb200_trial_decide (the loop's decisions repeated on the device: the
@@ -599,14 +603,25 @@ class FusedBackend:
     def trial(self, tau, bt=0, host=(0, -np.inf, 0.0)):
         return self._collect_trial(self._queue_trial(tau, bt, host))
 
-    def trial_accel(self, tau, alpha_prev, restart):
-        """One FISTA trial with the contractions in a single pass (reference :181-188 and :220-249): forward step and
-        prox, the x extrapolation and the sweep (z_accel1 = A x_accel1, extrapolated z, f at both, gradient, BB sums)
-        queued back to back with the extrapolation weight the host loop will form, one fetch per trial."""
+    # ---- FISTA trials with the contractions in a single pass (reference :181-188 and :220-249) ------------------
+    # The extrapolation weight c = (alpha0 - 1) / alpha1 depends on the restart test of reference :231, a sum of the
+    # very forward step being computed, but it has only two possible values: the regular one (alpha0 = the previous
+    # alpha1), known before the launch, and 0.  A trial is therefore queued with the weight the caller expects and
+    # reports the restart dot; the caller repeats it with c = 0 in the rare iterations that restart.  Queue / collect
+    # are split (in-stream snapshot of the sums) so that the host loop can queue the NEXT trial before collecting this one.
+    @staticmethod
+    def accel_weight(alpha_prev):
+        alpha1 = (1 + np.sqrt(1 + 4 * alpha_prev ** 2)) / 2          # reference :238-240 with alpha0 = alpha_prev
+        return (alpha_prev - 1) / alpha1
+
+    def _queue_accel(self, tau, c):
         x0, g0 = self.X[self.ip], self.G[self.gp]
         xa1, xa0 = self.XA[self.ac], self.XA[self.ap]
         if self.use_tv_accel:
-            return self._trial_accel_tv(tau, alpha_prev, restart)
+            # TV: the whole trial in ONE kernel (15U bytes)
+            self.drv.fista_fused(x0, g0, tau, c, self.loss.tag, self.loss.b, xa0, self.ZA[self.ap], xa1, self.ZA[self.ac],
+                                 self.X[self.ic], self.G[self.gc], self.ws)
+            return "tv", self.ws.snapshot(), c
         p0, p1 = self.pen.params(tau)
         st = self._st()
         if self.pen.tag == S.PROX_L1BALL:
@@ -620,51 +635,30 @@ class FusedBackend:
                                             xa0.data_ptr(), self.n, self.XH.data_ptr(), xa1.data_ptr(),
                                             self.DX.data_ptr(), self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st),
                     "fb200_fbs_step")
-        self.launches += 1
-        # The extrapolation weight has two possible values: the regular (alpha0 - 1) / alpha1 with alpha0 = alpha_prev, or 0
-        # when the restart test of reference :231 -- a sum of this very forward step -- fires.  Queue the extrapolation and
-        # the sweep with the regular one behind the step, fetch ONCE, and repeat the two with c = 0 in the rare iterations
-        # that restart (the step's own sums stay in the scalar block).
-        alpha1 = (1 + np.sqrt(1 + 4 * alpha_prev ** 2)) / 2          # reference :238-240 with alpha0 = alpha_prev
-        c = (alpha_prev - 1) / alpha1
+        # x1 = x_accel1 + c (x_accel1 - x_accel0), |x1 - x1hat|^2, sum |x1|   (m = 0: the z part is the sweep's)
+        _cabi.check(self.lib.fb200_accel_step(float(c), xa1.data_ptr(), xa0.data_ptr(), self.XH.data_ptr(), self.n,
+                                              self.X[self.ic].data_ptr(), 0, 0, 0, 0, S.LOSS_NONE, self.pen.tag, 0, 0,
+                                              self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st), "fb200_accel_step")
+        self.launches += 2
+        self.drv.sweep_accel(xa1, self.loss.tag, self.loss.b, self.ZA[self.ap], c, self.ZA[self.ac], self.Z, self.R,
+                             self.G[self.gc], 2, x0, self.XH, self.DX, tau, self.ws)
+        return "dense", self.ws.snapshot(), c
 
-        def extrapolate_and_sweep(weight):
-            # x1 = x_accel1 + c (x_accel1 - x_accel0), |x1 - x1hat|^2, sum |x1|   (m = 0: the z part is the sweep's)
-            _cabi.check(self.lib.fb200_accel_step(float(weight), xa1.data_ptr(), xa0.data_ptr(), self.XH.data_ptr(), self.n,
-                                                  self.X[self.ic].data_ptr(), 0, 0, 0, 0, S.LOSS_NONE, self.pen.tag, 0, 0,
-                                                  self.ws.scal.data_ptr(), self.ws.buf.data_ptr(), st), "fb200_accel_step")
-            self.launches += 1
-            self.drv.sweep_accel(xa1, self.loss.tag, self.loss.b, self.ZA[self.ap], weight, self.ZA[self.ac], self.Z, self.R,
-                                 self.G[self.gc], 2, x0, self.XH, self.DX, tau, self.ws)
-            return self.ws.fetch()
-
-        s = extrapolate_and_sweep(c)
-        if restart and s[S.S_RESTART] > 1E-30 and c != 0.0:
-            s = extrapolate_and_sweep(0.0)
+    def _collect_accel(self, handle):
+        kind, ticket, c = handle
+        s = self.ws.collect(ticket)
         self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
-        extrap = Scalars(f=self.loss.finalize(s[S.S_AUX3]), xmxh_sq=s[S.S_XMXH_SQ], pen=self.pen.value(s[S.S_PEN]))
+        pen = self.pen.value(0.0) if kind == "tv" else self.pen.value(s[S.S_PEN])
+        extrap = Scalars(f=self.loss.finalize(s[S.S_AUX3]), xmxh_sq=s[S.S_XMXH_SQ], pen=pen)
         return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ], xmxh_sq=s[S.S_XMXH_SQ],
-                       pen=self.pen.value(s[S.S_PEN]), restart=s[S.S_RESTART], extrap=extrap)
+                       pen=pen, restart=s[S.S_RESTART], extrap=extrap, c=c)
 
-    def _trial_accel_tv(self, tau, alpha_prev, restart):
-        """TV + FISTA: ONE kernel per trial.  The extrapolation weight has two possible values -- the regular
-        (alpha0 - 1) / alpha1 with alpha0 = alpha_prev, or 0 when the restart test of reference :231 fires -- so the
-        kernel is launched with the regular one and repeated with c = 0 in the rare iterations that restart."""
-        alpha1 = (1 + np.sqrt(1 + 4 * alpha_prev ** 2)) / 2           # reference :238-240 with alpha0 = alpha_prev
-        c = (alpha_prev - 1) / alpha1
-        args = (self.X[self.ip], self.G[self.gp], tau)
-        bufs = (self.loss.tag, self.loss.b, self.XA[self.ap], self.ZA[self.ap], self.XA[self.ac], self.ZA[self.ac],
-                self.X[self.ic], self.G[self.gc], self.ws)
-        self.drv.fista_fused(*args, c, *bufs)
-        s = self.ws.fetch()
-        if restart and s[S.S_RESTART] > 1E-30 and c != 0.0:
-            self.drv.fista_fused(*args, 0.0, *bufs)
-            s = self.ws.fetch()
-        self._spec = Scalars(dx_dg=s[S.S_DX_DG], dg_sq=s[S.S_DG_SQ], g_sq=s[S.S_G1_SQ])
-        zero = self.pen.value(0.0)
-        extrap = Scalars(f=self.loss.finalize(s[S.S_AUX3]), xmxh_sq=s[S.S_XMXH_SQ], pen=zero)
-        return Scalars(f=self.loss.finalize(s[S.S_F]), dx_g0=s[S.S_DX_G0], dx_sq=s[S.S_DX_SQ], xmxh_sq=s[S.S_XMXH_SQ],
-                       pen=zero, restart=s[S.S_RESTART], extrap=extrap)
+    def trial_accel(self, tau, alpha_prev, restart):
+        """One FISTA trial, collected at once: the regular weight first, repeated with c = 0 if the restart test fires."""
+        t = self._collect_accel(self._queue_accel(tau, self.accel_weight(alpha_prev)))
+        if restart and t.restart > 1E-30 and t.c != 0.0:
+            t = self._collect_accel(self._queue_accel(tau, 0.0))
+        return t
 
     def trial_launch(self, tau):
         """Queue the next iteration's first trial; until trial_finish() the 'current' iterate is X[ip]."""

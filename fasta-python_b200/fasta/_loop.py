@@ -142,6 +142,11 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     if speculate:
         rule_id = _BUILTIN_RULES.get(stop_rule, -1)          # a user's rule is evaluated by the host only
         be.speculate_begin(f1, g1_sq, adaptive, backtrack, max_backtracks, window, rule_id, tolerance)
+    # FISTA trials (fused back-ends, fixed step size): the next trial's step size and -- unless this trial restarts the
+    # acceleration -- its extrapolation weight are known before this trial's sums are: it is queued by value ahead of
+    # the collect, and dropped (it only wrote scratch buffers) if this trial restarts or is rejected by the line search.
+    spec_accel = (fused_accel and not adaptive and getattr(be, "accel_speculate_ok", False)
+                  and os.environ.get("FASTA_B200_RUN_AHEAD", "1") != "0")
     spec_stats = dict(speculated=0, dropped=0, mismatched=0)
     by_value = True           # whether `pending` was queued with the host's step size (else: the device's)
     pending = None            # handle of the trial queued for iteration i
@@ -177,6 +182,26 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
                 by_value = True
             if not by_value:
                 tau0 = t.tau_used                           # the device's value of the :253-270 algebra, the one it used
+        elif spec_accel:
+            if pending is None:
+                be.advance()                                # ref :176-178
+                pending = be._queue_accel(tau0, be.accel_weight(alpha1))
+            be._ahead = False
+            rot = be.rotation()
+            ahead = None
+            if i + 1 < max_iters:
+                be.advance()
+                be._ahead = True                            # weight of trial i+1 if trial i does not restart (ref :238-240)
+                ahead = be._queue_accel(tau0, be.accel_weight((1 + np.sqrt(1 + 4 * alpha1 ** 2)) / 2))
+                spec_stats["speculated"] += 1
+            t = be._collect_accel(pending)
+            pending = None
+            if restart and t.restart > 1E-30 and t.c != 0.0:            # ref :231 fires: the weight must be 0, repeat
+                if ahead is not None:
+                    be.restore(rot)
+                    ahead = None
+                    spec_stats["dropped"] += 1
+                t = be._collect_accel(be._queue_accel(tau0, 0.0))
         elif queued:
             t = be.trial_finish()
             queued = False
@@ -241,7 +266,13 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
 
         # ref :308 -- evaluated here (it depends only on the residuals above) so that no trial is queued past the end
         stop = stop_rule(i, residual_hist[i], norm_residual_hist[i], max_residual, tolerance)
-        if speculate:
+        if spec_accel:
+            if ahead is None and not stop and i + 1 < max_iters:
+                be.advance()                                # after a restart / backtracked iteration: queue the next trial now
+                be._ahead = True
+                ahead = be._queue_accel(tau1, be.accel_weight(alpha1))
+            pending, ahead = ahead, None
+        elif speculate:
             if ahead is None and not stop and i + 1 < max_iters:
                 be.advance()                                # after a backtracked iteration: queue the next trial now
                 be._ahead = True
@@ -281,7 +312,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     times[i] = time()                                       # ref :315
     res = Convergence(residual_hist, norm_residual_hist, tau_hist, total_backtracks, times, i, be.solution(),
                       objective_hist, iterate_hist, function_hist)
-    res.speculation = spec_stats if speculate else None
+    res.speculation = spec_stats if (speculate or spec_accel) else None
     return res
 
 

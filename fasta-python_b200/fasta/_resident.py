@@ -81,7 +81,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     best.copy_(xa)                                          # stays the answer if no iterate ever improves (nan quality)
     ga, gb = be.G[be.gc], be.G[(be.gc + 1) % 3]
     alpha_d = f64(max_iters) if accelerate else None
-    fista = [be.XA[be.ac], be.XA[1 - be.ac], be.ZA[be.ac], be.ZA[1 - be.ac], alpha_d] if accelerate else [None] * 5
+    fista = [be.XA[be.ac], be.XA[(be.ac + 1) % 3], be.ZA[be.ac], be.ZA[(be.ac + 1) % 3], alpha_d] if accelerate else [None] * 5
     t_launch = time()
     _cabi.check(lib.fb200_resident_fbs(
         be.drv.A.data_ptr(), be.drv.lda, be.drv.M, be.drv.N, be.loss.b.data_ptr(), be.loss.tag, pen.tag, mu, lo, hi,

@@ -256,12 +256,46 @@ class CpuSpeculatingBackend(CpuFusedBackend):
         self.cfg = (bool(backtrack), max_backtracks, window, stop_rule_id, tolerance)
         self.dev = dict(skip=False, it=0, maxres=-np.inf, g0sq=np.float64(g0_sq), f=[np.float64(f0)])
 
+    _ROT = ("x0", "g0", "x1", "g1", "xa0", "za0", "xa1", "za1", "_ahead")
+
     def rotation(self):
-        return self.x0, self.g0, self.x1, self.g1, self._ahead
+        return tuple(getattr(self, k, None) for k in self._ROT)
 
     def restore(self, state):
-        self.x0, self.g0, self.x1, self.g1, self._ahead = state
+        for k, v in zip(self._ROT, state):
+            setattr(self, k, v)
         self.dropped += 1
+
+    # ---- FISTA: queue / collect with the extrapolation weight passed by value (FusedBackend._queue_accel) ----------
+    @property
+    def use_sweep_accel(self):
+        return self.accelerate
+
+    accel_speculate_ok = True
+
+    @staticmethod
+    def accel_weight(alpha_prev):
+        alpha1 = (1 + np.sqrt(1 + 4 * alpha_prev ** 2)) / 2
+        return (alpha_prev - 1) / alpha1
+
+    def _queue_accel(self, tau, c):
+        self.queued += 1
+        t = CpuFusedBackend.trial(self, tau)
+        e = CpuFusedBackend.extrapolate(self, c)
+        g = CpuFusedBackend.gradient(self, tau, False)
+        return "dense", (t, e, g), c
+
+    def _collect_accel(self, handle):
+        t, e, g = handle[1]
+        t.extrap, t.c = e, handle[2]
+        self._spec = g
+        return t
+
+    def trial_accel(self, tau, alpha_prev, restart):
+        t = self._collect_accel(self._queue_accel(tau, self.accel_weight(alpha_prev)))
+        if restart and t.restart > 1E-30 and t.c != 0.0:
+            t = self._collect_accel(self._queue_accel(tau, 0.0))
+        return t
 
     def _queue_trial(self, tau, bt=0, host=(0, -np.inf, 0.0)):
         """Eager: the trial's kernels and fb200_trial_decide, with the device-side state in self.dev."""
@@ -319,7 +353,7 @@ class CpuSpeculatingBackend(CpuFusedBackend):
         return self._collect_trial(self._queue_trial(tau, bt, host))
 
     def gradient(self, tau, adaptive):
-        if not hasattr(self, "dev"):
+        if self._spec is None:
             return CpuFusedBackend.gradient(self, tau, adaptive)
         g, self._spec = self._spec, None
         return g

@@ -74,6 +74,7 @@ def test_host_driven_loop_matches_golden_on_small_problems(case, mode, monkeypat
     res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
     assert not res.resident and res.single_pass
     assert_trajectory(res, gold, label=f"host-loop/{case}/{mode}")
+    assert res.speculation is not None and res.speculation["speculated"] > 0 and res.speculation["mismatched"] == 0
 
 
 @pytest.mark.parametrize("case,mode", [cm for cm in golden_cases(prefixes=("lasso_200x1000_k50", "logistic", "lasso_4000", "tv_64", "nnls"))

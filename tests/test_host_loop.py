@@ -50,6 +50,32 @@ def test_speculative_run_ahead_matches_golden(case, mode):
     assert np.array_equal(res2.solution, ref2.solution) and np.array_equal(res2.stepsizes, ref2.stepsizes)
 
 
+@pytest.mark.parametrize("case", sorted({c for c, m in CASES if m == "accelerated"}))
+def test_speculative_fista_trials_match_golden(case):
+    """Accelerated mode on a fused back-end: the next FISTA trial is queued (step size and no-restart extrapolation
+    weight by value) before this trial's sums are collected; dropped when this trial restarts or is rejected."""
+    gold = load_golden(case, "accelerated")
+    p = problems.build(case, int(gold["seed"]))
+    be = backend_for(p, True, speculate=True)
+    be.load()
+    res = _loop.run(be, p.x0.shape, **gold["opts"])
+    assert_trajectory(res, gold, label=f"speculative-fista/{case}")
+    assert res.speculation["speculated"] >= res.iteration_count - 1 and be.queued >= res.iteration_count
+    # restart=False and a run that restarts often (short horizon, larger step) against the plain protocol
+    for kw in (dict(restart=False, max_iters=60), dict(max_iters=80, L=1.0, tau0=3.0 * res.stepsizes[0])):
+        outs = []
+        for spec in (True, False):
+            b2 = backend_for(p, True, speculate=spec)
+            b2.load()
+            np.random.seed(3)
+            outs.append(_loop.run(b2, p.x0.shape, **dict(gold["opts"], **kw)))
+        a, b = outs
+        assert (a.iteration_count, a.backtracks) == (b.iteration_count, b.backtracks)
+        n = a.iteration_count
+        assert np.array_equal(a.residuals[:n], b.residuals[:n]) and np.array_equal(a.solution, b.solution)
+        assert np.array_equal(a.objectives[:n + 1], b.objectives[:n + 1])
+
+
 def test_speculative_run_ahead_corner_cases():
     """User stop rule (the device cannot evaluate it: rule id -1), a window too long for the device's ring (speculation
     off), backtracking disabled, max_iters = 1 and a tolerance that stops at once."""
