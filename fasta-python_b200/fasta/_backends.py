@@ -365,8 +365,6 @@ class FusedBackend:
         self.use_sweep_accel = (self.accelerate and bool(getattr(driver, "sweep_ok", False))
                                 and hasattr(driver, "sweep_accel") and loss.tag != S.LOSS_NONE
                                 and os.environ.get("FASTA_B200_SWEEP_ACCEL", "1") != "0")
-        self.accel_speculate_ok = ((self.use_tv_accel or self.use_sweep_accel)
-                                   and os.environ.get("FASTA_B200_SPECULATE", "1") != "0")
         # Lipschitz prologue: one probe pass instead of two when the gradient of the loss is affine (see lipschitz_push)
         self.affine_probe = (loss.tag == S.LOSS_LEAST_SQUARES
                              and os.environ.get("FASTA_B200_AFFINE_PROBE", "1") != "0")
@@ -389,6 +387,9 @@ class FusedBackend:
         self.use_tv_accel = (self.accelerate and isinstance(driver, TVDriver) and driver.fused_step_ok
                              and driver.fista_fused_ok and penalty.tag == S.PROX_TV_BALL
                              and loss.tag in (S.LOSS_LEAST_SQUARES, S.LOSS_LOGISTIC))
+        # FISTA trials can be queued ahead of the collect (see _queue_accel and _loop.run)
+        self.accel_speculate_ok = ((self.use_tv_accel or self.use_sweep_accel)
+                                   and os.environ.get("FASTA_B200_SPECULATE", "1") != "0")
 
     # -- helpers --------------------------------------------------------------------------------
     def _st(self):

@@ -48,3 +48,28 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("# oracle", ""), f"{fn} mentions the oracle"
+
+
+def test_backend_constructors_assign_before_use():
+    """Static check (the GPU back-ends cannot be constructed without a device): no attribute of `self` is read in an
+    __init__ of fasta/_backends.py before it has been assigned there."""
+    import ast
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fasta-python_b200", "fasta", "_backends.py")
+    tree = ast.parse(open(path).read())
+    for cls in (n for n in tree.body if isinstance(n, ast.ClassDef)):
+        inits = [f for f in cls.body if isinstance(f, ast.FunctionDef) and f.name == "__init__"]
+        if not inits:
+            continue
+        names = {f.name for f in cls.body if isinstance(f, ast.FunctionDef)}
+        names |= {t.id for n in cls.body if isinstance(n, ast.Assign) for t in n.targets if isinstance(t, ast.Name)}
+        assigned = set()
+        for stmt in inits[0].body:
+            for n in ast.walk(stmt):
+                if isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == "self" \\
+                        and isinstance(n.ctx, ast.Load):
+                    assert n.attr in assigned or n.attr in names, f"{cls.name}.__init__ reads self.{n.attr} (line {n.lineno}) before assigning it"
+            for n in ast.walk(stmt):
+                if isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == "self" \\
+                        and isinstance(n.ctx, ast.Store):
+                    assigned.add(n.attr)
