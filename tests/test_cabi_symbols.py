@@ -66,10 +66,10 @@ def test_backend_constructors_assign_before_use():
         assigned = set()
         for stmt in inits[0].body:
             for n in ast.walk(stmt):
-                if isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == "self" \\
-                        and isinstance(n.ctx, ast.Load):
+                if (isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == "self"
+                        and isinstance(n.ctx, ast.Load)):
                     assert n.attr in assigned or n.attr in names, f"{cls.name}.__init__ reads self.{n.attr} (line {n.lineno}) before assigning it"
             for n in ast.walk(stmt):
-                if isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == "self" \\
-                        and isinstance(n.ctx, ast.Store):
+                if (isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == "self"
+                        and isinstance(n.ctx, ast.Store)):
                     assigned.add(n.attr)
