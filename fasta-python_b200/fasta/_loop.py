@@ -17,6 +17,17 @@ device->host sync:
     keep_best()              best <- x1                                               ref :298-300
     iterate()                current x1 in the caller's array type                    ref :292,296
     solution()               best iterate in the caller's array type                  ref :317
+
+Optional protocols of the fused back-ends, used when present (see ``run``):
+
+    lipschitz_push / lipschitz_finish, start_async     pipelined prologue
+    trial_accel(tau, alpha_prev, restart)              FISTA trial incl. extrapolation and gradient, one collect
+    trial_launch / trial_finish                        next trial queued right after the decision (run-ahead)
+    speculate_begin, _queue_trial(tau | None, bt, host_state), _collect_trial, rotation / restore
+                                                       next trial queued BEFORE this trial's sums are read: the device
+                                                       repeats the decisions (fb200_trial_decide), tau=None = "use the
+                                                       step size left on the device, return at once if told to skip"
+    _queue_accel(tau, c), _collect_accel, accel_weight the same for FISTA trials, step size and weight by value
 """
 
 import os
