@@ -16,7 +16,7 @@ import torch.multiprocessing as mp
 from conftest import PKG, ROOT
 
 
-def _worker(rank, world, port, case, mode, q):
+def _worker(rank, world, port, case, mode, q, speculate=False):
     for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -38,7 +38,7 @@ def _worker(rank, world, port, case, mode, q):
         rows = row_slice(p.A.shape[0], rank, world)
         local = problems.Problem(p.kind, p.loss, p.penalty, p.mu, p.x0, A=p.A[rows], b=p.b[rows])
         drv = ShardedDriver(CpuDenseDriver(local.A))
-        be = backend_for(local, gold["opts"]["accelerate"], driver=drv)
+        be = backend_for(local, gold["opts"]["accelerate"], driver=drv, speculate=speculate)
         be.load()
         res = _loop.run(be, p.x0.shape, **gold["opts"])
         n = res.iteration_count
@@ -47,15 +47,18 @@ def _worker(rank, world, port, case, mode, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("speculate", [False, True])
 @pytest.mark.parametrize("case,mode", [("lasso_200x1000_k50", "adaptive"), ("lasso_200x1000_k10", "accelerated"),
                                        ("logistic_1000x2000", "adaptive")])
-def test_row_sharded_two_ranks_match_golden(case, mode):
+def test_row_sharded_two_ranks_match_golden(case, mode, speculate):
+    """speculate=True drives the speculative run-ahead protocol of the loop (trials queued ahead, dropped on a
+    rejection / restart): both ranks must take the same decisions, or the collectives of the two would not pair up."""
     from helpers import load_golden
     gold = load_golden(case, mode)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, mode, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if speculate else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, mode, q, speculate)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
