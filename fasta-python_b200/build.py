@@ -56,17 +56,23 @@ def build(force=False, verbose=False):
     headers.append(os.path.abspath(__file__))
     nvcc = _nvcc()
     objs = []
-    rebuilt = False
+    jobs = []
     for src, extra in UNITS:
         s = os.path.join(CSRC, src)
         o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, "-c", s, "-o", o] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else [])
+            jobs.append([nvcc, "-c", s, "-o", o] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []))
+    rebuilt = bool(jobs)
+    if jobs:                                    # translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             if verbose:
                 print(" ".join(cmd))
-            subprocess.run(cmd, check=True)
-            rebuilt = True
+            return subprocess.run(cmd, check=True)
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1, 8)) as pool:
+            list(pool.map(run, jobs))
     if rebuilt or force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ARCH + ["-Xcompiler", "-fPIC", "-cudart", "static"]
         if verbose:
