@@ -138,10 +138,61 @@ def stopping_kats(ref):
     return dict(table=np.array(rows))
 
 
+# Option semantics of fasta() itself (reference __init__.py:42-53), beyond the three harness modes: stop rules, no
+# backtracking, user L / tau0, window / shrink overrides, restart off, adaptive + accelerated together, hooks.
+OPTION_SETS = [
+    dict(stop_rule="residual", tolerance=1e-3),
+    dict(stop_rule="norm_residual", tolerance=1e-4),
+    dict(stop_rule="ratio_residual", tolerance=1e-4),
+    dict(backtrack=False, adaptive=False, max_iters=50),
+    dict(L=1.3, tau0=0.11, max_iters=40, evaluate_objective=False),
+    dict(window=3, stepsize_shrink=0.5, max_iters=60),
+    dict(window=70, max_iters=90),
+    dict(accelerate=True, adaptive=False, restart=False, max_iters=120),
+    dict(accelerate=True, adaptive=True, max_iters=80),
+    dict(accelerate=True, adaptive=False, max_iters=200),
+    dict(record_iterates=True, func="max_abs", max_iters=12),
+    dict(max_iters=1),
+    dict(tolerance=1e9),
+]
+OPTION_CASE, OPTION_SEED = "lasso_200x1000_k50", 5
+
+
+def run_options(ref):
+    """One npz with the live reference's answer for every option set of OPTION_SETS on OPTION_CASE."""
+    out = dict(case=OPTION_CASE, seed=OPTION_SEED, count=len(OPTION_SETS), numpy_version=np.__version__)
+    for k, o in enumerate(OPTION_SETS):
+        p = problems.build(OPTION_CASE, 0)
+        apply, adjoint, vshape, wshape = problems.numpy_operator(p)
+        A = ref.linalg.LinearMap(apply, adjoint, vshape, wshape)
+        f, gradf, g, proxg = problems.numpy_callables(p)
+        opts = dict(verbose=False, evaluate_objective=True)
+        opts.update(o)
+        if "stop_rule" in opts:
+            opts["stop_rule"] = getattr(ref.stopping, opts["stop_rule"])
+        if opts.get("func") == "max_abs":
+            opts["func"] = lambda x: np.abs(x).max()
+        np.random.seed(OPTION_SEED)
+        res = ref.fasta(A, f, gradf, g, proxg, p.x0, **opts)
+        n = res.iteration_count
+        out[f"opts{k}"] = repr(o)
+        out[f"n{k}"], out[f"bt{k}"] = n, res.backtracks
+        out[f"residuals{k}"], out[f"norm_residuals{k}"], out[f"stepsizes{k}"] = res.residuals, res.norm_residuals, res.stepsizes
+        out[f"solution{k}"] = res.solution
+        if res.objectives is not None:
+            out[f"objectives{k}"] = res.objectives
+        if res.iterates is not None:
+            out[f"iterates{k}"] = res.iterates
+        if res.function_hist is not None:
+            out[f"function_hist{k}"] = res.function_hist
+        print(f"options {k:2d} {repr(o):90s} iters={n:4d} bt={res.backtracks:3d}")
+    return out
+
+
 def main(argv):
     ref = ref_loader.load()
     os.makedirs(GOLDEN, exist_ok=True)
-    cases = argv or (list(problems.CASES) + list(examples_extra.CASES))
+    cases = [] if argv == ["options"] else (argv or (list(problems.CASES) + list(examples_extra.CASES)))
     for case in cases:
         for mode in problems.MODES:
             rec = run_extra(ref, case, mode) if case in examples_extra.CASES else run_case(ref, case, mode)
@@ -154,6 +205,8 @@ def main(argv):
         np.savez_compressed(os.path.join(GOLDEN, "kat_stopping.npz"), **stopping_kats(ref))
         np.savez_compressed(os.path.join(GOLDEN, "kat_row_prox.npz"), **row_prox_kats())
         print("wrote prox / stopping known-answer vectors")
+    if not argv or argv == ["options"]:
+        np.savez_compressed(os.path.join(GOLDEN, "kat_options.npz"), **run_options(ref))
 
 
 if __name__ == "__main__":

@@ -282,7 +282,7 @@ class CpuSpeculatingBackend(CpuFusedBackend):
         self.queued += 1
         t = CpuFusedBackend.trial(self, tau)
         e = CpuFusedBackend.extrapolate(self, c)
-        g = CpuFusedBackend.gradient(self, tau, False)
+        g = CpuFusedBackend.gradient(self, tau, True)       # the fused trial always forms the BB sums (bb = 2)
         return "dense", (t, e, g), c
 
     def _collect_accel(self, handle):

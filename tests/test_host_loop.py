@@ -145,3 +145,39 @@ def test_options_semantics():
     assert np.array_equal(res.iterates[0], p.x0)
     assert res.function_hist.shape == (4,) and res.function_hist[0] == 0.0
     assert res.function_hist[3] == float(np.abs(res.iterates[3]).sum())
+
+
+@pytest.mark.parametrize("speculate", [False, True])
+def test_host_loop_option_semantics_match_reference(speculate, golden_dir):
+    """The product's host loop (plain and speculative protocols of the test double) against the LIVE reference's answer
+    for every option set of tests/golden/kat_options.npz (stop rules, backtrack off, user L / tau0, window / shrink
+    overrides incl. a window too long for the device ring, restart off, adaptive + accelerated, hooks, immediate stop)."""
+    import ast
+    import fasta
+    with np.load(f"{golden_dir}/kat_options.npz", allow_pickle=False) as z:
+        g = {k: z[k] for k in z.files}
+    for k in range(int(g["count"])):
+        o = ast.literal_eval(str(g[f"opts{k}"]))
+        p = problems.build(str(g["case"]), 0)
+        opts = dict(verbose=False, evaluate_objective=True)
+        opts.update(o)
+        if "stop_rule" in opts:
+            opts["stop_rule"] = getattr(fasta.stopping, opts["stop_rule"])
+        if opts.get("func") == "max_abs":
+            opts["func"] = lambda x: np.abs(x).max()
+        be = backend_for(p, bool(opts.get("accelerate", False)), speculate=speculate)
+        be.load()
+        np.random.seed(int(g["seed"]))
+        res = _loop.run(be, p.x0.shape, **opts)
+        n = int(g[f"n{k}"])
+        assert (res.iteration_count, res.backtracks) == (n, int(g[f"bt{k}"])), o
+        assert np.linalg.norm(res.solution - g[f"solution{k}"]) <= 1e-9 * np.linalg.norm(g[f"solution{k}"]), o
+        assert np.all(res.residuals[n:] == 0) and res.residuals.shape == g[f"residuals{k}"].shape
+        np.testing.assert_allclose(res.stepsizes[:n], g[f"stepsizes{k}"][:n], rtol=1e-6)
+        if f"objectives{k}" in g:
+            np.testing.assert_allclose(res.objectives[:n + 1], g[f"objectives{k}"][:n + 1], rtol=1e-10)
+        else:
+            assert res.objectives is None
+        if f"iterates{k}" in g:
+            np.testing.assert_allclose(res.iterates, g[f"iterates{k}"], rtol=0, atol=1e-9 * np.abs(g[f"iterates{k}"]).max())
+            np.testing.assert_allclose(res.function_hist, g[f"function_hist{k}"], rtol=1e-9)

@@ -80,3 +80,42 @@ def test_oracle_matches_reference_on_extra_examples(case, mode):
     else:
         np.testing.assert_allclose(res.solution, gold["solution"], rtol=0, atol=1e-9 * np.abs(gold["solution"]).max())
         np.testing.assert_allclose(res.objectives[:n + 1], gold["objectives"], rtol=1e-10)
+
+
+def _option_sets(golden_dir):
+    import ast
+    with np.load(f"{golden_dir}/kat_options.npz", allow_pickle=False) as z:
+        g = {k: z[k] for k in z.files}
+    sets = []
+    for k in range(int(g["count"])):
+        sets.append((k, ast.literal_eval(str(g[f"opts{k}"]))))
+    return g, sets
+
+
+def test_oracle_option_semantics_match_reference_bitwise(golden_dir):
+    """Stop rules, backtrack off, user L / tau0, window / shrink overrides, restart off, adaptive + accelerated, hooks,
+    max_iters = 1, immediate stop: the oracle against the LIVE reference's answer for every option set
+    (oracle/make_golden.py OPTION_SETS -> tests/golden/kat_options.npz)."""
+    g, sets = _option_sets(golden_dir)
+    same_build = str(g["numpy_version"]) == np.__version__
+    for k, o in sets:
+        p = problems.build(str(g["case"]), 0)
+        f, gradf, gg, proxg = problems.numpy_callables(p)
+        opts = dict(evaluate_objective=True)
+        opts.update(o)
+        if "stop_rule" in opts:
+            opts["stop_rule"] = getattr(fasta_oracle, "stop_" + opts["stop_rule"])
+        if opts.get("func") == "max_abs":
+            opts["func"] = lambda x: np.abs(x).max()
+        np.random.seed(int(g["seed"]))
+        res = fasta_oracle.solve(lambda x: p.A @ x, lambda y: p.A.T @ y, f, gradf, gg, proxg, p.x0, **opts)
+        assert (res.iteration_count, res.backtracks) == (int(g[f"n{k}"]), int(g[f"bt{k}"])), o
+        for name in ("residuals", "norm_residuals", "stepsizes", "solution", "objectives", "iterates", "function_hist"):
+            want = g.get(f"{name}{k}")
+            got = getattr(res, name)
+            if want is None:
+                assert got is None, (o, name)
+            elif same_build:
+                assert np.array_equal(got, want), (o, name)          # full-length arrays, zero padding included
+            else:
+                np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12)
