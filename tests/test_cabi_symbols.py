@@ -73,3 +73,46 @@ def test_backend_constructors_assign_before_use():
                 if (isinstance(n, ast.Attribute) and isinstance(n.value, ast.Name) and n.value.id == "self"
                         and isinstance(n.ctx, ast.Store)):
                     assigned.add(n.attr)
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/fasta_b200.h against its ctypes signature in fasta/_cabi.py: same number of
+    parameters, same kind (pointer / double / int / int64 / size_t) at every position, same return kind -- an ABI drift
+    between the two would otherwise only show up as garbage arguments on the GPU.  Also: the enum constants mirrored
+    in _cabi.py carry the header's values."""
+    from fasta import _cabi
+    text = open(os.path.join(ROOT, "include", "fasta_b200.h")).read()
+    nocomment = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+
+    def kind(ctype_decl):
+        d = ctype_decl.strip()
+        if "*" in d:
+            return "ptr"
+        base = re.sub(r"\b(const|unsigned)\b", "", d).split()
+        base = base[0] if base else ""
+        return {"double": "double", "int": "int", "int64_t": "i64", "size_t": "size", "void": "void"}[base]
+
+    of_ctype = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_double: "double", ctypes.c_int: "int",
+                ctypes.c_int64: "i64", ctypes.c_size_t: "size"}
+    protos = re.findall(r"(?m)^\s*((?:const\s+)?[A-Za-z_0-9]+\s*\**)\s*(fb200_[a-zA-Z0-9_]+)\s*\(([^;{]*?)\)\s*;", nocomment)
+    assert len(protos) >= 40
+    seen = set()
+    for ret, name, params in protos:
+        seen.add(name)
+        restype, argtypes = _cabi.SIGNATURES[name]
+        plist = [p for p in (q.strip() for q in params.replace("\n", " ").split(",")) if p and p != "void"]
+        kinds = [kind(re.sub(r"\b[A-Za-z_0-9]+\s*(\[[^\]]*\])?$", "", p) if not p.endswith("*") else p) for p in plist]
+        assert len(kinds) == len(argtypes), f"{name}: header has {len(kinds)} parameters, _cabi.py {len(argtypes)}"
+        kind_of = lambda a: of_ctype.get(a, "ptr" if hasattr(a, "_type_") and not isinstance(a._type_, str) else None)
+        for i, (k, a) in enumerate(zip(kinds, argtypes)):
+            assert kind_of(a) == k, f"{name}: parameter {i} is {k} in the header, {kind_of(a)} in _cabi.py"
+        assert kind_of(restype) == kind(ret), f"{name}: return type"
+    assert seen == set(_cabi.SIGNATURES)
+    # enum mirrors
+    for cname, pyname in (("FB200_S_F", "S_F"), ("FB200_S_RESTART", "S_RESTART"), ("FB200_S_G1_SQ", "S_G1_SQ"),
+                          ("FB200_S_AUX3", "S_AUX3"), ("FB200_S_TAU", "S_TAU"), ("FB200_S_TAU_USED", "S_TAU_USED"),
+                          ("FB200_S_SKIP", "S_SKIP"), ("FB200_S_SKIPPED", "S_SKIPPED"), ("FB200_S_FRING", "S_FRING")):
+        m = re.search(rf"\b{cname}\s*=\s*(\d+)", nocomment)
+        assert m and int(m.group(1)) == getattr(_cabi, pyname), cname
+    assert int(re.search(r"#define\s+FB200_NSCAL\s+(\d+)", text).group(1)) == _cabi.NSCAL
+    assert int(re.search(r"#define\s+FB200_FRING\s+(\d+)", text).group(1)) == _cabi.FRING
