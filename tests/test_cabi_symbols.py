@@ -116,3 +116,30 @@ def test_ctypes_signatures_match_the_header_prototypes():
         assert m and int(m.group(1)) == getattr(_cabi, pyname), cname
     assert int(re.search(r"#define\s+FB200_NSCAL\s+(\d+)", text).group(1)) == _cabi.NSCAL
     assert int(re.search(r"#define\s+FB200_FRING\s+(\d+)", text).group(1)) == _cabi.FRING
+
+
+def test_call_sites_pass_the_declared_number_of_arguments():
+    """Static check of every `....fb200_xxx(...)` call in the product package: the number of positional arguments is
+    the number of parameters of the ctypes signature (call sites with starred arguments are counted as 'at least')."""
+    import ast
+    from fasta import _cabi
+    pkg = os.path.join(ROOT, "fasta-python_b200", "fasta")
+    checked = 0
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("fb200_"):
+                name = node.func.attr
+                assert name in _cabi.SIGNATURES, f"{fn}:{node.lineno}: {name} is not declared"
+                want = len(_cabi.SIGNATURES[name][1])
+                starred = [a for a in node.args if isinstance(a, ast.Starred)]
+                plain = len(node.args) - len(starred)
+                assert not node.keywords, f"{fn}:{node.lineno}: keyword arguments in a C call"
+                if starred:
+                    assert plain <= want, f"{fn}:{node.lineno}: {name} gets more than {want} arguments"
+                else:
+                    assert plain == want, f"{fn}:{node.lineno}: {name} gets {plain} arguments, the C function takes {want}"
+                checked += 1
+    assert checked >= 60
