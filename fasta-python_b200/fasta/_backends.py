@@ -376,7 +376,7 @@ class FusedBackend:
         # TV: one fused kernel per half-iteration (see TVDriver.step_forward)
         self.use_tv_fused = ((not self.accelerate) and isinstance(driver, TVDriver) and driver.fused_step_ok
                              and penalty.tag == S.PROX_TV_BALL and loss.tag != S.LOSS_NONE)
-        # Speculative run-ahead: the step size of the next trial stays on the device (fb200_stepsize_next), so the next
+        # Speculative run-ahead: the step size of the next trial stays on the device (fb200_trial_decide), so the next
         # iteration's trial is queued BEFORE the host has seen this trial's sums; see _loop.run
         tv_iter = self.use_tv_fused and driver.iter_fused_ok
         elementwise = penalty.tag in (S.PROX_NONNEG, S.PROX_BOX, S.PROX_IDENTITY) or \
@@ -538,7 +538,7 @@ class FusedBackend:
 
     def _queue_trial(self, tau, bt=0, host=(0, -np.inf, 0.0)):
         """Queue one trial (reference :181-188, plus the speculative gradient of the single-pass kernels).  tau=None:
-        the kernels read the step size fb200_stepsize_next left in scal[S_TAU].  Returns a handle for _collect_trial."""
+        the kernels read the step size fb200_trial_decide left in scal[S_TAU].  Returns a handle for _collect_trial."""
         x0, g0 = self.X[self.ip], self.G[self.gp]
         x1 = self.XA[self.ac] if self.accelerate else self.X[self.ic]
         z1 = self.ZA[self.ac] if self.accelerate else self.Z

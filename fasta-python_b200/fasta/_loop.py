@@ -145,7 +145,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     run_ahead = hasattr(be, "trial_launch") and not fused_accel and os.environ.get("FASTA_B200_RUN_AHEAD", "1") != "0"
     queued = False
     # Speculative run-ahead (back-ends with speculate_ok): the Barzilai-Borwein step size of a trial is formed on the
-    # device right behind it (fb200_stepsize_next, the algebra of :253-270), so the NEXT iteration's trial -- which in
+    # device right behind it (fb200_trial_decide, the algebra of :253-270), so the NEXT iteration's trial -- which in
     # the common case differs from this one only in the step size and the buffer rotation -- is queued before the host
     # has read this trial's sums.  The device never waits for the host.  If the line search rejects the trial, the
     # speculated one is dropped (it only wrote scratch buffers) and the backtracking runs as usual.
