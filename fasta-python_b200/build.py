@@ -32,6 +32,7 @@ UNITS = [
     ("batched_vector.cu", ["-fmad=false"]),
     ("resident_loop.cu", ["-fmad=false"]),
     ("jacobi_svd.cu", []),
+    ("legacy_rng.cu", ["-fmad=false"]),
 ]
 
 

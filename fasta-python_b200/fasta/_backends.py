@@ -313,6 +313,11 @@ class ShardedDriver:
     def sync_probe(self, v):
         self.dist.broadcast(v, src=self._root(), group=self.group)
 
+    def sync_state(self, s):
+        # device-side probes (fasta/_rng.py): every rank continues rank 0's numpy stream -- one 2.5 KB message
+        self.dist.broadcast(s, src=self._root(), group=self.group)
+        self.collectives += 1
+
 
 # =================================================================================================
 # fused back-end
@@ -438,6 +443,12 @@ class FusedBackend:
         dst.copy_(stage, non_blocking=True)
         if hasattr(self.drv, "sync_probe"):
             self.drv.sync_probe(dst)
+        self._probe_queue(k)
+
+    def _probe_queue(self, k):
+        """Probe k is in XH (k = 0) / DX (k = 1): queue its contraction pair (see lipschitz_push)."""
+        t = self.t
+        dst = self.XH if k == 0 else self.DX
         if self.affine_probe:
             if k == 0:
                 return
@@ -458,6 +469,30 @@ class FusedBackend:
         else:
             self.drv.forward(dst, self.loss.tag, self.loss.b, self.Z, self.R, self.ws)
             self.drv.adjoint(self.R, d, 0, None, None, None, 0.0, self.ws)
+
+    # -- the same prologue with the probes drawn ON THE DEVICE from numpy's global stream (fasta/_rng.py): no host
+    # draw, no upload, and on a row-sharded map one 2.5 KB state broadcast instead of two N-vector broadcasts
+    def lipschitz_device_ok(self):
+        from . import _rng
+        return self.XH.is_cuda and _rng.usable(self.XH.device, self.n)
+
+    def lipschitz_device(self):
+        """Returns (|dgrad|, |dpoint|) like lipschitz_finish(), or None when the device draw has to be repeated on the
+        host (numpy's generator is then untouched)."""
+        from . import _rng
+        gen = getattr(self, "_randn", None)
+        if gen is None:
+            gen = self._randn = _rng.DeviceRandn(self.XH.device)
+        gen.begin(sync_fn=getattr(self.drv, "sync_state", None))
+        for k, dst in enumerate((self.XH, self.DX)):
+            self.launches += gen.draw(dst)
+            if k == 1:
+                gen.finish_async()               # the end state travels back while the probe sweeps run
+            self._probe_queue(k)
+        out = self.lipschitz_finish()
+        if gen.finish() is None:
+            return None
+        return out
 
     def lipschitz_finish(self):
         a, b = self.XH, self.DX

@@ -82,6 +82,8 @@ SIGNATURES = {
     "fb200_diff_nrm2sq": (_int, [_p, _p, _i64, _p, _p, _p]),
     "fb200_asum": (_int, [_p, _i64, _p, _p, _p]),
     "fb200_prox_apply": (_int, [_p, _int, _dbl, _dbl, _i64, _p, _p, _p]),
+    "fb200_randn_scratch_bytes": (_sz, [_i64]),
+    "fb200_randn_legacy": (_int, [_p, _i64, _p, _p, _sz, _p, _p]),
 }
 
 _lib = None

@@ -81,6 +81,28 @@ def _sq(norm_squared):
     return np.sqrt(norm_squared) ** 2
 
 
+def lipschitz_probes(be, x0_shape):
+    """|A^H gradf(A x1) - A^H gradf(A x2)| and |x1 - x2| for two standard-normal probes (ref :102-110).
+
+    The probes are the next 2 N values of numpy's global legacy stream, x1 first, exactly as the reference's two
+    ``np.random.randn(*x0.shape)`` calls -- either drawn on the device (fused back-ends, ``fasta/_rng.py``: the kernels
+    continue the very stream and hand numpy its end state back) or on the host and uploaded."""
+    if hasattr(be, "lipschitz_push"):
+        # pipelined prologue: the device starts on z = A x0 / gradf1 (ref :135-139, independent of the probes)
+        be.start_async()
+        if be.lipschitz_device_ok():
+            out = be.lipschitz_device()
+            if out is not None:
+                return out
+        # ... and on each probe's sweep while the host draws the next probe
+        be.lipschitz_push(0, np.random.randn(*x0_shape))
+        be.lipschitz_push(1, np.random.randn(*x0_shape))
+        return be.lipschitz_finish()
+    v1 = np.random.randn(*x0_shape)                         # ref :102-103
+    v2 = np.random.randn(*x0_shape)
+    return be.lipschitz(v1, v2)
+
+
 def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iters=1000, tolerance=1e-5,
         stop_rule=stopping.hybrid_residual, L=None, tau0=None, backtrack=True, stepsize_shrink=None,
         window=10, max_backtracks=20, restart=True, evaluate_objective=False, record_iterates=False,
@@ -90,18 +112,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
         stepsize_shrink = 0.2 if adaptive else 0.5
 
     if not L or not tau0:                                   # ref :100 -- both are needed to skip
-        # same two draws from numpy's global legacy RNG, in the same order (ref :102-103)
-        if hasattr(be, "lipschitz_push"):
-            # pipelined prologue: the device starts on z = A x0 / gradf1 (ref :135-139, independent of the probes)
-            # and on each probe's sweep while the host draws the next probe
-            be.start_async()
-            be.lipschitz_push(0, np.random.randn(*x0_shape))
-            be.lipschitz_push(1, np.random.randn(*x0_shape))
-            dgrad, dpoint = be.lipschitz_finish()
-        else:
-            v1 = np.random.randn(*x0_shape)
-            v2 = np.random.randn(*x0_shape)
-            dgrad, dpoint = be.lipschitz(v1, v2)
+        dgrad, dpoint = lipschitz_probes(be, x0_shape)
         L = dgrad / dpoint                                  # ref :110
         tau0 = (2 / L) / 10                                 # ref :113
     if not tau0:                                            # ref :115-116 (unreachable, kept)

@@ -13,7 +13,7 @@ from time import time
 import numpy as np
 
 from . import _cabi, _device, stopping
-from ._loop import Convergence
+from ._loop import Convergence, lipschitz_probes
 
 _RULES = {stopping.residual: 0, stopping.norm_residual: 1, stopping.ratio_residual: 2, stopping.hybrid_residual: 3}
 _PROX_OK = (_cabi.PROX_SHRINK, _cabi.PROX_NONNEG, _cabi.PROX_BOX, _cabi.PROX_IDENTITY)
@@ -48,10 +48,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     if stepsize_shrink is None and backtrack:               # ref :92-97
         stepsize_shrink = 0.2 if adaptive else 0.5
     if not L or not tau0:                                   # ref :100-113, pipelined as in _loop.run
-        be.start_async()
-        be.lipschitz_push(0, np.random.randn(*x0_shape))
-        be.lipschitz_push(1, np.random.randn(*x0_shape))
-        dgrad, dpoint = be.lipschitz_finish()
+        dgrad, dpoint = lipschitz_probes(be, x0_shape)
         L = dgrad / dpoint
         tau0 = (2 / L) / 10
     if not tau0:

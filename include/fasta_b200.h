@@ -340,6 +340,19 @@ int fb200_dot(const double* a, const double* b, int64_t n, double* out, void* ws
 int fb200_diff_nrm2sq(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream);
 int fb200_asum(const double* a, int64_t n, double* out, void* ws, void* stream);
 
+/* ---- np.random.randn on the device (csrc/legacy_rng.cu) --------------------------------------------------------
+ * Replaces `x1 = np.random.randn(*x0.shape); x2 = np.random.randn(*x0.shape)` (reference fasta/__init__.py:102-103):
+ * continues numpy's legacy MT19937 + polar-method Gaussian stream bit for bit from `state` and returns the state
+ * numpy would be left in, so the host generator can be kept in step with np.random.set_state().
+ *   state      device, 628 32-bit words: key[624], pos, has_gauss, cached gauss (a double at word 626)
+ *   out        device, n doubles
+ *   scratch    device, >= fb200_randn_scratch_bytes(n) bytes, 256-byte aligned
+ *   state_out  device, 632 words: the end state (628 words), status (word 628: 0 ok / 1 too few accepted candidate
+ *              points -- then nothing may be used; probability < 1e-11), tries used (64-bit at word 630) */
+size_t fb200_randn_scratch_bytes(int64_t n);
+int fb200_randn_legacy(const void* state, int64_t n, double* out, void* scratch, size_t scratch_bytes,
+                       void* state_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
