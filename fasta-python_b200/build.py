@@ -27,6 +27,7 @@ UNITS = [
     ("tv_stencil.cu", ["-fmad=false"]),
     ("dense_stream.cu", []),
     ("dense_sweep.cu", []),
+    ("dense_gsweep.cu", []),
     ("batched_gemm.cu", []),
     ("ozaki_gemm.cu", []),
     ("batched_vector.cu", ["-fmad=false"]),

@@ -15,6 +15,8 @@ namespace fb200 {
 //   [0, 256)                       ticket counters for the "last block finalises" reductions
 //   [256, 2048)                    per-cluster loss partials of the single-pass sweep (FPART_MAX doubles)
 //   [2048, 2048 + RED_BYTES)       per-block reduction partials  [MAX_RED_BLOCKS][MAX_RED_K]
+//   [XCHG_OFF, XCHG_OFF + XCHG_BYTES)   exchange rings of the grid sweep (dense_gsweep.cu): [bands][XCHG_RING][slabs] x 16 B,
+//                                  touched by nothing else (its sequence flags must never be overwritten with data)
 //   [DENSE_OFF, ...)               split partials of the dense maps: zp[S][ldz] then gp[S][ldg]
 // ------------------------------------------------------------------------------------------------
 constexpr int    MAX_RED_BLOCKS = 8192;
@@ -22,7 +24,11 @@ constexpr int    MAX_RED_K      = 12;
 constexpr size_t CTR_BYTES      = 2048;
 constexpr int    FPART_MAX      = 160;
 constexpr size_t RED_BYTES      = size_t(MAX_RED_BLOCKS) * MAX_RED_K * sizeof(double);
-constexpr size_t DENSE_OFF      = CTR_BYTES + RED_BYTES;
+constexpr int    GS_XRING       = 32;                  // rows a band's exchange ring holds (> 2 x the deepest stage ring)
+constexpr int    GS_XCTAS       = 160;                 // CTAs (bands x slabs) the exchange area serves
+constexpr size_t XCHG_OFF       = CTR_BYTES + RED_BYTES;
+constexpr size_t XCHG_BYTES     = size_t(GS_XCTAS) * GS_XRING * 16;
+constexpr size_t DENSE_OFF      = XCHG_OFF + XCHG_BYTES;
 constexpr int    MAX_SPLIT      = 32;
 
 constexpr int VEC_THREADS = 256;
@@ -34,11 +40,13 @@ struct Workspace {
     double*   fpart;
     double*   red;
     double*   dense;
+    void*     xchg;
     __host__ explicit Workspace(void* ws)
         : counter(reinterpret_cast<unsigned*>(ws)),
           fpart(reinterpret_cast<double*>(static_cast<char*>(ws) + 256)),
           red(reinterpret_cast<double*>(static_cast<char*>(ws) + CTR_BYTES)),
-          dense(reinterpret_cast<double*>(static_cast<char*>(ws) + DENSE_OFF)) {}
+          dense(reinterpret_cast<double*>(static_cast<char*>(ws) + DENSE_OFF)),
+          xchg(static_cast<char*>(ws) + XCHG_OFF) {}
 };
 
 void set_error(const char* fmt, ...);

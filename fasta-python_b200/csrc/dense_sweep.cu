@@ -340,12 +340,27 @@ static bool sweep_eligible(const double* A, int64_t lda, int64_t M, int64_t N) {
 
 int sweep_max_clusters() { return 160; }
 
+// grid variant (dense_gsweep.cu): all SMs, partial dots exchanged through L2 instead of cluster DSMEM
+bool gsweep_eligible(const double* A, int64_t lda, int64_t M, int64_t N);
+int gsweep_plan(int64_t M, int64_t N, int* plan);
+int gsweep_launch(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss, const double* b,
+                  double* z, double* r, double* g, int bb, const double* x0, const double* xhat, const double* dx,
+                  double tau, double* scal, void* ws, size_t ws_bytes, void* stream, const double* za0,
+                  double* za1, double c);
+
+// FASTA_B200_SWEEP_KERNEL=cluster selects the cluster / DSMEM kernel of this file (the round-1 default)
+static bool use_grid_sweep() {
+    const char* e = getenv("FASTA_B200_SWEEP_KERNEL");
+    return !(e && e[0] == 'c');
+}
+
 }  // namespace fb200
 
 using namespace fb200;
 
 // plan[0..4] = cluster size, clusters co-resident, stages, columns per CTA, double2 per thread
 extern "C" int fb200_sweep_plan(int64_t M, int64_t N, int* plan) {
+    if (use_grid_sweep()) return gsweep_plan(M, N, plan);      // slabs, bands, stages, columns per CTA, double2 per thread
     SweepPlan p = make_sweep_plan(FB200_LOSS_LEAST_SQUARES, M, N);
     if (!p.ok) return 1;
     plan[0] = p.cs; plan[1] = p.ncl; plan[2] = p.nstage; plan[3] = p.nc; plan[4] = p.cpt;
@@ -353,6 +368,10 @@ extern "C" int fb200_sweep_plan(int64_t M, int64_t N, int* plan) {
 }
 
 extern "C" int fb200_sweep_supported(const double* A, int64_t lda, int64_t M, int64_t N) {
+    if (use_grid_sweep()) {
+        int plan[5];
+        return (gsweep_eligible(A, lda, M, N) && gsweep_plan(M, N, plan) == 0) ? plan[0] : 0;
+    }
     if (!sweep_eligible(A, lda, M, N)) return 0;
     SweepPlan p = make_sweep_plan(FB200_LOSS_LEAST_SQUARES, M, N);
     return p.ok ? p.cs : 0;
@@ -363,6 +382,8 @@ static int sweep_launch(const double* A, int64_t lda, int64_t M, int64_t N, cons
                         double* z, double* r, double* g, int bb, const double* x0, const double* xhat, const double* dx,
                         double tau, double* scal, void* ws, size_t ws_bytes, void* stream, const double* za0,
                         double* za1, double c) {
+    if (use_grid_sweep())
+        return gsweep_launch(A, lda, M, N, x, loss, b, z, r, g, bb, x0, xhat, dx, tau, scal, ws, ws_bytes, stream, za0, za1, c);
     if (!sweep_eligible(A, lda, M, N) || reinterpret_cast<uintptr_t>(x) % 16 != 0) {
         set_error("dense_sweep: matrix not eligible (needs 16-byte aligned base and x, even lda and N, N <= %d)", SW_MAXCS * SW_GROUP * 26);
         return 1;
