@@ -1,29 +1,35 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark: dense fp64 lasso solved by FASTA's forward-backward splitting.
+"""bench.py -- FASTA's forward-backward splitting on B200, measured on the configs BASELINE.json names.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Metric (BASELINE.json): lasso FBS iterations/sec (fp64) on config 2, dense lasso M=40000 N=100000
-(32 GB A), row-sharded over the N GPUs of one box (strong scaling: the problem is fixed).
+Workloads (``--workload``; the default is the configuration BASELINE.json's metric is quoted on):
 
-A "step" is ONE full solve to tolerance 1e-5 (adaptive mode, hybrid stop rule, verbose off)
-through the public API ``fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, x0)``.
-  value   = iterations performed in the K timed solves / device time of the K solves, with A, b,
-            x0 already resident in HBM (max over ranks, barrier + synchronize on both sides).
-            The time includes each solve's prologue (Lipschitz estimate + initial gradient = 6
-            passes over A), so it is a lower bound on the in-loop rate (also reported).
-  e2e     = the same metric when every step also uploads A, b, x0 from pinned host memory and
-            downloads the solution (the call a user with host arrays makes).
-  roofline= dominant kernel, timed with CUDA events around every launch DURING the timed solves:
-            the single-pass dense_sweep_kernel (z = A x, loss, g = A^T r in one read of A;
-            algorithmic bytes = the reference's two contractions = 2*M*N*8 per launch, DRAM traffic
-            = M*N*8), or the two-pass dense_stream_kernel (M*N*8 per launch) when the sweep is off.
-  cpu_baseline = the numpy oracle (oracle/fasta_oracle.py, a port of the reference loop; numpy's
-            OpenBLAS dgemv is the same arithmetic the reference runs) on the host cores, on a
-            bounded sample (first iterations of the same problem).
-``--impl reference`` prints the CPU arm alone (rank 0 only under torchrun).
+    lasso_40000x100000        config 2  dense lasso, 32 GB A, rows sharded over the N GPUs (strong scaling)   [default]
+    lasso_8000x20000          its small twin for development boxes
+    lasso_200x1000            config 1  the reference's own CPU-sized example (replicas at N > 1)
+    logistic_100000x20000     config 3  sparse logistic regression, l1 prox, adaptive BB, rows sharded
+    tv_4096                   config 4  total-variation denoising 4096^2, matrix-free div / grad stencils (replicas)
+    batched_256x20000x50000   config 5  256-lambda lasso path as tensor-core GEMM iterations, columns sharded
+
+A "step" is ONE full solve through the public API (``fasta.fasta`` / ``fasta.batched.lasso_path``): Lipschitz prologue
++ iterations to tolerance 1e-5 (config 1: a batch of 100 such solves).  Every line carries the same keys:
+  value    = units (iterations; column-iterations for config 5) of the K timed steps / device time, inputs resident
+             in HBM, barrier + synchronize on both sides, max over ranks.  Includes each solve's prologue, so it is a
+             lower bound on the in-loop rate (``iters_per_sec_in_loop``, the reference's own definition,
+             examples/__init__.py:59-60).
+  e2e      = the same metric when every step also uploads its inputs from pinned host memory and downloads the
+             solution (the call a user with host arrays makes); ``pcie_ceiling`` is what the copies alone allow.
+  roofline = the dominant kernel, timed with CUDA events around every launch DURING the timed steps.  ``frac`` is the
+             DRAM-side fraction (bytes the kernel must move from HBM / time / measured copy peak);
+             ``frac_algorithmic`` uses SURVEY 8d's accounting (the reference's two contractions per iteration), which
+             exceeds 1 for the single-pass sweep because it reads A once for both.
+  cpu_baseline = the UNMODIFIED reference (baseline/_ref, pip-installed from /root/reference; else the oracle port)
+             on the host cores on the same inputs, all BLAS threads, with the parity of OUR result against it:
+             iteration / backtrack counts, solution and objective-history relative errors (north_star bar 1e-9 / 1e-10).
+``--impl reference`` prints the CPU arm alone (rank 0 only under torchrun; BLAS threads restored to all cores).
 """
 
 import argparse
@@ -35,19 +41,18 @@ import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm must use every host core, and BLAS reads
+    # the variable when numpy is imported
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(_v, None)
 for _p in (ROOT, os.path.join(ROOT, "fasta-python_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
 import numpy as np  # noqa: E402
 
-WORKLOADS = {
-    # name: M, N, K (non-zeros of the true signal), sigma, mu, row chunks for seeding
-    "lasso_40000x100000": dict(M=40000, N=100000, K=5000, sigma=0.01, mu=0.02, chunks=64),
-    "lasso_8000x20000": dict(M=8000, N=20000, K=1000, sigma=0.01, mu=0.02, chunks=64),   # dev / small boxes
-}
-SOLVER_OPTS = dict(adaptive=True, accelerate=False, verbose=False, tolerance=1e-5, max_iters=1000)
-CPU_SAMPLE_ITERS = 3
+TOL = 1e-5
 
 
 def parse():
@@ -59,41 +64,78 @@ def parse():
     ap.add_argument("--workload", default="lasso_40000x100000", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--debug-phases", action="store_true", help="print host-side phase times of every timed solve to stderr")
+    ap.add_argument("--cpu-iters", type=int, default=0, help="bound the CPU arm to this many iterations (0 = the workload's default)")
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------------------------------
-# synthetic data: identical for every world size (seeded per fixed row chunk)
+# host-core plumbing for the CPU arm
 # --------------------------------------------------------------------------------------------------
-def make_local_problem(w, rank, world, device):
-    """Rows [lo, hi) of the config-2 recipe: A = randn / (sqrt(M)+sqrt(N)),
-    x_true with K ones, b = A x_true + sigma * randn.  Generated on the device."""
-    import torch
-    M, N, K = w["M"], w["N"], w["K"]
-    assert M % w["chunks"] == 0 and w["chunks"] % world == 0
-    rows_per_chunk = M // w["chunks"]
-    lo, hi = (M * rank) // world, (M * (rank + 1)) // world
-    A = torch.empty(hi - lo, N, dtype=torch.float64, device=device)
-    noise = torch.empty(hi - lo, dtype=torch.float64, device=device)
-    gen = torch.Generator(device=device)
-    for c in range(lo // rows_per_chunk, hi // rows_per_chunk):
-        gen.manual_seed(1000 + c)
-        r0 = c * rows_per_chunk - lo
-        A[r0:r0 + rows_per_chunk].normal_(generator=gen)
-        noise[r0:r0 + rows_per_chunk].normal_(generator=gen)
-    A /= (np.sqrt(M) + np.sqrt(N))
-    cpu_gen = torch.Generator().manual_seed(7)
-    support = torch.randperm(N, generator=cpu_gen)[:K]
-    x_true = torch.zeros(N, dtype=torch.float64)
-    x_true[support] = 1.0
-    x_true = x_true.to(device)
-    b = torch.mv(A, x_true) + w["sigma"] * noise      # setup only, untimed
-    return A, b, x_true
+def blas_all_cores():
+    """Give BLAS every core this process may run on (torchrun pins OMP_NUM_THREADS=1); returns (threads, pools)."""
+    cores = len(os.sched_getaffinity(0))
+    pools = []
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=cores)
+        pools = [f"{p.get('internal_api')}:{p.get('num_threads')}" for p in threadpoolctl.threadpool_info()]
+        blas = [p.get("num_threads") for p in threadpoolctl.threadpool_info() if p.get("user_api") == "blas"]
+        threads = max(blas) if blas else cores
+    except Exception:
+        threads = cores
+    return int(threads), pools
 
 
+def load_reference():
+    """(reference module or None, kind, where)"""
+    try:
+        from oracle import ref_loader
+        mod, root = ref_loader.load_isolated()
+    except Exception:
+        mod, root = None, None
+    if mod is not None:
+        return mod, "reference", os.path.relpath(root, ROOT) if root.startswith(ROOT) else root
+    return None, "port", "oracle/fasta_oracle.py"
+
+
+def reference_solve(ref, A_map, f, gradf, g, proxg, x0, opts):
+    """One run of the reference's fasta() (or of the oracle port) on numpy inputs.  A_map = (apply, adjoint, Vshape, Wshape)."""
+    if ref is not None:
+        op = ref.linalg.LinearMap(A_map[0], A_map[1], A_map[2], A_map[3])
+        return ref.fasta(op, f, gradf, g, proxg, x0, **opts)
+    from oracle import fasta_oracle
+    return fasta_oracle.solve(A_map[0], A_map[1], f, gradf, g, proxg, x0, **opts)
+
+
+def rel(a, b):
+    """max elementwise relative error; entries whose reference is exactly 0 are compared absolutely"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b) / np.where(b == 0, 1.0, np.abs(b))))
+
+
+def parity_block(got, want, n=None):
+    """OUR Convergence against the reference's on the same inputs: the north_star bar."""
+    n = int(want.iteration_count) if n is None else n
+    sol = got.solution.detach().cpu().numpy() if hasattr(got.solution, "detach") else np.asarray(got.solution)
+    out = dict(iterations=[int(got.iteration_count), int(want.iteration_count)],
+               backtracks=[int(got.backtracks), int(want.backtracks)],
+               solution_rel_err=float(np.linalg.norm((sol - want.solution).ravel()) / (np.linalg.norm(want.solution.ravel()) or 1.0)),
+               stepsizes_rel_err=rel(got.stepsizes[:n], want.stepsizes[:n]),
+               residuals_rel_err=rel(got.residuals[:n], want.residuals[:n]))
+    if getattr(got, "objectives", None) is not None and getattr(want, "objectives", None) is not None:
+        out["objective_history_rel_err"] = rel(got.objectives[:n + 1], want.objectives[:n + 1])
+        out["final_objective"] = [float(got.objectives[n]), float(want.objectives[n])]
+    out["ok"] = bool(out["iterations"][0] == out["iterations"][1] and out["backtracks"][0] == out["backtracks"][1]
+                     and out["solution_rel_err"] <= 1e-9 and out.get("objective_history_rel_err", 0.0) <= 1e-10)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks (the profiling recipe's nvidia-smi line, sampled every 200 ms in the background)
+# --------------------------------------------------------------------------------------------------
 def clocks_sampler():
-    """nvidia-smi clocks line of the profiling recipe, sampled every 200 ms in the background."""
     try:
         f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -150,7 +192,6 @@ def clocks_summary(proc, f, device_index, t_begin, t_end):
     except OSError:
         pass
     if sm:
-        # median over samples taken under load (the upper half of the observed clocks)
         out["sm_mhz"] = float(np.median(sm))
         out["sm_max_mhz"] = float(max(smmax))
         out["samples"] = len(sm)
@@ -159,95 +200,666 @@ def clocks_summary(proc, f, device_index, t_begin, t_end):
     return out
 
 
-# --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores
-# --------------------------------------------------------------------------------------------------
-def cpu_arm(w, A_host, b_host, sample_iters=CPU_SAMPLE_ITERS, gpu_solve=None):
-    """Bounded sample: Lipschitz prologue + `sample_iters` iterations of the same problem with numpy
-    (all host threads).  Rate = iterations / in-loop time, the reference's own definition
-    (examples/__init__.py:59-60), which EXCLUDES the prologue -- the most favourable reading."""
-    from oracle import fasta_oracle
-    try:
-        from threadpoolctl import threadpool_info
-        pools = [f"{p.get('internal_api')}:{p.get('num_threads')}" for p in threadpool_info()]
-    except Exception:
-        pools = []
-    mu = w["mu"]
-    la = np.linalg
-    f = lambda z: .5 * la.norm((z - b_host).ravel()) ** 2
-    gradf = lambda z: z - b_host
-    g = lambda x: mu * la.norm(x.ravel(), 1)
-    proxg = lambda x, t: fasta_oracle.shrink(x, t * mu)
-    op = lambda x: A_host @ x
-    adj = lambda y: A_host.T @ y
-    np.random.seed(0)
-    t0 = time.time()
-    opts = dict(SOLVER_OPTS)
-    opts["max_iters"] = sample_iters
-    res = fasta_oracle.solve(op, adj, f, gradf, g, proxg, np.zeros(w["N"]), **opts)
-    wall = time.time() - t0
-    n = res.iteration_count
-    loop = res.times[n] - res.times[0]
-    cores = len(os.sched_getaffinity(0))
-    out = dict(value=n / loop, unit="iterations/s", cores=cores, kind="port",
-               sample=(f"oracle/fasta_oracle.py (numpy {np.__version__}, BLAS pools {pools}) on the full "
-                       f"{w['M']}x{w['N']} problem, first {n} iterations (in-loop time {loop:.2f} s; whole call "
-                       f"incl. 6-pass prologue {wall:.2f} s); os.cpu_count()={os.cpu_count()}"))
-    if gpu_solve is not None:
-        # the oracle as the checker (not the thing measured): the same first iterations on the GPU, same seed
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class Ctx:
+    """What a workload needs to know about the run."""
+
+    def __init__(self, args, rank, world, local, device, torch, dist):
+        self.args, self.rank, self.world, self.local, self.device = args, rank, world, local, device
+        self.torch, self.dist = torch, dist
+
+
+class KernelTimer:
+    """CUDA events around every call of the named back-end methods while `on` (the launching stream is torch's current one)."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.on = False
+        self.events = {}
+        self._undo = []
+
+    def wrap(self, cls, name, key):
+        orig = getattr(cls, name)
+        sink = self.events.setdefault(key, [])
+        timer = self
+
+        def wrapper(self_, *a, **k):
+            if not timer.on:
+                return orig(self_, *a, **k)
+            e0, e1 = timer.torch.cuda.Event(enable_timing=True), timer.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig(self_, *a, **k)
+            e1.record()
+            sink.append((e0, e1))
+            return out
+        setattr(cls, name, wrapper)
+        self._undo.append((cls, name, orig))
+
+    def ms(self, key):
+        return [a.elapsed_time(b) for a, b in self.events.get(key, [])]
+
+
+# ==================================================================================================
+# workloads
+# ==================================================================================================
+class DenseWorkload:
+    """Configs 2 / 3 (and the small lasso twin): dense A generated on the device, rows sharded over the ranks."""
+    scaling = "strong"
+    unit = "iterations/s"
+
+    def __init__(self, name, kind, M, N, K, mu, sigma=0.01, chunks=64, cpu_iters=None):
+        self.name, self.kind, self.M, self.N, self.K, self.mu, self.sigma, self.chunks = name, kind, M, N, K, mu, sigma, chunks
+        self.metric = "lasso_fbs_iterations_per_sec" if kind == "lasso" else "logistic_fbs_iterations_per_sec"
+        self.opts = dict(adaptive=True, accelerate=False, verbose=False, tolerance=TOL, max_iters=1000, evaluate_objective=True)
+        self.cpu_iters = cpu_iters
+
+    # ---- synthetic data: identical for every world size (seeded per fixed row chunk) -------------
+    def local_problem(self, rank, world, device):
+        """Rows [lo, hi).  lasso: A = randn / (sqrt(M)+sqrt(N)), b = A x_true + sigma randn.
+        logistic (config 3, sparse_logistic.py:66-80 at scale): A = randn, b = 2 (rand < sigmoid(A x_true)) - 1."""
+        import torch
+        M, N, K = self.M, self.N, self.K
+        assert M % self.chunks == 0 and self.chunks % world == 0
+        rows = M // self.chunks
+        lo, hi = (M * rank) // world, (M * (rank + 1)) // world
+        A = torch.empty(hi - lo, N, dtype=torch.float64, device=device)
+        aux = torch.empty(hi - lo, dtype=torch.float64, device=device)
+        gen = torch.Generator(device=device)      # (a CPU box generates a different, equally valid instance)
+        for c in range(lo // rows, hi // rows):
+            gen.manual_seed(1000 + c)
+            r0 = c * rows - lo
+            A[r0:r0 + rows].normal_(generator=gen)
+            if self.kind == "lasso":
+                aux[r0:r0 + rows].normal_(generator=gen)
+            else:
+                aux[r0:r0 + rows].uniform_(generator=gen)
+        if self.kind == "lasso":
+            A /= (np.sqrt(M) + np.sqrt(N))
+        support = torch.randperm(N, generator=torch.Generator().manual_seed(7))[:K]
+        x_true = torch.zeros(N, dtype=torch.float64)
+        x_true[support] = 1.0
+        x_true = x_true.to(device)
+        if self.kind == "lasso":
+            b = torch.mv(A, x_true) + self.sigma * aux           # setup only, untimed
+        else:
+            b = 2.0 * (aux < torch.sigmoid(torch.mv(A, x_true))).double() - 1.0
+        return A, b
+
+    def make_inputs(self, ctx):
+        self.ctx = ctx
+        self.A, self.b = self.local_problem(ctx.rank, ctx.world, ctx.device)
+
+    def setup(self, ctx):
+        import fasta
+        self.make_inputs(ctx)
+        t = ctx.torch
+        self.x0 = t.zeros(self.N, dtype=t.float64, device=ctx.device)
+        self.op, self.loss, self.pen = self.objects(self.A, self.b)
+        self.fasta = fasta
+
+    def objects(self, A, b):
+        import fasta
+        op = fasta.distributed.RowShardedMatrix(A) if self.ctx.world > 1 else fasta.linalg.LinearMap.from_matrix(A)
+        loss = fasta.losses.LeastSquares(b) if self.kind == "lasso" else fasta.losses.Logistic(b)
+        return op, loss, fasta.proximal.L1Norm(self.mu)
+
+    def instrument(self, timer):
+        from fasta import _backends
+        timer.wrap(_backends.DenseDriver, "sweep", "sweep")
+        timer.wrap(_backends.DenseDriver, "forward", "stream")
+        timer.wrap(_backends.DenseDriver, "adjoint", "stream")
+
+    def solve(self, opts=None):
+        np.random.seed(0)          # identical tau0 probes in every step and on every rank
+        return self.fasta.fasta(self.op, self.loss.f, self.loss.gradf, self.pen.g, self.pen.prox, self.x0, **(opts or self.opts))
+
+    def step(self):
+        return [self.solve()]
+
+    def units(self, outs):
+        return sum(r.iteration_count for r in outs)
+
+    def config(self, world):
+        what = (f"dense lasso M={self.M} N={self.N} K={self.K} fp64 ({self.M * self.N * 8 / 1e9:.1f} GB A), mu={self.mu}"
+                if self.kind == "lasso" else
+                f"sparse logistic regression M={self.M} N={self.N} K={self.K} fp64 ({self.M * self.N * 8 / 1e9:.1f} GB A), l1 prox mu={self.mu}")
+        return dict(workload=f"{self.name}: {what}, adaptive (BB) FASTA to tolerance 1e-5, A row-sharded over {world} GPU(s)",
+                    step="one full solve (Lipschitz prologue + iterations to tolerance)",
+                    l2="inputs (A) are far larger than the 126 MB L2; no flush needed",
+                    scaling_recipe="A = randn/(sqrt(M)+sqrt(N)) (SURVEY.md 8d)" if self.kind == "lasso" else
+                    "A = randn, mu = 40*sqrt(M/1000) (SURVEY.md 8d)")
+
+    def roofline(self, timer, outs, loop_s):
+        sweep, stream = timer.ms("sweep"), timer.ms("stream")
+        single_pass = len(sweep) > 0
+        all_ms = sweep if single_pass else stream
+        # a speculative launch whose predecessor was rejected / final returns at once (fb200_trial_decide): not a pass over A
+        live = [v for v in all_ms if v > 0.2 * float(np.median(all_ms))]
+        avg = float(np.mean(live))
+        peak, src = measured_peak()
+        dram_bytes = self.A.shape[0] * self.N * 8               # one read of the local rows of A
+        alg_bytes = (2 if single_pass else 1) * dram_bytes      # reference contractions covered by one launch (SURVEY 8d)
+        iters, bts = self.units(outs), sum(r.backtracks for r in outs)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath) and self.ctx.world == 1:
+            tj = json.load(open(tpath))
+            traffic = tj.get(self.name, {}).get("gsweep_dram_bytes_per_launch" if single_pass else "stream_dram_bytes_per_launch")
+        name = ("dense_gsweep_kernel (single pass: z = A x, loss, g = A^T r in ONE read of A; one launch per iteration covers the "
+                "reference's two contractions)" if single_pass else "dense_stream_kernel (A x and A^T r, one launch each per iteration)")
+        dram_gbs = dram_bytes / (avg * 1e-3) / 1e9
+        return dict(bound="hbm", kernel=name, achieved=dram_gbs, peak=peak, unit="GB/s", frac=dram_gbs / peak, traffic=traffic,
+                    peak_source=src, dram_bytes_per_launch=dram_bytes, avg_launch_ms=avg, launches_timed=len(live),
+                    speculative_launches_returned_at_once=len(all_ms) - len(live),
+                    frac_of_nominal_8TBs=dram_gbs / 8000.0,
+                    achieved_algorithmic=alg_bytes / (avg * 1e-3) / 1e9, frac_algorithmic=alg_bytes / (avg * 1e-3) / 1e9 / peak,
+                    algorithmic_bytes_per_launch=alg_bytes,
+                    whole_iteration_algorithmic_GBs=(2 * iters + bts) * dram_bytes / loop_s / 1e9,
+                    whole_iteration_frac_of_nominal_8TBs=(2 * iters + bts) * dram_bytes / loop_s / 1e9 / 8000.0)
+
+    # ---- end to end: host buffers in, host result out ------------------------------------------
+    def e2e_prepare(self):
+        t = self.ctx.torch
+        self.pinned = True
         try:
+            self.A_host = t.empty(self.A.shape, dtype=t.float64, pin_memory=True)
+        except Exception:
+            self.A_host = t.empty(self.A.shape, dtype=t.float64)
+            self.pinned = False
+        self.A_host.copy_(self.A)
+        self.b_host = self.b.cpu().pin_memory()
+        self.x0_host = t.zeros(self.N, dtype=t.float64).pin_memory()
+        self.sol_host = t.empty(self.N, dtype=t.float64).pin_memory()
+        t.cuda.synchronize()
+        self.h2d = int((self.A.numel() + self.b.numel() + self.N) * 8)
+        self.d2h = int(self.N * 8)
+
+    def e2e_step(self):
+        t, dev = self.ctx.torch, self.ctx.device
+        self.A.copy_(self.A_host, non_blocking=True)          # reuse the resident buffers as upload targets
+        b_dev = self.b_host.to(dev, non_blocking=True)
+        x_dev = self.x0_host.to(dev, non_blocking=True)
+        op, loss, pen = self.objects(self.A, b_dev)
+        np.random.seed(0)
+        r = self.fasta.fasta(op, loss.f, loss.gradf, pen.g, pen.prox, x_dev, **self.opts)
+        self.sol_host.copy_(r.solution, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        return [r]
+
+    # ---- CPU arm ------------------------------------------------------------------------------
+    def host_problem(self):
+        if getattr(self, "A_host", None) is not None:
+            A = self.A_host.numpy()
+        else:
+            A = self.A.cpu().numpy()
+        return A, self.b.cpu().numpy()
+
+    def callables(self, A, b):
+        la, mu = np.linalg, self.mu
+        if self.kind == "lasso":                                # sparse_least_squares.py:41-44
+            f = lambda z: .5 * la.norm((z - b).ravel()) ** 2
+            gradf = lambda z: z - b
+        else:                                                   # sparse_logistic.py:47-48
+            f = lambda z: np.sum(np.log(1 + np.exp(z)) - (b == 1) * z)
+            gradf = lambda z: -b / (1 + np.exp(b * z))
+        g = lambda x: mu * la.norm(x.ravel(), 1)
+        proxg = lambda x, t: np.sign(x) * np.maximum(np.abs(x) - t * mu, 0)      # proximal.py:67 with t*mu
+        amap = (lambda x: A @ x, lambda y: A.T @ y, (A.shape[1],), (A.shape[0],))
+        return amap, f, gradf, g, proxg
+
+    def cpu_arm(self, ref, max_iters=None):
+        """The reference on the host cores on the very same A, b: full solve to tolerance unless bounded."""
+        A, b = self.host_problem()
+        amap, f, gradf, g, proxg = self.callables(A, b)
+        opts = dict(self.opts)
+        if max_iters:
+            opts["max_iters"] = int(max_iters)
+        np.random.seed(0)
+        t0 = time.time()
+        res = reference_solve(ref, amap, f, gradf, g, proxg, np.zeros(self.N), opts)
+        wall = time.time() - t0
+        n = res.iteration_count
+        loop = res.times[n] - res.times[0]
+        what = "to tolerance" if not max_iters else f"bounded to {max_iters} iterations"
+        sample = (f"the full {self.M}x{self.N} problem {what}: {n} iterations, {res.backtracks} backtracks, in-loop {loop:.2f} s "
+                  f"(whole call incl. the 6-pass Lipschitz prologue {wall:.2f} s)")
+        return res, n / loop, sample, opts
+
+
+class SmallLasso(DenseWorkload):
+    """Config 1: the reference's own example, sparse_least_squares.py:51-76 defaults (M=200, N=1000, K=10, seed 0)."""
+    scaling = "weak"
+    BATCH = 100
+
+    def __init__(self):
+        super().__init__("lasso_200x1000", "lasso", 200, 1000, 10, 0.02)
+
+    def local_problem(self, rank, world, device):
+        import torch
+        np.random.seed(0)
+        M, N, K = self.M, self.N, self.K
+        x = np.zeros(N)
+        x[np.random.permutation(N)[:K]] = 1                     # draw order of the reference: permutation, randn(M,N), randn(M)
+        A = np.random.randn(M, N)
+        A /= np.linalg.norm(A, 2)
+        b = A @ x + self.sigma * np.random.randn(M)
+        self.A_np, self.b_np = A, b
+        return torch.from_numpy(A).to(device), torch.from_numpy(b).to(device)
+
+    def objects(self, A, b):
+        import fasta
+        return fasta.linalg.LinearMap.from_matrix(A), fasta.losses.LeastSquares(b), fasta.proximal.L1Norm(self.mu)
+
+    def step(self):
+        return [self.solve() for _ in range(self.BATCH)]
+
+    def config(self, world):
+        return dict(workload=f"{self.name}: the reference's sparse_least_squares example (M=200 N=1000 K=10 sigma=0.01 mu=0.02, seed 0, "
+                             f"A /= |A|_2), adaptive FASTA to tolerance 1e-5; {world} independent replica(s)",
+                    step=f"{self.BATCH} consecutive full solves of the same problem",
+                    l2="1.6 MB problem, deliberately cache / shared-memory resident (latency-bound config): no flush")
+
+    def instrument(self, timer):
+        pass
+
+    def roofline(self, timer, outs, loop_s):
+        iters = self.units(outs)
+        peak, src = measured_peak()
+        alg = 2 * self.M * self.N * 8 * iters / loop_s / 1e9
+        return dict(bound="hbm", kernel="resident_fbs_kernel (whole loop in one launch, A staged once into the shared memory of one cluster)",
+                    achieved=alg, peak=peak, unit="GB/s", frac=alg / peak, traffic=None, peak_source=src,
+                    note="latency-bound: A never leaves shared memory, so HBM is idle by design; `achieved` is the reference's "
+                         "2*M*N*8 B per iteration over the in-loop time, reported for completeness only")
+
+    def e2e_prepare(self):
+        t = self.ctx.torch
+        self.A_host = t.from_numpy(self.A_np).pin_memory()
+        self.b_host = t.from_numpy(self.b_np).pin_memory()
+        self.x0_host = t.zeros(self.N, dtype=t.float64).pin_memory()
+        self.sol_host = t.empty(self.N, dtype=t.float64).pin_memory()
+        self.pinned = True
+        self.h2d = int((self.A.numel() + self.b.numel() + self.N) * 8) * self.BATCH
+        self.d2h = int(self.N * 8) * self.BATCH
+
+    def e2e_step(self):
+        t, dev = self.ctx.torch, self.ctx.device
+        outs = []
+        for _ in range(self.BATCH):
+            A = self.A_host.to(dev, non_blocking=True)
+            b_dev = self.b_host.to(dev, non_blocking=True)
+            x_dev = self.x0_host.to(dev, non_blocking=True)
+            op, loss, pen = self.objects(A, b_dev)
             np.random.seed(0)
-            got = gpu_solve(opts)
-            rel = lambda a, b_: float(np.max(np.abs(np.asarray(a) - np.asarray(b_)) / np.maximum(np.abs(np.asarray(b_)), 1e-300)))
-            sol = got.solution.detach().cpu().numpy() if hasattr(got.solution, "detach") else np.asarray(got.solution)
-            out["parity_full_size"] = dict(
-                iterations=[int(got.iteration_count), int(n)], backtracks=[int(got.backtracks), int(res.backtracks)],
-                stepsizes_rel_err=rel(got.stepsizes[:n], res.stepsizes[:n]),
-                residuals_rel_err=rel(got.residuals[:n], res.residuals[:n]),
-                iterate_rel_err=float(la.norm(sol - res.solution) / max(la.norm(res.solution), 1e-300)))
-        except Exception as exc:                             # never lose the bench line over the cross-check
+            r = self.fasta.fasta(op, loss.f, loss.gradf, pen.g, pen.prox, x_dev, **self.opts)
+            self.sol_host.copy_(r.solution, non_blocking=True)
+            t.cuda.current_stream().synchronize()
+            outs.append(r)
+        return outs
+
+    def host_problem(self):
+        return self.A_np, self.b_np
+
+
+class TVWorkload:
+    """Config 4: tv_denoising.py:26-63,85-96 at n = 4096 on a synthetic image (scipy's `ascent` is not available offline)."""
+    scaling = "weak"
+    unit = "iterations/s"
+    metric = "tv_fbs_iterations_per_sec"
+
+    def __init__(self, n=4096, max_iters=1000):
+        self.name, self.n, self.mu = f"tv_{n}", n, 0.1
+        self.opts = dict(adaptive=True, accelerate=False, verbose=False, tolerance=TOL, max_iters=max_iters, evaluate_objective=True)
+
+    def make_inputs(self, ctx):
+        self.ctx = ctx
+        n = self.n
+        rng = np.random.RandomState(0)
+        yy, xx = np.mgrid[0:n, 0:n]
+        img = (((yy // 64) + (xx // 64)) % 2).astype(np.float64)            # 64-pixel checkerboard in [0, 1]
+        img += 0.1 * rng.randn(n, n)
+        self.b_np = img / self.mu
+
+    def setup(self, ctx):
+        import fasta
+        self.make_inputs(ctx)
+        self.fasta = fasta
+        t, n = ctx.torch, self.n
+        self.b = t.from_numpy(self.b_np).to(ctx.device)
+        self.Y0 = t.zeros(n, n, 2, dtype=t.float64, device=ctx.device)
+        self.op, self.loss, self.pen = fasta.tv.divergence_map((n, n)), fasta.losses.LeastSquares(self.b), fasta.proximal.TVBall()
+
+    def instrument(self, timer):
+        from fasta import _backends
+        timer.wrap(_backends.TVDriver, "iterate_fused", "tv_iter")
+
+    def solve(self, opts=None):
+        np.random.seed(0)
+        return self.fasta.fasta(self.op, self.loss.f, self.loss.gradf, self.pen.g, self.pen.prox, self.Y0, **(opts or self.opts))
+
+    def step(self):
+        return [self.solve()]
+
+    def units(self, outs):
+        return sum(r.iteration_count for r in outs)
+
+    def config(self, world):
+        n = self.n
+        return dict(workload=f"{self.name}: total-variation denoising {n}x{n} (dual problem, matrix-free div / grad stencils) fp64, 64-px "
+                             f"checkerboard + 0.1 randn, mu=0.1, adaptive FASTA, tolerance 1e-5, max_iters {self.opts['max_iters']} (the reference "
+                             f"default); {world} independent replica(s)",
+                    step=f"one full solve (Lipschitz prologue incl. two {2 * n * n / 1e6:.1f}M-element Gaussian probes + iterations)",
+                    l2=f"state is {5 * n * n * 16 / 1e6:.0f} MB per iteration, larger than the 126 MB L2; no flush needed")
+
+    def roofline(self, timer, outs, loop_s):
+        ms = timer.ms("tv_iter")
+        live = [v for v in ms if v > 0.2 * float(np.median(ms))]
+        avg = float(np.mean(live))
+        peak, src = measured_peak()
+        U = self.n * self.n * 8
+        dram = 9 * U                                             # read x0 (2U), g0 (2U), b (U); write x1 (2U), g1 (2U)
+        alg = 11 * U                                             # SURVEY 8d's accounting of one iteration
+        gbs = dram / (avg * 1e-3) / 1e9
+        return dict(bound="hbm", kernel="tv_iter_march_kernel (whole trial in one pass: step, ball projection, div, loss, grad, 7 sums)",
+                    achieved=gbs, peak=peak, unit="GB/s", frac=gbs / peak, traffic=None, peak_source=src, dram_bytes_per_launch=dram,
+                    avg_launch_ms=avg, launches_timed=len(live), speculative_launches_returned_at_once=len(ms) - len(live),
+                    achieved_algorithmic=alg / (avg * 1e-3) / 1e9, frac_algorithmic=alg / (avg * 1e-3) / 1e9 / peak,
+                    algorithmic_bytes_per_launch=alg)
+
+    def e2e_prepare(self):
+        t = self.ctx.torch
+        self.b_host = t.from_numpy(self.b_np).pin_memory()
+        self.Y0_host = t.zeros(self.n, self.n, 2, dtype=t.float64).pin_memory()
+        self.sol_host = t.empty(self.n, self.n, 2, dtype=t.float64).pin_memory()
+        self.pinned = True
+        self.h2d = int(self.b.numel() + self.Y0.numel()) * 8
+        self.d2h = int(self.Y0.numel()) * 8
+
+    def e2e_step(self):
+        t, dev = self.ctx.torch, self.ctx.device
+        b_dev = self.b_host.to(dev, non_blocking=True)
+        y_dev = self.Y0_host.to(dev, non_blocking=True)
+        loss = self.fasta.losses.LeastSquares(b_dev)
+        np.random.seed(0)
+        r = self.fasta.fasta(self.op, loss.f, loss.gradf, self.pen.g, self.pen.prox, y_dev, **self.opts)
+        self.sol_host.copy_(r.solution, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        return [r]
+
+    def cpu_arm(self, ref, max_iters=None):
+        """tv_denoising.py:26-63 (grad / div by np.roll), :85-96 (f, gradf, ball projection) on the same image."""
+        b, n = self.b_np, self.n
+
+        def grad(X):                                            # tv_denoising.py:26-40
+            G = np.zeros(X.shape + (X.ndim,))
+            for d in range(X.ndim):
+                G[..., d] = np.roll(X, 1, axis=d) - X
+            return G
+
+        def div(Y):                                             # tv_denoising.py:43-63
+            D = np.zeros(Y.shape[:-1])
+            for d in range(Y.shape[-1]):
+                D += np.roll(Y[..., d], -1, axis=d) - Y[..., d]
+            return D
+
+        f = lambda Z: .5 * np.linalg.norm((Z - b).ravel()) ** 2
+        gradf = lambda Z: Z - b
+        g = lambda Y: 0
+
+        def proxg(Y, t):                                        # tv_denoising.py:89-96
+            norms = np.maximum(np.sqrt(np.sum(Y * Y, axis=-1)), 1)
+            return Y / norms[..., np.newaxis]
+
+        opts = dict(self.opts)
+        opts["max_iters"] = int(max_iters or 6)
+        np.random.seed(0)
+        t0 = time.time()
+        res = reference_solve(ref, (div, grad, (n, n, 2), (n, n)), f, gradf, g, proxg, np.zeros((n, n, 2)), opts)
+        wall = time.time() - t0
+        k = res.iteration_count
+        loop = res.times[k] - res.times[0]
+        sample = (f"the same {n}x{n} image, first {k} iterations ({res.backtracks} backtracks), in-loop {loop:.2f} s (whole call incl. the "
+                  f"Lipschitz prologue {wall:.2f} s); TV + adaptive BB amplifies last-bit noise after ~70 iterations (SURVEY 7.3-1), so "
+                  f"parity is asserted on this horizon")
+        return res, k / loop, sample, opts
+
+
+class BatchedWorkload:
+    """Config 5: 256 lambdas x (M=20000, N=50000): lock-step FBS whose contractions are tcgen05 GEMMs; columns sharded."""
+    scaling = "strong"
+    unit = "column-iterations/s"
+    metric = "batched_lasso_path_column_iterations_per_sec"
+    INT8_PEAK_TOPS = 4500.0          # nominal B200 dense int8 (MEASURED_PEAKS.json has no int8 figure)
+
+    def __init__(self, B=256, M=20000, N=50000):
+        self.name, self.B, self.M, self.N = f"batched_{B}x{M}x{N}", B, M, N
+        self.opts = dict(adaptive=True, verbose=False, tolerance=TOL, max_iters=1000, evaluate_objective=True)
+
+    def make_inputs(self, ctx):
+        self.ctx = ctx
+        t, M, N = ctx.torch, self.M, self.N
+        gen = t.Generator(device=ctx.device).manual_seed(5) if ctx.device.type == "cuda" else t.Generator().manual_seed(5)
+        A = t.randn(M, N, dtype=t.float64, device=ctx.device, generator=gen)
+        A /= (np.sqrt(M) + np.sqrt(N))                               # SURVEY 8d scaling recipe (config 2 / 5)
+        xt = t.zeros(N, dtype=t.float64, device=ctx.device)
+        xt[t.randperm(N, generator=t.Generator().manual_seed(5))[:N // 20].to(ctx.device)] = 1.0
+        self.A = A
+        self.b = t.mv(A, xt) + 0.01 * t.randn(M, dtype=t.float64, device=ctx.device, generator=gen)
+        self.lam_max = float(t.mv(A.t(), self.b).abs().max())
+        self.mus_all = self.lam_max * np.logspace(-3, 0, self.B)
+        self.cols = np.arange(ctx.rank, self.B, ctx.world)           # round-robin: neighbours in lambda cost alike
+        self.mus = self.mus_all[self.cols]
+
+    def setup(self, ctx):
+        import fasta
+        from fasta import batched
+        self.make_inputs(ctx)
+        self.fasta, self.batched = fasta, batched
+        assert list(self.cols) == list(batched.column_shard(self.B, ctx.rank, ctx.world))
+        self.op = fasta.linalg.LinearMap.from_matrix(self.A)
+        self.X0 = ctx.torch.zeros(self.N, len(self.cols), dtype=ctx.torch.float64, device=ctx.device)   # device in -> device out
+
+    def instrument(self, timer):
+        self.timer = timer
+
+    def solve(self, opts=None, mus=None):
+        np.random.seed(0)
+        return self.batched.lasso_path(self.op, self.b, self.mus if mus is None else mus, x0=self.X0 if mus is None else None,
+                                       **(opts or self.opts))
+
+    def step(self):
+        self.batched.GEMM_EVENTS = [] if getattr(self, "timer", None) is not None and self.timer.on else None
+        out = self.solve()
+        if self.batched.GEMM_EVENTS is not None:
+            self.timer.events.setdefault("gemm", []).extend(self.batched.GEMM_EVENTS)
+        self.batched.GEMM_EVENTS = None
+        self.last_path = out
+        return [out]
+
+    def units(self, outs):
+        return int(sum(r.iteration_count for path in outs for r in path))
+
+    def config(self, world):
+        return dict(workload=f"{self.name}: lasso regularisation path, {self.B} lambdas log-spaced in [1e-3, 1]*|A^T b|_inf, M={self.M} N={self.N} "
+                             f"fp64 ({self.M * self.N * 8 / 1e9:.1f} GB A), adaptive FASTA per column to tolerance 1e-5, lock-step iterations with "
+                             f"both contractions as tcgen05 int8 digit-plane GEMMs; columns dealt round-robin over {world} GPU(s), A replicated",
+                    step="one full path (every column to its own tolerance)",
+                    l2=f"A's digit planes ({2 * self.M * self.N * 8 / 1e9:.1f} GB) are far larger than the 126 MB L2; no flush needed")
+
+    def roofline(self, timer, outs, loop_s):
+        ev = timer.events.get("gemm", [])
+        pad64 = lambda k: (k + 63) // 64 * 64
+        gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in ev)
+        flops = sum(2.0 * self.M * self.N * k for _, _, _, k in ev)                    # useful fp64-equivalent flops (active columns)
+        int8_ops = sum(36 * 2.0 * self.M * self.N * pad64(k) for _, _, _, k in ev)      # what the tensor pipe executed
+        Bl = len(self.cols)
+        full = [(a.elapsed_time(b), adj) for a, b, adj, k in ev if k == Bl]
+        tops = int8_ops / gemm_ms / 1e9
+        return dict(bound="tensor", kernel="ozaki_gemm_kernel (fp64 product as 36 exact int8 digit-pair GEMMs on tcgen05.mma.kind::i8, int32 TMEM accumulators)",
+                    achieved=tops, peak=self.INT8_PEAK_TOPS, unit="TOP/s (int8)", frac=tops / self.INT8_PEAK_TOPS, traffic=None,
+                    peak_source="nominal B200 dense int8 (no measured int8 figure in MEASURED_PEAKS.json)",
+                    gemm_calls=len(ev), gemm_ms=gemm_ms, gemm_fp64_equiv_tflops=flops / gemm_ms / 1e9,
+                    full_width_gemm_ms=dict(forward=float(np.mean([v for v, adj in full if not adj])) if any(not adj for _, adj in full) else None,
+                                            adjoint=float(np.mean([v for v, adj in full if adj])) if any(adj for _, adj in full) else None))
+
+    def e2e_prepare(self):
+        t = self.ctx.torch
+        self.A_host = t.empty(self.A.shape, dtype=t.float64, pin_memory=True)
+        self.A_host.copy_(self.A)
+        self.b_host = self.b.cpu().pin_memory()
+        self.sol_host = t.empty(len(self.cols), self.N, dtype=t.float64).pin_memory()
+        self.pinned = True
+        t.cuda.synchronize()
+        self.h2d = int(self.A.numel() + self.b.numel()) * 8
+        self.d2h = int(self.sol_host.numel()) * 8
+
+    def e2e_step(self):
+        t, dev = self.ctx.torch, self.ctx.device
+        self.A.copy_(self.A_host, non_blocking=True)
+        b_dev = self.b_host.to(dev, non_blocking=True)
+        op = self.fasta.linalg.LinearMap.from_matrix(self.A)
+        np.random.seed(0)
+        out = self.batched.lasso_path(op, b_dev, self.mus, x0=self.X0, **self.opts)
+        for j, r in enumerate(out):
+            self.sol_host[j].copy_(r.solution, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        return [out]
+
+    # columns checked against the reference: spread over the lambda range; (column, horizon) -- a small-lambda column
+    # runs ~900 iterations of ~0.6 s each on the host, so those are compared on a bounded horizon of the histories
+    # (position in the path, horizon); the very last column (mu = |A^T b|_inf, solution exactly 0) is degenerate
+    CHECK = ((0.97, None), (0.875, None), (0.625, 12), (0.375, 10), (0.125, 10), (0.0, 10))
+
+    def cpu_arm(self, ref, max_iters=None):
+        """Sampled columns of the path, each ONE reference run on the same A, b (the reference has no batched mode).  With
+        a finished path at hand (``last_path``: the timed full-width run on the tcgen05 GEMMs) every sampled column of it
+        is checked against the reference: counts, solution and objective history for the columns run to tolerance,
+        the histories on the horizon for the others."""
+        A, b = self.A.cpu().numpy(), self.b.cpu().numpy()
+        la = np.linalg
+        rate_n, rate_t, checks = 0, 0.0, []
+        path = getattr(self, "last_path", None)
+        local = {int(c): k for k, c in enumerate(self.cols)}
+        seen = set()
+        for where, horizon in self.CHECK:
+            col = int(round(where * (self.B - 1)))
+            if col not in local or col in seen:
+                continue
+            seen.add(col)
+            mu = float(self.mus_all[col])
+            f = lambda z: .5 * la.norm((z - b).ravel()) ** 2
+            gradf = lambda z: z - b
+            g = lambda x: mu * la.norm(x.ravel(), 1)
+            proxg = lambda x, t: np.sign(x) * np.maximum(np.abs(x) - t * mu, 0)
+            opts = dict(self.opts)
+            if horizon or max_iters:
+                opts["max_iters"] = int(max_iters or horizon)
+            np.random.seed(0)
+            want = reference_solve(ref, (lambda x: A @ x, lambda y: A.T @ y, (self.N,), (self.M,)), f, gradf, g, proxg, np.zeros(self.N), opts)
+            n = want.iteration_count
+            rate_n += n
+            rate_t += want.times[n] - want.times[0]
+            if path is None:
+                continue
+            got = path[local[col]]
+            if "max_iters" in opts and opts["max_iters"] < self.opts["max_iters"] and got.iteration_count > n:
+                p = dict(iterations_on_horizon=int(n), stepsizes_rel_err=rel(got.stepsizes[:n], want.stepsizes[:n]),
+                         residuals_rel_err=rel(got.residuals[:n], want.residuals[:n]),
+                         objective_history_rel_err=rel(got.objectives[:n + 1], want.objectives[:n + 1]))
+                p["ok"] = bool(p["objective_history_rel_err"] <= 1e-10 and p["stepsizes_rel_err"] <= 1e-6)
+                p["horizon"] = int(n)
+            else:
+                p = parity_block(got, want)
+                p["horizon"] = "to tolerance"
+            p.update(column=int(col), mu_over_lam_max=float(mu / self.lam_max))
+            checks.append(p)
+        self.column_checks = checks if path is not None else None
+        sample = (f"{len(self.CHECK)} columns of the path solved ONE AT A TIME by the reference on the same A, b (it has no batched mode), the "
+                  f"large-lambda ones to tolerance, the others on a bounded horizon: {rate_n} column-iterations in {rate_t:.1f} s in-loop")
+        return None, rate_n / max(rate_t, 1e-9), sample, None
+
+
+WORKLOADS = {
+    "lasso_40000x100000": lambda: DenseWorkload("lasso_40000x100000", "lasso", 40000, 100000, 5000, 0.02),
+    "lasso_8000x20000": lambda: DenseWorkload("lasso_8000x20000", "lasso", 8000, 20000, 1000, 0.02),
+    "lasso_200x1000": lambda: SmallLasso(),
+    "logistic_100000x20000": lambda: DenseWorkload("logistic_100000x20000", "logistic", 100000, 20000, 50, 400.0, chunks=40),
+    "logistic_10000x2000": lambda: DenseWorkload("logistic_10000x2000", "logistic", 10000, 2000, 5, 40.0 * np.sqrt(10.0), chunks=16),
+    "tv_4096": lambda: TVWorkload(4096),
+    "tv_512": lambda: TVWorkload(512),
+    "batched_256x20000x50000": lambda: BatchedWorkload(256, 20000, 50000),
+    "batched_32x2000x5000": lambda: BatchedWorkload(32, 2000, 5000),
+}
+
+
+# ==================================================================================================
+# the two arms
+# ==================================================================================================
+def cpu_leg(w, ctx, gpu_check=True, max_iters=None):
+    """cpu_baseline object: the reference on the host cores (+ parity of our arm against it)."""
+    threads, pools = blas_all_cores()
+    ref, kind, where = load_reference()
+    want, rate, sample, opts = w.cpu_arm(ref, max_iters=max_iters or None)
+    out = dict(value=rate, unit=w.unit, cores=threads, kind=kind,
+               sample=f"{where} ({'the unmodified reference fasta.fasta' if ref is not None else 'numpy port of the reference loop'}, numpy "
+                      f"{np.__version__}, BLAS pools {pools}, os.cpu_count()={os.cpu_count()}) on {sample}")
+    if gpu_check:
+        try:
+            if want is not None:
+                out["parity_full_size"] = parity_block(w.solve(opts), want)
+            elif getattr(w, "column_checks", None) is not None:
+                out["parity_full_size"] = dict(columns=w.column_checks, ok=bool(all(c["ok"] for c in w.column_checks)))
+        except Exception as exc:                                 # never lose the bench line over the cross-check
             out["parity_full_size"] = dict(error=repr(exc))
     return out
 
 
 def reference_main(args):
-    """--impl reference: time the reference's CPU path (oracle port) on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    w = WORKLOADS[args.workload]
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
-    A, b, _ = make_local_problem(w, 0, 1, dev)
-    A_host, b_host = A.cpu().numpy(), b.cpu().numpy()
-    del A
-    steps = max(1, args.steps)
-    vals = []
+    w = WORKLOADS[args.workload]()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local) if torch.cuda.is_available() else torch.device("cpu")
+    ctx = Ctx(args, 0, 1, local, dev, torch, None)
+    threads, pools = blas_all_cores()
+    ref, kind, where = load_reference()
+    # inputs only (generated exactly as in our arm: torch / numpy); nothing of this repo's package is imported below
+    w.make_inputs(ctx)
+    if isinstance(w, DenseWorkload) and not isinstance(w, SmallLasso) and dev.type == "cuda":
+        A_host, b_host = w.A.cpu().numpy(), w.b.cpu().numpy()
+        w.A = w.b = None
+        torch.cuda.empty_cache()
+        w.host_problem = lambda: (A_host, b_host)
+    bound = args.cpu_iters or None
+    vals, samples = [], []
     for _ in range(min(args.warmup, 1)):
-        cpu_arm(w, A_host, b_host, 1)
-    for _ in range(min(steps, 2)):
-        base = cpu_arm(w, A_host, b_host)
-        vals.append(base["value"])
-    base["value"] = float(np.mean(vals))
-    line = dict(impl="reference", metric="lasso_fbs_iterations_per_sec", value=base["value"], unit="iterations/s",
-                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 / base["value"],
-                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                config=config_of(w, args.gpus), cpu_baseline=base,
-                e2e=dict(value=base["value"], unit="iterations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        w.cpu_arm(ref, max_iters=2)
+    for _ in range(max(1, min(args.steps, 2))):
+        _, rate, sample, _ = w.cpu_arm(ref, max_iters=bound)
+        vals.append(rate)
+        samples.append(sample)
+    value = float(np.mean(vals))
+    assert threads > 1 or len(os.sched_getaffinity(0)) == 1, f"reference arm is running on {threads} BLAS thread(s)"
+    assert "fasta" not in sys.modules or not os.path.realpath(sys.modules["fasta"].__file__).startswith(
+        os.path.realpath(os.path.join(ROOT, "fasta-python_b200"))), "the reference arm must not import this repo's package"
+    base = dict(value=value, unit=w.unit, cores=threads, kind=kind,
+                sample=f"{where} (numpy {np.__version__}, BLAS pools {pools}, os.cpu_count()={os.cpu_count()}) on {samples[-1]}; "
+                       f"mean of {len(vals)} runs")
+    line = dict(impl="reference", metric=w.metric, value=value, unit=w.unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 / value, higher_is_better=True, scaling=w.scaling, vs_baseline=None, dtype="f64", data="synthetic",
+                config=w.config(args.gpus), cpu_baseline=base, num_threads=threads,
+                e2e=dict(value=value, unit=w.unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
-def config_of(w, world):
-    return dict(workload=f"dense lasso M={w['M']} N={w['N']} K={w['K']} fp64 ({w['M'] * w['N'] * 8 / 1e9:.1f} GB A), "
-                         f"adaptive FASTA to tolerance 1e-5, A row-sharded over {world} GPU(s)",
-                step="one full solve (Lipschitz prologue + iterations to tolerance)",
-                l2="inputs (A) are far larger than the 126 MB L2; no flush needed",
-                sigma=w["sigma"], mu=w["mu"], scaling_recipe="A = randn/(sqrt(M)+sqrt(N)) (SURVEY.md 8d)")
-
-
-# --------------------------------------------------------------------------------------------------
-# our arm
-# --------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == "reference":
@@ -256,80 +868,23 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import fasta
-    from fasta import _backends
+    import fasta  # noqa: F401
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    ctx = Ctx(args, rank, world, local, device, torch, dist)
 
-    w = WORKLOADS[args.workload]
-    M, N = w["M"], w["N"]
-    A, b, _ = make_local_problem(w, rank, world, device)
-    m_local = A.shape[0]
-    x0 = torch.zeros(N, dtype=torch.float64, device=device)
-
-    # ---- operator / loss / penalty (public API objects) -------------------------------------------
-    def build_objects(A_dev, b_dev):
-        op = fasta.distributed.RowShardedMatrix(A_dev) if world > 1 else fasta.linalg.LinearMap.from_matrix(A_dev)
-        return op, fasta.losses.LeastSquares(b_dev), fasta.proximal.L1Norm(w["mu"])
-
-    op, loss, pen = build_objects(A, b)
-
-    # live kernel timing: CUDA events around every dense contraction launched in the timed region
-    kernel_events = []
-    orig_forward, orig_adjoint = _backends.DenseDriver.forward, _backends.DenseDriver.adjoint
-    orig_sweep = _backends.DenseDriver.sweep
-    record = {"on": False}
-    sweep_events = []
-
-    def timed(fn, sink):
-        def wrapper(self, *a, **k):
-            if not record["on"]:
-                return fn(self, *a, **k)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = fn(self, *a, **k)
-            e1.record()
-            sink.append((e0, e1))
-            return out
-        return wrapper
-
-    _backends.DenseDriver.forward = timed(orig_forward, kernel_events)
-    _backends.DenseDriver.adjoint = timed(orig_adjoint, kernel_events)
-    _backends.DenseDriver.sweep = timed(orig_sweep, sweep_events)
-
-    marks = []
-    if args.debug_phases:
-        def phase(cls, name):
-            orig = getattr(cls, name)
-
-            def f(self, *a, **k):
-                t0 = time.perf_counter()
-                out = orig(self, *a, **k)
-                marks.append((name, time.perf_counter() - t0))
-                return out
-            setattr(cls, name, f)
-        for name in ("__init__", "load", "lipschitz", "start", "solution", "close"):
-            phase(_backends.FusedBackend, name)
-
-    def solve(xstart):
-        np.random.seed(0)          # identical tau0 probes in every step and on every rank
-        t0 = time.perf_counter()
-        res = fasta.fasta(op, loss.f, loss.gradf, pen.g, pen.prox, xstart, **SOLVER_OPTS)
-        if args.debug_phases and rank == 0:
-            loop = res.times[res.iteration_count] - res.times[0]
-            print(f"[phases] call {1e3 * (time.perf_counter() - t0):.1f} ms, loop {1e3 * loop:.1f} ms :: " +
-                  ", ".join(f"{n} {1e3 * t:.2f}" for n, t in marks), file=sys.stderr, flush=True)
-            marks.clear()
-        return res
+    w = WORKLOADS[args.workload]()
+    w.setup(ctx)
+    timer = KernelTimer(torch)
+    w.instrument(timer)
 
     def barrier():
         if world > 1:
@@ -344,9 +899,10 @@ def main():
         e0.record()
         outs = []
         for _ in range(steps):
-            if outs:
-                outs[-1].solution = None     # drop the previous solution buffer, as a caller's loop would: the caching
-            outs.append(fn())                # allocator then stays in steady state (no cudaMalloc inside the timed region)
+            for r in outs[-1:]:                 # drop the previous solution buffers, as a caller's loop would: the caching
+                if hasattr(r, "solution"):      # allocator then stays in steady state (no cudaMalloc inside the timed region)
+                    r.solution = None
+            outs.extend(fn())
         e1.record()
         barrier()
         wall = time.time() - t0
@@ -356,112 +912,133 @@ def main():
         return outs, float(ms.item()), wall
 
     # ---- warm-up, then the resident-input measurement ---------------------------------------------
+    warm = max(args.warmup, 3)
     sampler, sfile = clocks_sampler() if rank == 0 else (None, None)
-    for _ in range(max(args.warmup, 3)):
-        res = solve(x0)
-    record["on"] = True
+    for _ in range(warm):
+        w.step()
+    timer.on = True
     t_begin = time.time()
-    outs, ms_total, wall = timed_region(lambda: solve(x0), args.steps)
+    outs, ms_total, wall = timed_region(w.step, args.steps)
     t_end = time.time()
-    record["on"] = False
+    timer.on = False
     torch.cuda.synchronize()
     clocks = clocks_summary(sampler, sfile, local, t_begin, t_end) if rank == 0 else None
 
-    iters = sum(r.iteration_count for r in outs)
-    peer_reductions = sum(getattr(r, "peer_reductions", 0) for r in outs)
-    backtracks = sum(r.backtracks for r in outs)
-    launches = sum(r.kernel_launches for r in outs)
-    loop_s = sum(r.times[r.iteration_count] - r.times[0] for r in outs)
-    value = iters / (ms_total / 1e3)
-    single_pass = len(sweep_events) > 0
-    kern_ms_all = [a.elapsed_time(b_) for a, b_ in (sweep_events if single_pass else kernel_events)]
-    # a speculative launch whose predecessor was rejected / final returns at once (fb200_trial_decide): not a pass over A
-    kern_ms = [t for t in kern_ms_all if t > 0.2 * float(np.median(kern_ms_all))]
-    kern_avg_ms = float(np.mean(kern_ms))
-    dram_bytes = m_local * N * 8                       # one read of the local rows of A
-    alg_bytes = (2 if single_pass else 1) * dram_bytes  # reference contractions covered by one launch
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    flat = [r for o in outs for r in (o if isinstance(o, list) else [o])]
+    units = w.units(outs)
+    if isinstance(w, BatchedWorkload):
+        launches = sum(path[0].batch["kernel_launches"] for path in outs)
+        loop_s = sum(path[0].batch.get("loop_s", 0.0) for path in outs) or ms_total / 1e3
+        backtracks = sum(r.backtracks for r in flat)
     else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        t = json.load(open(tpath))
-        if t.get("workload") == args.workload and world == 1:
-            traffic = t.get("sweep_dram_bytes_per_launch" if single_pass else "dram_bytes_per_launch")
-    kernel_name = ("dense_sweep_kernel (single pass: z = A x, loss, g = A^T r; one launch per iteration, covers the "
-                   "reference's two contractions = 2*M*N*8 algorithmic bytes while reading A from HBM once)"
-                   if single_pass else "dense_stream_kernel (A x and A^T r, one launch each per iteration)")
-    roofline = dict(bound="hbm", kernel=kernel_name,
-                    achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                    peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
-                    avg_launch_ms=kern_avg_ms, launches_timed=len(kern_ms),
-                    speculative_launches_returned_at_once=len(kern_ms_all) - len(kern_ms),
-                    frac_of_nominal_8TBs=achieved / 8000.0,
-                    dram_GBs=dram_bytes / (kern_avg_ms * 1e-3) / 1e9,
-                    dram_frac_of_measured_peak=dram_bytes / (kern_avg_ms * 1e-3) / 1e9 / peak,
-                    whole_iteration_algorithmic_GBs=(2 * iters + backtracks) * dram_bytes / loop_s / 1e9,
-                    whole_iteration_frac_of_nominal_8TBs=(2 * iters + backtracks) * dram_bytes / loop_s / 1e9 / 8000.0)
+        launches = sum(r.kernel_launches for r in flat)
+        loop_s = sum(r.times[r.iteration_count] - r.times[0] for r in flat)
+        backtracks = sum(r.backtracks for r in flat)
+    tot = torch.tensor([float(units), float(launches)], dtype=torch.float64, device=device)
+    if world > 1 and (w.scaling == "weak" or isinstance(w, BatchedWorkload)):
+        dist.all_reduce(tot)                    # replicas / column shards: every rank did its own units
+    units_all, launches_all = float(tot[0].item()), int(tot[1].item())
+    value = units_all / (ms_total / 1e3)
+    roofline = w.roofline(timer, outs, loop_s)
 
     # ---- end to end: host buffers in, host result out ---------------------------------------------
     e2e = None
     if not args.no_e2e:
-        pinned = True
-        try:
-            A_host = torch.empty(A.shape, dtype=torch.float64, pin_memory=True)
-        except Exception:
-            A_host = torch.empty(A.shape, dtype=torch.float64)
-            pinned = False
-        A_host.copy_(A)
-        b_host = b.cpu().pin_memory()
-        x0_host = torch.zeros(N, dtype=torch.float64).pin_memory()
-        sol_host = torch.empty(N, dtype=torch.float64).pin_memory()
+        w.e2e_prepare()
+        w.e2e_step()
+        e_outs, e_ms, _ = timed_region(w.e2e_step, args.steps)
+        e_units = torch.tensor([float(w.units(e_outs))], dtype=torch.float64, device=device)
+        if world > 1 and (w.scaling == "weak" or isinstance(w, BatchedWorkload)):
+            dist.all_reduce(e_units)
+        # what the copies alone allow: the H2D bytes of a step at the rate of a plain pinned copy, measured here
+        big = max((getattr(w, k, None) for k in ("A_host", "b_host")), key=lambda v: 0 if v is None else v.numel())
+        dst = torch.empty_like(big, device=device)
         torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        dst.copy_(big, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = big.numel() * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del dst
+        copy_ms = (w.h2d + w.d2h) / (h2d_gbs * 1e9) * 1e3
+        e2e = dict(value=float(e_units.item()) / (e_ms / 1e3), unit=w.unit, h2d_bytes_per_step=int(w.h2d * world),
+                   d2h_bytes_per_step=int(w.d2h * world), ms_per_step=e_ms / args.steps, pinned_host=bool(w.pinned),
+                   pcie_ceiling=dict(h2d_GBs_measured=h2d_gbs, copy_ms_per_step=copy_ms,
+                                     value_if_only_copies=float(e_units.item()) / args.steps / (copy_ms / 1e3),
+                                     note="upload and solve are not overlapped: the solver needs all of A for its first pass"))
 
-        def e2e_step():
-            A.copy_(A_host, non_blocking=True)          # reuse the resident buffers as upload targets
-            b_dev = b_host.to(device, non_blocking=True)
-            x_dev = x0_host.to(device, non_blocking=True)
-            op_, loss_, pen_ = build_objects(A, b_dev)
-            np.random.seed(0)
-            r = fasta.fasta(op_, loss_.f, loss_.gradf, pen_.g, pen_.prox, x_dev, **SOLVER_OPTS)
-            sol_host.copy_(r.solution, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return r
-
-        e2e_step()
-        e_outs, e_ms, _ = timed_region(e2e_step, args.steps)
-        e_iters = sum(r.iteration_count for r in e_outs)
-        e2e = dict(value=e_iters / (e_ms / 1e3), unit="iterations/s",
-                   h2d_bytes_per_step=int((A.numel() + b.numel() + N) * 8 * world),
-                   d2h_bytes_per_step=int(N * 8 * world), ms_per_step=e_ms / args.steps, pinned_host=pinned)
-
-    # ---- CPU baseline on the same problem (rank 0, N=1 only) --------------------------------------
+    # ---- CPU baseline + full-size parity on the same problem (rank 0; the CPU run does not depend on N) ----------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        A_np = A_host.numpy() if e2e is not None else A.cpu().numpy()
-        cpu = cpu_arm(w, A_np, b.cpu().numpy(), gpu_solve=lambda o: fasta.fasta(op, loss.f, loss.gradf, pen.g, pen.prox, x0, **o))
+    if not args.no_cpu_baseline:
+        if world == 1:
+            cpu = cpu_leg(w, ctx, gpu_check=True, max_iters=args.cpu_iters)
+        elif isinstance(w, DenseWorkload) and not isinstance(w, SmallLasso):
+            # N > 1: rank 0 rebuilds the whole problem on the host from the same seeded row chunks; every rank takes part
+            # in the sharded GPU solve that is checked against it
+            cpu = sharded_parity(w, ctx, args)
 
     if rank == 0:
-        line = dict(metric="lasso_fbs_iterations_per_sec", value=value, unit="iterations/s", n_gpus=world,
-                    steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps,
-                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                    config=config_of(w, world), roofline=roofline, cpu_baseline=cpu, e2e=e2e,
-                    gpu_launches=int(launches), clocks=clocks,
-                    iterations_per_solve=iters / args.steps, backtracks_per_solve=backtracks / args.steps,
-                    time_to_tol_ms=1e3 * loop_s / args.steps, iters_per_sec_in_loop=iters / loop_s,
+        line = dict(metric=w.metric, value=value, unit=w.unit, n_gpus=world, steps=args.steps, warmup=warm,
+                    ms_per_step=ms_total / args.steps, higher_is_better=True, scaling=w.scaling, vs_baseline=None, dtype="f64",
+                    data="synthetic", config=w.config(world), roofline=roofline, cpu_baseline=cpu, e2e=e2e,
+                    gpu_launches=int(launches_all), clocks=clocks,
+                    units_per_step=units_all / args.steps, backtracks_per_step=backtracks / args.steps,
+                    time_to_tol_ms=1e3 * loop_s / max(len(flat) if not isinstance(w, BatchedWorkload) else len(outs), 1),
+                    iters_per_sec_in_loop=(units / loop_s) * (world if (w.scaling == "weak" or isinstance(w, BatchedWorkload)) else 1),
                     wall_ms_per_step=1e3 * wall / args.steps)
-        line["final_residual"] = float(outs[-1].residuals[outs[-1].iteration_count - 1])
-        line["speculation"] = getattr(outs[-1], "speculation", None)
-        if world > 1:
-            line["collective"] = ("fused peer-memory all-reduce + BB epilogue kernel over NVLink (fb200_peer_allreduce_bb), "
-                                  f"{peer_reductions} calls in the timed region" if peer_reductions else "ncclAllReduce + bb kernel")
+        last = flat[-1]
+        line["final_residual"] = float(last.residuals[last.iteration_count - 1])
+        line["backend"] = dict(name=getattr(last, "backend", None), single_pass=getattr(last, "single_pass", None),
+                               resident=getattr(last, "resident", None), speculation=getattr(last, "speculation", None))
+        if isinstance(w, BatchedWorkload):
+            meta = outs[-1][0].batch
+            line["batched"] = dict(lockstep_iterations=meta["iterations_lockstep"], gemm=meta["gemm"], columns_this_rank=len(w.cols),
+                                   iterations_min_max=[int(min(r.iteration_count for r in outs[-1])), int(max(r.iteration_count for r in outs[-1]))])
+        if world > 1 and isinstance(w, DenseWorkload) and w.scaling == "strong":
+            peer = sum(getattr(r, "peer_reductions", 0) for r in flat)
+            line["collective"] = (f"fused peer-memory all-reduce + BB epilogue kernel over NVLink (fb200_peer_allreduce_bb), {peer} calls in "
+                                  f"the timed region" if peer else "ncclAllReduce + bb kernel")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_parity(w, ctx, args):
+    """N > 1: the row-sharded GPU solve against the reference run on rank 0's host (same seeded chunks, whole problem)."""
+    torch, dist = ctx.torch, ctx.dist
+    cpu = None
+    want = opts = None
+    bound = args.cpu_iters or None
+    if ctx.rank == 0:
+        threads, pools = blas_all_cores()
+        ref, kind, where = load_reference()
+        # whole problem on the host, chunk by chunk through this rank's GPU (same generator seeds as every shard)
+        A_host = np.empty((w.M, w.N))
+        b_host = np.empty(w.M)
+        full = type(w)(w.name, w.kind, w.M, w.N, w.K, w.mu, w.sigma, w.chunks)
+        full.ctx = ctx
+        parts = ctx.world
+        for p in range(parts):
+            A_p, b_p = full.local_problem(p, parts, ctx.device)
+            lo, hi = (w.M * p) // parts, (w.M * (p + 1)) // parts
+            A_host[lo:hi] = A_p.cpu().numpy()
+            b_host[lo:hi] = b_p.cpu().numpy()
+            del A_p, b_p
+        torch.cuda.empty_cache()
+        full.host_problem = lambda: (A_host, b_host)
+        want, rate, sample, opts = full.cpu_arm(ref, max_iters=bound)
+        cpu = dict(value=rate, unit=w.unit, cores=threads, kind=kind,
+                   sample=f"{where} (numpy {np.__version__}, BLAS pools {pools}, os.cpu_count()={os.cpu_count()}) on {sample}")
+    box = [opts]
+    dist.broadcast_object_list(box, src=0)
+    got = w.solve(box[0])                                         # every rank takes part
+    if ctx.rank == 0:
+        try:
+            cpu["parity_full_size"] = parity_block(got, want)
+        except Exception as exc:
+            cpu["parity_full_size"] = dict(error=repr(exc))
+    return cpu
 
 
 if __name__ == "__main__":

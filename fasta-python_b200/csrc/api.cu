@@ -24,16 +24,24 @@ int check_launch(const char* what) {
     return 0;
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return (dev < 0 || dev >= MAX_DEVICES) ? 0 : dev;
+}
+
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    static std::mutex m;
+    static int n[MAX_DEVICES] = {};
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(m);
+    if (n[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) {
             cudaGetLastError();
-            n = 148;   // B200
+            n[dev] = 148;   // B200
         }
     }
-    return n;
+    return n[dev];
 }
 
 size_t dense_partial_elems(int64_t M, int64_t N);

@@ -185,14 +185,15 @@ extern "C" int fb200_gemm_f64(int adjoint, const double* A, int64_t lda, const d
     }
     if (!adjoint && (K & 1)) { set_error("gemm_f64: forward product needs an even inner dimension"); return 1; }
     if (adjoint && (Mg & 1)) { set_error("gemm_f64: adjoint product needs an even output row count"); return 1; }
-    static bool attr_done[2] = {false, false};
+    static DeviceOnce attr_once[2];
     const int smem = gemm_smem(adjoint ? 1 : 0);
-    if (!attr_done[adjoint ? 1 : 0]) {
-        cudaError_t e = adjoint ? cudaFuncSetAttribute(batched_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                                : cudaFuncSetAttribute(batched_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) { set_error("gemm_f64: smem attribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return 1; }
-        attr_done[adjoint ? 1 : 0] = true;
-    }
+    if (attr_once[adjoint ? 1 : 0].run([&] {
+            cudaError_t e = adjoint ? cudaFuncSetAttribute(batched_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                    : cudaFuncSetAttribute(batched_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) { set_error("gemm_f64: smem attribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return 1; }
+            return 0;
+        }))
+        return 1;
     if (splits < 1) splits = 1;
     dim3 grid(unsigned((Ng + GB_BN - 1) / GB_BN), unsigned((Mg + GB_BM - 1) / GB_BM), unsigned(splits));
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/fasta_b200.h"
 
 namespace fb200 {
@@ -51,7 +53,25 @@ struct Workspace {
 
 void set_error(const char* fmt, ...);
 int  check_launch(const char* what);
-int  sm_count();
+int  sm_count();          // of the CURRENT device
+int  current_device();    // cudaGetDevice, clamped to [0, MAX_DEVICES)
+
+// One-time setup PER DEVICE (cudaFuncSetAttribute, occupancy queries and the plans derived from them belong to one
+// device's context; a process may solve on several devices, and ctypes releases the GIL, so callers may race).
+constexpr int MAX_DEVICES = 64;
+struct DeviceOnce {
+    std::mutex m;
+    bool       done[MAX_DEVICES] = {};
+    template <class F>
+    int run(F&& f) {          // f() returns 0 on success; a failure is retried by the next caller
+        const int dev = current_device();
+        std::lock_guard<std::mutex> lock(m);
+        if (done[dev]) return 0;
+        const int rc = f();
+        if (rc == 0) done[dev] = true;
+        return rc;
+    }
+};
 
 // grid for an n-element streaming kernel: enough blocks to fill the chip, capped so that the
 // reduction partials fit the workspace.  148 SMs x 8 resident 256-thread blocks = 1184.

@@ -291,15 +291,15 @@ static StreamPlan make_plan(int mode, int64_t M, int64_t N) {
 }
 
 static int ensure_smem_attr() {
-    static bool done = false;
-    if (done) return 0;
-    if (cudaFuncSetAttribute(dense_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(dense_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(max dynamic smem %d) failed: %s", SMEM_BYTES, cudaGetErrorString(cudaGetLastError()));
-        return 1;
-    }
-    done = true;
-    return 0;
+    static DeviceOnce once;
+    return once.run([] {
+        if (cudaFuncSetAttribute(dense_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(dense_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(max dynamic smem %d) failed: %s", SMEM_BYTES, cudaGetErrorString(cudaGetLastError()));
+            return 1;
+        }
+        return 0;
+    });
 }
 
 size_t dense_partial_elems(int64_t M, int64_t N) {

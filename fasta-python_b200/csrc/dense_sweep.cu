@@ -292,12 +292,17 @@ static int fill_launch(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, const
 
 // plan cache keyed by (N, M-independent) -- the occupancy query costs ~10 us, the attribute set more
 static SweepPlan make_sweep_plan(int loss, int64_t M, int64_t N) {
+    // (per device: the attributes set below and the occupancy answer belong to the current device's context)
+    static std::mutex mtx;
     static SweepPlan cache[3][64];
     static int64_t cache_n[3][64];
+    static int cache_dev[3][64];
     static int cache_used[3] = {0, 0, 0};
     const int li = loss == FB200_LOSS_LEAST_SQUARES ? 1 : (loss == FB200_LOSS_LOGISTIC ? 2 : 0);
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(mtx);
     for (int i = 0; i < cache_used[li]; ++i)
-        if (cache_n[li][i] == N) return cache[li][i];
+        if (cache_n[li][i] == N && cache_dev[li][i] == dev) return cache[li][i];
 
     SweepPlan p{};
     p.ok = false;
@@ -327,6 +332,7 @@ static SweepPlan make_sweep_plan(int loss, int64_t M, int64_t N) {
     }
     if (cache_used[li] < 64) {
         cache_n[li][cache_used[li]] = N;
+        cache_dev[li][cache_used[li]] = dev;
         cache[li][cache_used[li]++] = p;
     }
     (void)M;

@@ -497,12 +497,13 @@ extern "C" int fb200_ozaki_gemm(const void* LS, const double* lscale, int64_t Mg
     if (splits < 1) splits = 1;
     if (splits > nkb) splits = nkb;
     if (int64_t((nkb + splits - 1) / splits) * OZ_BK > OZ_MAX_KSPLIT) { set_error("ozaki_gemm: K split too long for exact int32 accumulation"); return 1; }
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
-        if (e != cudaSuccess) { set_error("ozaki_gemm: smem attribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return 1; }
-        attr_done = true;
-    }
+    static DeviceOnce attr_once;
+    if (attr_once.run([] {
+            cudaError_t e = cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+            if (e != cudaSuccess) { set_error("ozaki_gemm: smem attribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return 1; }
+            return 0;
+        }))
+        return 1;
     CUtensorMap mapA, mapX;
     if (oz_make_map(&mapA, LS, OZ_S * mpad, kpad, OZ_BM) || oz_make_map(&mapX, RS, OZ_S * npad, kpad, OZ_BN)) return 1;
     const int nblk_m = int(mpad / OZ_BM), nblk_n = int(npad / OZ_BN);

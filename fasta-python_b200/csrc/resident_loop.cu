@@ -436,12 +436,16 @@ extern "C" int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64
         kc = resident_kernel<true>(loss, prox, accelerate);
         csmem = resident_cluster_smem(M, N);
         // attributes and the placement query once per kernel and shared-memory size
+        // (per device: attributes and placement belong to the current device's context)
+        static std::mutex ok_mutex;
         static ResidentKernel ok_kernel[64];
         static size_t ok_smem[64];
-        static int ok_state[64], ok_count = 0;
+        static int ok_state[64], ok_dev[64], ok_count = 0;
+        const int dev = current_device();
+        std::lock_guard<std::mutex> ok_lock(ok_mutex);
         int state = -1;
         for (int i = 0; i < ok_count; ++i)
-            if (ok_kernel[i] == kc && ok_smem[i] == csmem) state = ok_state[i];
+            if (ok_kernel[i] == kc && ok_smem[i] == csmem && ok_dev[i] == dev) state = ok_state[i];
         if (state < 0) {
             cudaLaunchConfig_t probe{};
             cudaLaunchAttribute pattr[1];
@@ -457,7 +461,7 @@ extern "C" int fb200_resident_fbs(const double* A, int64_t lda, int64_t M, int64
                 cudaGetLastError();
                 state = 0;                              // this device cannot place the cluster: grid variant
             }
-            if (ok_count < 64) { ok_kernel[ok_count] = kc; ok_smem[ok_count] = csmem; ok_state[ok_count] = state; ++ok_count; }
+            if (ok_count < 64) { ok_kernel[ok_count] = kc; ok_smem[ok_count] = csmem; ok_state[ok_count] = state; ok_dev[ok_count] = dev; ++ok_count; }
         }
         if (!state) kc = nullptr;
     }

@@ -826,13 +826,14 @@ extern "C" int fb200_tv_iter_fused(const double* x0, const double* g0, double ta
     int grid = sm_count() * TVI_BLOCKS_PER_SM;
     if (grid > ntiles) grid = ntiles;
     if (grid > MAX_RED_BLOCKS) grid = MAX_RED_BLOCKS;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e1 = cudaFuncSetAttribute(tv_iter_kernel<FB200_LOSS_LEAST_SQUARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVI_SMEM);
-        cudaError_t e2 = cudaFuncSetAttribute(tv_iter_kernel<FB200_LOSS_LOGISTIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVI_SMEM);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("tv_iter_fused: smem attribute failed"); cudaGetLastError(); return 1; }
-        attr_done = true;
-    }
+    static DeviceOnce attr_once;
+    if (attr_once.run([] {
+            cudaError_t e1 = cudaFuncSetAttribute(tv_iter_kernel<FB200_LOSS_LEAST_SQUARES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVI_SMEM);
+            cudaError_t e2 = cudaFuncSetAttribute(tv_iter_kernel<FB200_LOSS_LOGISTIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TVI_SMEM);
+            if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("tv_iter_fused: smem attribute failed"); cudaGetLastError(); return 1; }
+            return 0;
+        }))
+        return 1;
     switch (loss) {
         case FB200_LOSS_LEAST_SQUARES:
             tv_iter_kernel<FB200_LOSS_LEAST_SQUARES><<<grid, TVI_THREADS, TVI_SMEM, st>>>((const double2*)x0, (const double2*)g0, tau, int(n0), int(n1), b, (double2*)x1, (double2*)g1, int(tx), ntiles, scal, w.red, w.counter);

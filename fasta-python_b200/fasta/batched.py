@@ -31,7 +31,7 @@ import numpy as np
 from . import _cabi, _device, linalg, losses, proximal, stopping
 from ._loop import Convergence, EPSILON
 
-__all__ = ["fasta_batched", "lasso_path"]
+__all__ = ["fasta_batched", "lasso_path", "column_shard", "lasso_path_sharded"]
 
 # measurement hook (tools/bench_batched.py): when set to a list, every GEMM appends
 # (start_event, end_event, adjoint, active_columns) recorded on the launching stream
@@ -467,13 +467,14 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
 
         with np.errstate(all="ignore"):
             resid = dx_norm / tau_cur
-            normalizer = np.maximum(np.sqrt(g0_sq), np.sqrt(xmxh_sq) / tau_cur) + EPSILON
+            na, nb = np.sqrt(g0_sq), np.sqrt(xmxh_sq) / tau_cur
+            normalizer = np.where(nb > na, nb, na) + EPSILON               # python max(a, b): a unless b > a (keeps a nan a)
             nresid = resid / normalizer
         resid_h[act, i] = resid[act]
         tau_h[act, i] = tau_cur[act]
         nresid_h[act, i] = nresid[act]
         f_h[act, i + 1] = f1[act]
-        max_resid[act] = np.maximum(max_resid[act], resid[act])
+        max_resid[act] = np.where(resid[act] > max_resid[act], resid[act], max_resid[act])     # python max(max_residual, resid)
         if evaluate_objective:
             obj = f1 + penalty.value(pen_raw)
             obj_h[act, i + 1] = obj[act]
@@ -509,7 +510,7 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
         c = Convergence(resid_h[j], nresid_h[j], tau_h[j], int(total_bt[j]), tj, n, sol,
                         obj_h[j] if evaluate_objective else None, None, None)
         results.append(c)
-    results_meta = dict(kernel_launches=st.launches, gemm_splits=(st.sf, st.sa), iterations_lockstep=i,
+    results_meta = dict(kernel_launches=st.launches, gemm_splits=(st.sf, st.sa), iterations_lockstep=i, loop_s=float(times[i] - times[0]),
                         fanout=dict(depth=fan, spare_columns=spare, rounds_with_fanout=fan_rounds, candidates_adopted_from_slots=fan_hits),
                         gemm="tcgen05-i8-digit-planes" if st.ozaki else "dmma-f64")
     for c in results:
@@ -525,3 +526,35 @@ def lasso_path(A, b, mus, x0=None, **options):
     if x0 is None:
         x0 = np.zeros((A.N, len(mus)))
     return fasta_batched(A, losses.LeastSquares(b), proximal.L1Norm(mus), x0, **options)
+
+
+def column_shard(n_columns, rank, world):
+    """Columns of a batch that rank ``rank`` of ``world`` solves: dealt round-robin, because neighbouring penalty
+    weights need about the same number of iterations (columns are independent units, no exchange)."""
+    return np.arange(int(rank), int(n_columns), int(world))
+
+
+def lasso_path_sharded(A, b, mus, group=None, gather=False, **options):
+    """The regularisation path split by columns over the ranks of ``group`` (one process per GPU, A replicated on every
+    GPU): each rank solves ``column_shard(len(mus), rank, world)`` with ``lasso_path``; nothing is exchanged during the
+    solve.  Returns ``(columns, results)`` of this rank, or with ``gather=True`` the full list of ``Convergence`` in
+    column order on every rank (solutions travel as host arrays)."""
+    import torch.distributed as dist
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+    mus = np.asarray(mus, dtype=np.float64)
+    cols = column_shard(len(mus), rank, world)
+    pad = len(cols) % 2 == 1                          # the batched kernels need an even width: duplicate the last column
+    local = mus[np.append(cols, cols[-1])] if pad else mus[cols]
+    res = lasso_path(A, b, local, **options)[:len(cols)]
+    if not gather or world == 1:
+        return cols, res
+    for r in res:
+        if hasattr(r.solution, "detach"):
+            r.solution = r.solution.detach().cpu().numpy()
+    box = [None] * world
+    dist.all_gather_object(box, (cols.tolist(), res), group=group)
+    full = [None] * len(mus)
+    for cs, rs in box:
+        for c, r in zip(cs, rs):
+            full[c] = r
+    return np.arange(len(mus)), full

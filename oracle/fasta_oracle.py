@@ -122,6 +122,10 @@ def solve(op, adj, f, gradf, g, proxg, x0, *, adaptive=True, accelerate=False, m
     if not L or not tau0:                                           # :100 (both needed to skip)
         L, tau0 = estimate_lipschitz(op, adj, gradf, x0.shape)
 
+    if verbose:                                                     # :118-120
+        print("Initializing FASTA...\n")
+        print("Iteration #\tResidual\tStepsize\tAccel. param\tBacktracks\tObjective")
+
     resid_h = np.zeros(max_iters)                                   # :123-127
     nresid_h = np.zeros(max_iters)
     tau_h = np.zeros(max_iters)
@@ -182,6 +186,8 @@ def solve(op, adj, f, gradf, g, proxg, x0, *, adaptive=True, accelerate=False, m
             alpha_prev = alpha_cur
             if restart and (x_prev - x_cur).ravel().T @ (x_cur - xa_prev).ravel() > 1e-30:
                 alpha_prev = 1.0
+                if verbose:                                         # :235
+                    print("Restarted acceleration.")
             alpha_cur = (1 + np.sqrt(1 + 4 * alpha_prev ** 2)) / 2
             x_cur = x_cur + (alpha_prev - 1) / alpha_cur * (xa_cur - xa_prev)
             z_cur = z_cur + (alpha_prev - 1) / alpha_cur * (za_cur - za_prev)
@@ -217,6 +223,11 @@ def solve(op, adj, f, gradf, g, proxg, x0, *, adaptive=True, accelerate=False, m
             fn_h[i + 1] = func(x_cur)
         if quality < best_q:
             best_x, best_q = x_cur, quality
+
+        if verbose:                                                 # :302-306 (alpha0; objective of the PREVIOUS iterate)
+            print("[{:<6}]\t{:e}\t{:e}\t{:e}\t{:6}\t{:e}".format(
+                i, resid_h[i], tau_h[i], alpha_prev if accelerate else 0.0, bt if backtrack else 0,
+                obj_h[i] if evaluate_objective else 0))
 
         if stop_rule(i, resid_h[i], nresid_h[i], max_resid, tolerance):   # :308-312
             i += 1

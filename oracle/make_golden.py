@@ -189,10 +189,47 @@ def run_options(ref):
     return out
 
 
+# The verbose text of fasta() (reference __init__.py:118-120 header, :235 restart notice, :302-306 one line per iteration):
+# (case, mode, extra options) -> the live reference's stdout, byte for byte.
+VERBOSE_SETS = [
+    ("lasso_200x1000_k50", "adaptive", {}),                              # backtracks column non-zero
+    ("lasso_200x1000_k50", "accelerated", {}),                           # alpha column, "Restarted acceleration."
+    ("lasso_200x1000_k50", "plain", dict(max_iters=25)),
+    ("logistic_1000x2000", "adaptive", {}),
+    ("lasso_200x1000_k10", "adaptive", dict(evaluate_objective=False)),  # objective column prints 0
+    ("lasso_200x1000_k10", "plain", dict(backtrack=False, max_iters=15)),
+    ("tv_64", "accelerated", dict(max_iters=30)),
+]
+
+
+def run_verbose(ref):
+    import contextlib
+    import io
+    out = dict(count=len(VERBOSE_SETS), numpy_version=np.__version__)
+    for k, (case, mode, extra) in enumerate(VERBOSE_SETS):
+        p = problems.build(case, 0)
+        apply, adjoint, vshape, wshape = problems.numpy_operator(p)
+        A = ref.linalg.LinearMap(apply, adjoint, vshape, wshape)
+        f, gradf, g, proxg = problems.numpy_callables(p)
+        opts = dict(problems.HARNESS_OPTS)
+        opts.update(problems.MODES[mode])
+        opts.update(extra)
+        opts["verbose"] = True
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf), np.errstate(all="ignore"):
+            res = ref.fasta(A, f, gradf, g, proxg, p.x0, **opts)
+        text = buf.getvalue()
+        out[f"case{k}"], out[f"mode{k}"], out[f"extra{k}"], out[f"text{k}"] = case, mode, repr(extra), text
+        out[f"n{k}"] = res.iteration_count
+        print(f"verbose {k} {case:22s} {mode:12s} {repr(extra):50s} iters={res.iteration_count:4d} lines={text.count(chr(10))} "
+              f"restarts={text.count('Restarted')}")
+    return out
+
+
 def main(argv):
     ref = ref_loader.load()
     os.makedirs(GOLDEN, exist_ok=True)
-    cases = [] if argv == ["options"] else (argv or (list(problems.CASES) + list(examples_extra.CASES)))
+    cases = [] if argv in (["options"], ["verbose"]) else (argv or (list(problems.CASES) + list(examples_extra.CASES)))
     for case in cases:
         for mode in problems.MODES:
             rec = run_extra(ref, case, mode) if case in examples_extra.CASES else run_case(ref, case, mode)
@@ -207,6 +244,8 @@ def main(argv):
         print("wrote prox / stopping known-answer vectors")
     if not argv or argv == ["options"]:
         np.savez_compressed(os.path.join(GOLDEN, "kat_options.npz"), **run_options(ref))
+    if not argv or argv == ["verbose"]:
+        np.savez_compressed(os.path.join(GOLDEN, "kat_verbose.npz"), **run_verbose(ref))
 
 
 if __name__ == "__main__":

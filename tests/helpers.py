@@ -58,10 +58,33 @@ def assert_trajectory(res, gold, sol_tol=1e-9, obj_tol=1e-10, hist_tol=1e-4, lab
         scale = np.maximum(np.abs(gold["objectives"]), floor * 1e-3)
         eo = float(np.max(np.abs(obj - gold["objectives"]) / scale))
         assert eo <= obj_tol, f"{label}: objective history rel err {eo:.3e}"
+    worst = 0.0
     for name in ("residuals", "stepsizes", "norm_residuals"):
         got = np.asarray(getattr(res, name))[:n]
         ref = gold[name]
         eh = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))) if n else 0.0
+        worst = max(worst, eh)
         assert eh <= hist_tol, f"{label}: {name} rel err {eh:.3e}"
+    if os.environ.get("FB200_RECORD_HIST"):          # developer aid: observed maxima, to set the per-case bars from
+        with open(os.environ["FB200_RECORD_HIST"], "a") as fh:
+            fh.write(f"{label}\t{worst:.3e}\t{e:.3e}\n")
     # arrays are full length and zero padded past iteration_count (SURVEY F-13)
     assert np.all(np.asarray(res.residuals)[n:] == 0)
+
+
+def assert_verbose_text(got, want, rtol=1e-5, label=""):
+    """The verbose text of fasta() against the live reference's stdout (reference __init__.py:118-120,235,302-306):
+    same lines in the same order, identical header / restart notices / iteration index / backtrack count, numeric
+    columns within ``rtol`` (``{:e}`` prints 7 significant digits; a different summation order can flip the last)."""
+    gl, wl = got.splitlines(), want.splitlines()
+    assert len(gl) == len(wl), f"{label}: {len(gl)} lines != {len(wl)}"
+    for k, (a, b) in enumerate(zip(gl, wl)):
+        if not b.startswith("["):
+            assert a == b, f"{label}: line {k}: {a!r} != {b!r}"
+            continue
+        fa, fb = a.split("\t"), b.split("\t")
+        assert len(fa) == len(fb) == 6 and fa[0] == fb[0] and fa[4] == fb[4], f"{label}: line {k}: {a!r} != {b!r}"
+        for ca, cb in zip(fa[1:4] + fa[5:], fb[1:4] + fb[5:]):
+            assert len(ca) == len(cb), f"{label}: line {k}: column width {ca!r} != {cb!r}"
+            va, vb = float(ca), float(cb)
+            assert abs(va - vb) <= rtol * abs(vb) + 1e-300, f"{label}: line {k}: {ca} != {cb}"

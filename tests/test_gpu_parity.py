@@ -395,3 +395,30 @@ def test_x0_not_mutated_and_torch_in_torch_out():
     assert torch.equal(x0, keep)
     assert isinstance(res.solution, torch.Tensor) and res.solution.is_cuda and res.solution.shape == x0.shape
     assert res.solution.data_ptr() != x0.data_ptr()
+
+
+def _verbose_sets():
+    import os
+    from conftest import GOLDEN
+    with np.load(os.path.join(GOLDEN, "kat_verbose.npz")) as z:
+        return [(str(z[f"case{k}"]), str(z[f"mode{k}"]), eval(str(z[f"extra{k}"])), str(z[f"text{k}"])) for k in range(int(z["count"]))]
+
+
+@pytest.mark.parametrize("k", range(7))
+@pytest.mark.parametrize("resident", ["1", "0"])
+def test_verbose_text_is_the_reference_stdout(k, resident, capsys, monkeypatch):
+    """F-12 on the GPU: the text fasta() prints (host-driven loop and device-resident loop) against the live
+    reference's captured stdout -- same lines, header, restart notices, indices and backtrack counts; numeric columns to
+    the printed precision."""
+    import fasta
+    from helpers import assert_verbose_text
+    case, mode, extra, text = _verbose_sets()[k]
+    monkeypatch.setenv("FASTA_B200_RESIDENT", resident)
+    p = problems.build(case, 0)
+    A, loss, pen = tagged(p)
+    opts = dict(problems.HARNESS_OPTS, **problems.MODES[mode])
+    opts.update(extra)
+    opts["verbose"] = True
+    capsys.readouterr()
+    fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **opts)
+    assert_verbose_text(capsys.readouterr().out, text, rtol=5e-6, label=f"{case}/{mode}/resident={resident}")

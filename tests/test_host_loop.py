@@ -5,7 +5,7 @@ import pytest
 
 from cpu_backend import backend_for
 from fasta import _loop
-from helpers import assert_trajectory, golden_cases, load_golden
+from helpers import assert_trajectory, assert_verbose_text, golden_cases, load_golden
 from oracle import problems
 
 CASES = golden_cases(exclude=("lasso_4000x10000_k500",))
@@ -181,3 +181,29 @@ def test_host_loop_option_semantics_match_reference(speculate, golden_dir):
         if f"iterates{k}" in g:
             np.testing.assert_allclose(res.iterates, g[f"iterates{k}"], rtol=0, atol=1e-9 * np.abs(g[f"iterates{k}"]).max())
             np.testing.assert_allclose(res.function_hist, g[f"function_hist{k}"], rtol=1e-9)
+
+
+def _verbose_sets():
+    import os
+    from conftest import GOLDEN
+    with np.load(os.path.join(GOLDEN, "kat_verbose.npz")) as z:
+        return [(str(z[f"case{k}"]), str(z[f"mode{k}"]), eval(str(z[f"extra{k}"])), str(z[f"text{k}"])) for k in range(int(z["count"]))]
+
+
+@pytest.mark.parametrize("k", range(7))
+@pytest.mark.parametrize("speculate", [False, True])
+def test_verbose_text_is_the_reference_stdout(k, speculate, capsys):
+    """F-12: what the product's host loop prints is the live reference's stdout: header, one line per iteration with the
+    PREVIOUS objective and alpha0, "Restarted acceleration." at the same places; the numeric columns agree to the
+    printed precision up to a flip of the last digit (the back-end forms its sums in its own order)."""
+    case, mode, extra, text = _verbose_sets()[k]
+    p = problems.build(case, 0)
+    opts = dict(problems.HARNESS_OPTS, **problems.MODES[mode])
+    opts.update(extra)
+    opts["verbose"] = True
+    be = backend_for(p, opts["accelerate"], speculate=speculate)
+    be.load()
+    capsys.readouterr()
+    with np.errstate(all="ignore"):
+        _loop.run(be, p.x0.shape, **opts)
+    assert_verbose_text(capsys.readouterr().out, text, rtol=2e-6, label=f"{case}/{mode}")

@@ -119,3 +119,24 @@ def test_oracle_option_semantics_match_reference_bitwise(golden_dir):
                 assert np.array_equal(got, want), (o, name)          # full-length arrays, zero padding included
             else:
                 np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12)
+
+
+def _verbose_sets():
+    import os
+    from conftest import GOLDEN
+    with np.load(os.path.join(GOLDEN, "kat_verbose.npz")) as z:
+        return [(str(z[f"case{k}"]), str(z[f"mode{k}"]), eval(str(z[f"extra{k}"])), str(z[f"text{k}"])) for k in range(int(z["count"]))]
+
+
+@pytest.mark.parametrize("k", range(7))
+def test_oracle_verbose_text_is_the_reference_stdout(k, capsys):
+    """F-12: header, per-iteration line and restart notice (reference __init__.py:118-120,235,302-306), byte for byte."""
+    case, mode, extra, text = _verbose_sets()[k]
+    p = problems.build(case, 0)
+    opts = dict(problems.HARNESS_OPTS, **problems.MODES[mode])
+    opts.update(extra)
+    opts["verbose"] = True
+    capsys.readouterr()
+    with np.errstate(all="ignore"):
+        fasta_oracle.solve_problem(p, **opts)
+    assert capsys.readouterr().out == text
