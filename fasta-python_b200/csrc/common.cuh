@@ -151,6 +151,43 @@ __device__ __forceinline__ void grid_sum(double (&v)[K], double* red, unsigned* 
     }
 }
 
+// The same, and tells the caller whether this block was the one that finished the sums (true for ALL its threads, after
+// thread 0 has written the totals): work that needs every total -- the loop's decisions -- continues there.
+template <int K>
+__device__ __forceinline__ bool grid_sum_last(double (&v)[K], double* red, unsigned* counter, double* const (&out)[K]) {
+    __shared__ double sm[K * 32];
+    __shared__ bool   is_last;
+    const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+    const unsigned nb  = gridDim.x * gridDim.y;
+    block_sum<K>(v, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) red[size_t(bid) * K + k] = v[k];
+        __threadfence();
+        unsigned t = atomicAdd(counter, 1u);
+        is_last    = (t == nb - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (unsigned b = threadIdx.x; b < nb; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] += __ldcg(&red[size_t(b) * K + k]);
+    }
+    block_sum<K>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (out[k]) *out[k] = acc[k];
+        *counter = 0u;   // re-arm for the next launch on this stream
+    }
+    __syncthreads();
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // loss / prox element functions (compiled with -fmad=false: one rounding per numpy operation)
 // ------------------------------------------------------------------------------------------------

@@ -16,9 +16,11 @@
 //   * A-group (8 warps): x slab in registers; per row: dot, block reduce, and ONE 16-byte store of the partial
 //     into the band's exchange ring in global memory -- two (32-bit half, 32-bit sequence flag) pairs, so each
 //     8-byte half validates itself (no fence, no second flag store);
-//   * exchange warp: lane k polls rank k's entry of the row (ld.relaxed.gpu, L2), the warp adds the S partials
-//     in a fixed butterfly -- every CTA of the band forms the bit-identical z_i --, lane 0 evaluates the loss
-//     once (r_i = gradf(z_i)) and hands r_i to the B-group through a shared-memory ring + mbarrier;
+//   * exchange warps (4, rows dealt round-robin): lane k polls rank k's entry of the row (ld.relaxed.gpu, L2), the
+//     warp adds the S partials in a fixed butterfly -- every CTA of the band forms the bit-identical z_i --, lane 0
+//     evaluates the loss once (r_i = gradf(z_i)) and hands r_i to the B-group through a shared-memory ring +
+//     mbarrier.  One warp would bound the kernel by its own latency per row (an L2 round trip or two + the loss:
+//     ~1 us, measured as a per-row time that did not shrink with the slab; 1.17 us with the logistic loss);
 //   * B-group (8 warps): g slab accumulators in registers; per row re-reads the slab from shared memory:
 //     g += A[i, slab] * r_i, then frees the stage;
 //   * each band writes its g partial; the Barzilai-Borwein epilogue adds the band partials in index order.
@@ -42,11 +44,12 @@ int launch_bb(int bb, const double* gsrc, int nsplit, int64_t ld, int64_t n, dou
               const double* xhat, const double* dx, double tau, double* scal, Workspace& w, cudaStream_t st);
 
 constexpr int GS_GROUP   = 256;                   // threads in the A-group and in the B-group
-constexpr int GS_THREADS = 2 * GS_GROUP + 64;     // + producer warp + exchange warp
+constexpr int GS_XWARPS  = 4;                     // exchange warps: warp w takes the rows it = w (mod GS_XWARPS) of the band
+constexpr int GS_THREADS = 2 * GS_GROUP + 32 + 32 * GS_XWARPS;     // + producer warp + exchange warps
 constexpr int GS_MAXSTG  = 8;
 constexpr int GS_RSLOT   = 16;                    // r_i ring between the exchange warp and the B-group (> NST)
 constexpr int GS_MAXS    = 32;                    // column slabs per band (one lane of the exchange warp each)
-constexpr int GS_TAIL    = 2 * 8 * 8 + GS_RSLOT * 8 + (2 * GS_MAXSTG + GS_RSLOT) * 8;    // redA + r ring + barriers
+constexpr int GS_TAIL    = 2 * 8 * 8 + GS_RSLOT * 8 + 2 * GS_XWARPS * 8 + (2 * GS_MAXSTG + GS_RSLOT) * 8;    // redA + r ring + loss partials + barriers
 constexpr int GS_SMEM_MAX = 227 * 1024;
 
 template <int LOSS>
@@ -105,7 +108,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1) dense_gsweep_kernel(const GsArg
     const int nstage = a.nstage;
     double*   redA  = reinterpret_cast<double*>(smem + size_t(nstage) * STAGE_BYTES);       // [2][8]
     double*   rring = redA + 16;                                                          // [RSLOT]
-    uint64_t* full  = reinterpret_cast<uint64_t*>(rring + GS_RSLOT);
+    double*   fsm   = rring + GS_RSLOT;                                                   // [2][XWARPS]
+    uint64_t* full  = reinterpret_cast<uint64_t*>(fsm + 2 * GS_XWARPS);
     uint64_t* empty = full + GS_MAXSTG;
     uint64_t* rfull = empty + GS_MAXSTG;                                                   // [RSLOT]
 
@@ -147,20 +151,20 @@ __global__ void __launch_bounds__(GS_THREADS, 1) dense_gsweep_kernel(const GsArg
                 if (++stage == nstage) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 2 * GS_GROUP / 32 + 1) {
-        // ===================================== exchange warp: z_i, loss, r_i ==========================
+    } else if (warp > 2 * GS_GROUP / 32) {
+        // ===================================== exchange warps: z_i, loss, r_i =========================
+        // One row costs a warp an L2 round trip or two (the poll) plus the loss; several warps keep several rows in
+        // flight.  The B-group consumes the rows in order through the r ring, whichever warp delivers them.
+        const int xw = warp - (2 * GS_GROUP / 32 + 1);
         const double* b = a.b;
         const double* za0 = a.za0;
         double facc = 0.0, facc2 = 0.0;
-        double bnext = (row_lo < row_hi && b) ? __ldg(b + row_lo) : 0.0;
-        double qnext = (row_lo < row_hi && za0) ? __ldg(za0 + row_lo) : 0.0;
-        for (int row = row_lo; row < row_hi; ++row) {
+        for (int row = row_lo + xw; row < row_hi; row += GS_XWARPS) {
             const int it = row - row_lo;
             const uint64_t flag = a.seq0 + uint64_t(it);
             const uint4* src = xband + size_t(it & (GS_XRING - 1)) * S + lane;
-            const double bi = bnext, qi = qnext;
-            if (row + 1 < row_hi && b) bnext = __ldg(b + row + 1);
-            if (row + 1 < row_hi && za0) qnext = __ldg(za0 + row + 1);
+            const double bi = b ? __ldg(b + row) : 0.0;          // issued before the poll: off the critical path
+            const double qi = za0 ? __ldg(za0 + row) : 0.0;
             double v = 0.0;
             bool ok = lane >= S;
             while (true) {
@@ -191,9 +195,15 @@ __global__ void __launch_bounds__(GS_THREADS, 1) dense_gsweep_kernel(const GsArg
                 }
             }
         }
-        if (rank == 0 && lane == 0) {
-            a.fpart[band] = facc;
-            if (za0) a.fpart2[band] = facc2;
+        if (rank == 0) {                                       // the warps' loss partials, added in warp order
+            if (lane == 0) { fsm[xw] = facc; fsm[GS_XWARPS + xw] = facc2; }
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * GS_XWARPS) : "memory");
+            if (xw == 0 && lane == 0) {
+                double f = 0.0, f2 = 0.0;
+                for (int k = 0; k < GS_XWARPS; ++k) { f = __dadd_rn(f, fsm[k]); f2 = __dadd_rn(f2, fsm[GS_XWARPS + k]); }
+                a.fpart[band] = f;
+                if (za0) a.fpart2[band] = f2;
+            }
         }
     } else if (warp < GS_GROUP / 32) {
         // ===================================== A-group: partial z = slab . x ==========================
@@ -376,10 +386,12 @@ bool gsweep_eligible(const double* A, int64_t lda, int64_t M, int64_t N) {
 static std::atomic<uint64_t> g_seq{1};
 
 // za0 != nullptr: FISTA mode; S_F then holds f at the prox point and S_AUX3 f at the extrapolated z
+// raw != nullptr: leave the band partials (gradient: w.dense[band][ldg], loss: w.fpart / w.fpart + FPART_MAX / 2) to the
+// caller's own epilogue (the row-sharded exchange kernel) and report their layout: raw[0] = bands, raw[1] = ldg
 int gsweep_launch(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss, const double* b,
                   double* z, double* r, double* g, int bb, const double* x0, const double* xhat, const double* dx,
                   double tau, double* scal, void* ws, size_t ws_bytes, void* stream, const double* za0,
-                  double* za1, double c) {
+                  double* za1, double c, int64_t* raw) {
     if (!gsweep_eligible(A, lda, M, N) || reinterpret_cast<uintptr_t>(x) % 16 != 0) {
         set_error("dense_gsweep: matrix not eligible (needs 16-byte aligned base and x, even lda and N)");
         return 1;
@@ -430,6 +442,11 @@ int gsweep_launch(const double* A, int64_t lda, int64_t M, int64_t N, const doub
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, k, a);
     if (e != cudaSuccess) { set_error("dense_gsweep: launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return 1; }
+    if (raw) {
+        raw[0] = p.bands;
+        raw[1] = ldg;
+        return 0;
+    }
     if (loss != FB200_LOSS_NONE) {
         if (za0) {
             gsweep_fsum_kernel<<<1, 32, 0, st>>>(a.fpart2, p.bands, scal + FB200_S_F, a.skip);       // prox point: the line-search value

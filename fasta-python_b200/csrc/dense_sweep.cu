@@ -352,7 +352,7 @@ int gsweep_plan(int64_t M, int64_t N, int* plan);
 int gsweep_launch(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss, const double* b,
                   double* z, double* r, double* g, int bb, const double* x0, const double* xhat, const double* dx,
                   double tau, double* scal, void* ws, size_t ws_bytes, void* stream, const double* za0,
-                  double* za1, double c);
+                  double* za1, double c, int64_t* raw);
 
 // FASTA_B200_SWEEP_KERNEL=cluster selects the cluster / DSMEM kernel of this file (the round-1 default)
 static bool use_grid_sweep() {
@@ -389,7 +389,7 @@ static int sweep_launch(const double* A, int64_t lda, int64_t M, int64_t N, cons
                         double tau, double* scal, void* ws, size_t ws_bytes, void* stream, const double* za0,
                         double* za1, double c) {
     if (use_grid_sweep())
-        return gsweep_launch(A, lda, M, N, x, loss, b, z, r, g, bb, x0, xhat, dx, tau, scal, ws, ws_bytes, stream, za0, za1, c);
+        return gsweep_launch(A, lda, M, N, x, loss, b, z, r, g, bb, x0, xhat, dx, tau, scal, ws, ws_bytes, stream, za0, za1, c, nullptr);
     if (!sweep_eligible(A, lda, M, N) || reinterpret_cast<uintptr_t>(x) % 16 != 0) {
         set_error("dense_sweep: matrix not eligible (needs 16-byte aligned base and x, even lda and N, N <= %d)", SW_MAXCS * SW_GROUP * 26);
         return 1;
@@ -436,6 +436,37 @@ extern "C" int fb200_dense_sweep(const double* A, int64_t lda, int64_t M, int64_
                                  const double* xhat, const double* dx, double tau, double* scal, void* ws,
                                  size_t ws_bytes, void* stream) {
     return sweep_launch(A, lda, M, N, x, loss, b, z, r, g, bb, x0, xhat, dx, tau, scal, ws, ws_bytes, stream, nullptr, nullptr, 0.0);
+}
+
+// ---- row-sharded map: the sweep on this rank's rows + ONE kernel that finishes it across the ranks -------------------
+namespace fb200 {
+int launch_peer_exchange(const uint64_t* peer_data, const uint64_t* peer_flags, int rank, int P, uint32_t epoch, int64_t n,
+                         const double* gsrc, int nsplit, int64_t ld, const double* fpart, const double* fpart2, int with_loss,
+                         double* g, int bb, const double* x0, const double* xhat, const double* dx, double tau,
+                         const int* decide_i, const double* decide_d, double* scal, Workspace& w, cudaStream_t st);
+}
+
+extern "C" int fb200_sweep_exchange_supported(void) { return use_grid_sweep() ? 1 : 0; }
+
+extern "C" int fb200_dense_sweep_exchange(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss,
+                                          const double* b, double* z, double* r, const double* za0, double c, double* za1,
+                                          const uint64_t* peer_data, const uint64_t* peer_flags, int rank, int P,
+                                          uint32_t epoch, double* g, int bb, const double* x0, const double* xhat,
+                                          const double* dx, double tau, const int* decide_i, const double* decide_d,
+                                          double* scal, void* ws, size_t ws_bytes, void* stream) {
+    if (!use_grid_sweep()) { set_error("dense_sweep_exchange: needs the grid sweep kernel"); return 1; }
+    if (P < 1 || P > FB200_MAX_PEERS || rank < 0 || rank >= P) { set_error("dense_sweep_exchange: bad rank / world size"); return 1; }
+    int64_t raw[2] = {0, 0};
+    if (gsweep_launch(A, lda, M, N, x, loss, b, z, r, nullptr, 0, nullptr, nullptr, nullptr, isnan(tau) ? tau : 0.0, scal, ws, ws_bytes,
+                      stream, za0, za1, c, raw))
+        return 1;
+    Workspace w(ws);
+    const int with_loss = loss == FB200_LOSS_NONE ? 0 : (za0 ? 2 : 1);
+    // FISTA mode: fpart2 holds the loss at the prox point (the line-search value, S_F), fpart at the extrapolated point (S_AUX3)
+    const double* f_first = za0 ? w.fpart + FPART_MAX / 2 : w.fpart;
+    const double* f_second = za0 ? w.fpart : nullptr;
+    return launch_peer_exchange(peer_data, peer_flags, rank, P, epoch, N, w.dense, int(raw[0]), raw[1], f_first, f_second, with_loss,
+                                g, bb, x0, xhat, dx, tau, decide_i, decide_d, scal, w, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int fb200_dense_sweep_accel(const double* A, int64_t lda, int64_t M, int64_t N, const double* xa1, int loss,

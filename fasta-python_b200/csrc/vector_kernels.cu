@@ -407,27 +407,30 @@ __global__ void decide_init_kernel(double* scal, double f0, double g0_sq) {
     scal[FB200_S_FRING] = f0;
 }
 
-__global__ void trial_decide_kernel(double* scal, double tau, int loss, int adaptive, int backtrack, int bt,
-                                    int max_backtracks, int window, int stop_rule, double tolerance, int host_it,
-                                    double host_max_residual, double host_g0_sq) {
+struct DecideArgs {
+    int loss, adaptive, backtrack, bt, max_backtracks, window, stop_rule, host_it;
+    double tolerance, host_max_residual, host_g0_sq;
+};
+
+__device__ void decide_core(double* scal, double tau, const DecideArgs& d) {
     const bool speculative = isnan(tau);
     if (speculative && scal[FB200_S_SKIP] != 0.0) { scal[FB200_S_SKIPPED] = 1.0; return; }
     scal[FB200_S_SKIPPED] = 0.0;
     if (!speculative) {                                     // a trial queued by value carries the host's loop state
-        scal[FB200_S_IT] = double(host_it);
-        scal[FB200_S_MAXRES] = host_max_residual;
-        scal[FB200_S_G0SQ] = host_g0_sq;
+        scal[FB200_S_IT] = double(d.host_it);
+        scal[FB200_S_MAXRES] = d.host_max_residual;
+        scal[FB200_S_G0SQ] = d.host_g0_sq;
     }
     const double tau0 = speculative ? scal[FB200_S_TAU] : tau;
     scal[FB200_S_TAU_USED] = tau0;
     const double raw = scal[FB200_S_F];
-    const double f1 = (loss == FB200_LOSS_LEAST_SQUARES) ? .5 * dd_sq(raw) : raw;
+    const double f1 = (d.loss == FB200_LOSS_LEAST_SQUARES) ? .5 * dd_sq(raw) : raw;
     const int it = int(scal[FB200_S_IT]);
     const double dx_sq = scal[FB200_S_DX_SQ];
-    if (backtrack && bt < max_backtracks) {
+    if (d.backtrack && d.bt < d.max_backtracks) {
         double fmax_w = -INFINITY;
         bool has_nan = false;
-        for (int k = (it - window + 1 > 0 ? it - window + 1 : 0); k <= it; ++k) {
+        for (int k = (it - d.window + 1 > 0 ? it - d.window + 1 : 0); k <= it; ++k) {
             const double v = scal[FB200_S_FRING + k % FB200_FRING];
             if (isnan(v)) has_nan = true;
             fmax_w = fmax(fmax_w, v);
@@ -440,7 +443,7 @@ __global__ void trial_decide_kernel(double* scal, double tau, int loss, int adap
     }
     const double dx_norm = sqrt(dx_sq);
     double tau1 = tau0;
-    if (adaptive) {
+    if (d.adaptive) {
         const double dotprod = scal[FB200_S_DX_DG];
         const double tau_s = (dx_norm * dx_norm) / dotprod;
         const double q = dotprod / dd_sq(scal[FB200_S_DG_SQ]);
@@ -454,11 +457,11 @@ __global__ void trial_decide_kernel(double* scal, double tau, int loss, int adap
     const double nresid = resid / normalizer;
     const double max_residual = dd_pymax(scal[FB200_S_MAXRES], resid);
     bool stop = false;
-    switch (stop_rule) {
-        case 0: stop = resid < tolerance; break;
-        case 1: stop = nresid < tolerance; break;
-        case 2: stop = resid / max_residual < tolerance; break;
-        case 3: stop = (resid / max_residual < tolerance) || (nresid < tolerance); break;
+    switch (d.stop_rule) {
+        case 0: stop = resid < d.tolerance; break;
+        case 1: stop = nresid < d.tolerance; break;
+        case 2: stop = resid / max_residual < d.tolerance; break;
+        case 3: stop = (resid / max_residual < d.tolerance) || (nresid < d.tolerance); break;
         default: break;
     }
     scal[FB200_S_FRING + (it + 1) % FB200_FRING] = f1;
@@ -467,6 +470,147 @@ __global__ void trial_decide_kernel(double* scal, double tau, int loss, int adap
     scal[FB200_S_G0SQ] = scal[FB200_S_G1_SQ];
     scal[FB200_S_TAU] = tau1;
     scal[FB200_S_SKIP] = stop ? 1.0 : 0.0;
+}
+
+__global__ void trial_decide_kernel(double* scal, double tau, DecideArgs d) { decide_core(scal, tau, d); }
+
+// =================================================================================================
+// Row-sharded map, ONE kernel for what follows the local sweep (reference __init__.py:248,254-260,195-201,253-281 on the
+// row-partitioned map of SURVEY.md 8e): sum of this rank's band partials -> this rank's slice of the exchange buffer
+// (NVLink-mapped on every peer) -> per-chunk flags to the peers -> wait for the peers' flags of the same chunk -> read
+// their partials over NVLink, add in rank order (bit-identical g on every rank) -> Barzilai-Borwein sums -> and in the
+// block that finishes last the loop's decisions (fb200_trial_decide).  Block c owns chunk c of the N-vector from its
+// first instruction to its last, so the exchange of chunk c overlaps the band sums of the chunks behind it and nobody
+// waits for the whole vector: there is no barrier between "produce" and "consume", only one flag per (rank, chunk).
+//   flags[src][chunk] (32-bit, in every rank's mapped buffer) = epoch of the last call whose chunk `chunk` rank `src`
+//   finished writing; epochs grow by one per call on every rank, a waiter accepts any epoch >= its own.
+//   Two data slots alternate: a rank rewrites a slot two calls later, which it can only reach after every peer has
+//   signalled the call in between, i.e. finished reading (same argument as the two-buffer barrier scheme before).
+// All blocks of a rank must be resident (a block spins on its peers' flags): the grid is PEER_CHUNKS <= #SMs blocks.
+// =================================================================================================
+constexpr int PEER_CHUNKS = 128;
+
+struct PeerPtrs {
+    double*   data[FB200_MAX_PEERS];     // this call's slot of rank k's exchange buffer: n doubles + 2 loss partials
+    uint32_t* flags[FB200_MAX_PEERS];    // rank k's flag table [P][PEER_CHUNKS]
+};
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int BB>
+__global__ void __launch_bounds__(VEC_THREADS)
+peer_exchange_kernel(PeerPtrs pp, int rank, int P, uint32_t epoch, int64_t n, const double* __restrict__ gsrc, int nsplit,
+                     int64_t ld, const double* __restrict__ fpart, const double* __restrict__ fpart2, int with_loss,
+                     double* __restrict__ g, const double* __restrict__ x0, const double* __restrict__ xhat,
+                     const double* __restrict__ dx, double tau, int decide, DecideArgs dargs, double* scal, double* red,
+                     unsigned* counter) {
+    if (isnan(tau)) {                                       // speculative trial: see fb200_trial_decide
+        if (__ldcg(&scal[FB200_S_SKIP]) != 0.0) {
+            if (decide && blockIdx.x == 0 && threadIdx.x == 0) decide_core(scal, tau, dargs);    // reports S_SKIPPED
+            return;
+        }
+    }
+    const double tau_v = isnan(tau) ? __ldcg(&scal[FB200_S_TAU]) : tau;
+    const int c = blockIdx.x;
+    const int64_t per = ((n + PEER_CHUNKS - 1) / PEER_CHUNKS + 1) / 2 * 2;      // even: chunks start 16-byte aligned
+    const int64_t lo = int64_t(c) * per, hi = (lo + per < n) ? lo + per : n;
+    double* mine = pp.data[rank];
+    // 1. this rank's partial of the chunk: the band partials of the local sweep in index order
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        double gi = __ldcg(&gsrc[i]);
+        for (int k = 1; k < nsplit; ++k) gi += __ldcg(&gsrc[int64_t(k) * ld + i]);
+        mine[i] = gi;
+    }
+    if (c == 0 && threadIdx.x == 0 && with_loss) {
+        double f = 0.0;
+        for (int k = 0; k < nsplit; ++k) f += __ldcg(&fpart[k]);
+        mine[n] = f;
+        if (with_loss >= 2) {
+            double f2 = 0.0;
+            for (int k = 0; k < nsplit; ++k) f2 += __ldcg(&fpart2[k]);
+            mine[n + 1] = f2;
+        }
+    }
+    __syncthreads();
+    // 2. tell every peer that chunk c of this rank is complete, 3. wait for theirs
+    if (threadIdx.x < P && threadIdx.x != rank) {
+        __threadfence_system();
+        st_release_sys_u32(pp.flags[threadIdx.x] + rank * PEER_CHUNKS + c, epoch);
+        const uint32_t* f = pp.flags[rank] + threadIdx.x * PEER_CHUNKS + c;
+        while (int32_t(ld_acquire_sys_u32(f) - epoch) < 0) {}
+    }
+    __syncthreads();
+    // 4. g = sum over ranks in rank order, Barzilai-Borwein sums
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        double gi = ld_relaxed_sys_f64(pp.data[0] + i);
+        for (int k = 1; k < P; ++k) gi += ld_relaxed_sys_f64(pp.data[k] + i);
+        g[i] = gi;
+        if (BB >= 1) s[2] += gi * gi;
+        if (BB >= 2) {
+            const double dg = gi + (xhat[i] - x0[i]) / tau_v;   // __init__.py:254
+            s[0] += dx[i] * dg;                                  // :255
+            s[1] += dg * dg;                                     // :260
+        }
+    }
+    if (with_loss && c == 0 && threadIdx.x == 0) {
+        double f = ld_relaxed_sys_f64(pp.data[0] + n);
+        for (int k = 1; k < P; ++k) f += ld_relaxed_sys_f64(pp.data[k] + n);
+        scal[FB200_S_F] = f;
+        if (with_loss >= 2) {                               // FISTA sweep: second loss partial (extrapolated point)
+            double f2 = ld_relaxed_sys_f64(pp.data[0] + n + 1);
+            for (int k = 1; k < P; ++k) f2 += ld_relaxed_sys_f64(pp.data[k] + n + 1);
+            scal[FB200_S_AUX3] = f2;
+        }
+    }
+    double* const out[3] = {BB >= 2 ? scal + FB200_S_DX_DG : nullptr, BB >= 2 ? scal + FB200_S_DG_SQ : nullptr,
+                            BB >= 1 ? scal + FB200_S_G1_SQ : nullptr};
+    const bool last = grid_sum_last<3>(s, red, counter, out);
+    if (last && decide && threadIdx.x == 0) {
+        __threadfence();                                    // block 0's S_F precedes its ticket; ours came after
+        decide_core(scal, tau, dargs);
+    }
+}
+
+int launch_peer_exchange(const uint64_t* peer_data, const uint64_t* peer_flags, int rank, int P, uint32_t epoch, int64_t n,
+                         const double* gsrc, int nsplit, int64_t ld, const double* fpart, const double* fpart2, int with_loss,
+                         double* g, int bb, const double* x0, const double* xhat, const double* dx, double tau,
+                         const int* decide_i, const double* decide_d, double* scal, Workspace& w, cudaStream_t st) {
+    PeerPtrs pp;
+    for (int k = 0; k < FB200_MAX_PEERS; ++k) {
+        pp.data[k] = reinterpret_cast<double*>(peer_data[k < P ? k : 0]);
+        pp.flags[k] = reinterpret_cast<uint32_t*>(peer_flags[k < P ? k : 0]);
+    }
+    DecideArgs d{};
+    const int decide = decide_i ? 1 : 0;
+    if (decide) {
+        d.loss = decide_i[0]; d.adaptive = decide_i[1]; d.backtrack = decide_i[2]; d.bt = decide_i[3]; d.max_backtracks = decide_i[4];
+        d.window = decide_i[5]; d.stop_rule = decide_i[6]; d.host_it = decide_i[7];
+        d.tolerance = decide_d[0]; d.host_max_residual = decide_d[1]; d.host_g0_sq = decide_d[2];
+        if (d.window > FB200_FRING) { set_error("peer_exchange: window %d exceeds the device ring (%d)", d.window, FB200_FRING); return 1; }
+    }
+    if (sm_count() < PEER_CHUNKS) { set_error("peer_exchange: needs %d resident blocks", PEER_CHUNKS); return 1; }
+#define FB200_PEERX(BBV) peer_exchange_kernel<BBV><<<PEER_CHUNKS, VEC_THREADS, 0, st>>>(pp, rank, P, epoch, n, gsrc, nsplit, ld, fpart, fpart2, with_loss, g, x0, xhat, dx, tau, decide, d, scal, w.red, w.counter)
+    switch (bb) {
+        case 0: FB200_PEERX(0); break;
+        case 1: FB200_PEERX(1); break;
+        case 2: FB200_PEERX(2); break;
+        default: set_error("unknown bb mode %d", bb); return 1;
+    }
+#undef FB200_PEERX
+    return check_launch("peer_exchange");
 }
 
 // =================================================================================================
@@ -656,9 +800,11 @@ extern "C" int fb200_trial_decide(double* scal, double tau, int loss, int adapti
                                   double host_max_residual, double host_g0_sq, void* stream) {
     if (!scal) { set_error("trial_decide: null scalar block"); return 1; }
     if (window < 1 || window > FB200_FRING) { set_error("trial_decide: window %d not in 1..%d", window, FB200_FRING); return 1; }
-    trial_decide_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(scal, tau, loss, adaptive, backtrack, bt,
-                                                                        max_backtracks, window, stop_rule, tolerance,
-                                                                        host_it, host_max_residual, host_g0_sq);
+    DecideArgs d{};
+    d.loss = loss; d.adaptive = adaptive; d.backtrack = backtrack; d.bt = bt; d.max_backtracks = max_backtracks;
+    d.window = window; d.stop_rule = stop_rule; d.host_it = host_it;
+    d.tolerance = tolerance; d.host_max_residual = host_max_residual; d.host_g0_sq = host_g0_sq;
+    trial_decide_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(scal, tau, d);
     return check_launch("trial_decide");
 }
 

@@ -182,6 +182,9 @@ class ShardedDriver:
     _peer_cache = {}
     peer_ok = os.environ.get("FASTA_B200_PEER", "1") != "0"
 
+    PEER_CHUNKS = 128          # csrc/vector_kernels.cu: blocks (= flag words per rank) of the exchange kernel
+    fused_ok = os.environ.get("FASTA_B200_FUSED_EXCHANGE", "1") != "0"
+
     def _peer(self, n, device):
         key = (id(self.group), int(n), device.index)
         if key in ShardedDriver._peer_cache:
@@ -194,14 +197,18 @@ class ShardedDriver:
                 import torch.distributed._symmetric_memory as symm
                 t = _device.torch()
                 pitch = (int(n) + 8 + 1) // 2 * 2
-                buf = symm.empty(2 * pitch, dtype=t.float64, device=device)
+                P0 = self.dist.get_world_size(self.group)
+                flag_doubles = P0 * self.PEER_CHUNKS // 2            # P x 128 32-bit words behind the two data slots
+                buf = symm.empty(2 * pitch + flag_doubles, dtype=t.float64, device=device)
                 hdl = symm.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
                 P = hdl.world_size
                 ptrs = [(ctypes.c_uint64 * P)(*[int(hdl.buffer_ptrs[k]) + 8 * pitch * slot for k in range(P)])
                         for slot in (0, 1)]
+                flags = (ctypes.c_uint64 * P)(*[int(hdl.buffer_ptrs[k]) + 8 * 2 * pitch for k in range(P)])
                 buf.zero_()
                 hdl.barrier(channel=0)
-                st = dict(buf=buf, hdl=hdl, P=P, pitch=pitch, ptrs=ptrs, calls=0)
+                st = dict(buf=buf, hdl=hdl, P=P, pitch=pitch, ptrs=ptrs, flags=flags, calls=0, rank=int(hdl.rank),
+                          di=(ctypes.c_int * 8)(), dd=(ctypes.c_double * 3)())
         except Exception as exc:                       # no peer mapping on this system: NCCL path below
             import warnings
             warnings.warn(f"fasta-b200: peer-memory all-reduce unavailable ({exc}); using ncclAllReduce")
@@ -209,8 +216,56 @@ class ShardedDriver:
         ShardedDriver._peer_cache[key] = st
         return st
 
-    def sweep(self, x, loss_tag, b, z, r, g, bb, x0, xhat, dx, tau, ws):
+    # -- fused path (csrc: fb200_dense_sweep_exchange): the local sweep and ONE kernel that sums the band partials into
+    # the mapped buffer, signals / awaits the peers chunk by chunk, adds the P partials in rank order, forms the BB sums
+    # and takes the loop's decisions -- no scalar copy, no barrier kernel, no separate all-reduce / decide launches
+    def _fused(self, g):
+        if not (self.fused_ok and g.is_cuda and self.sweep_ok and hasattr(self.local, "A")):
+            return None
+        peer = self._peer(g.numel(), g.device)
+        if peer is None or not self.local.lib.fb200_sweep_exchange_supported():
+            return None
+        return peer
+
+    @property
+    def fuses_decide(self):
+        """Whether sweep(..., decide=...) takes the loop's decisions itself (then no fb200_trial_decide follows)."""
+        t = _device.torch()
+        probe = getattr(self, "_fused_probe", None)
+        if probe is None:
+            A = getattr(self.local, "A", None)
+            probe = self._fused_probe = bool(A is not None and A.is_cuda and self.fused_ok and self.sweep_ok
+                                             and self._peer(self.local.N, A.device) is not None
+                                             and self.local.lib.fb200_sweep_exchange_supported())
+        return probe
+
+    def _sweep_exchange(self, peer, x, loss_tag, b, z, r, za0, c, za1, g, bb, x0, xhat, dx, tau, ws, decide):
+        peer["calls"] += 1
+        epoch = peer["calls"]
+        di = dd = None
+        if decide is not None:
+            di, dd = peer["di"], peer["dd"]
+            di[:] = [int(v) for v in decide[:8]]
+            dd[:] = [float(v) for v in decide[8:11]]
+        L = self.local
+        _cabi.check(L.lib.fb200_dense_sweep_exchange(L.A.data_ptr(), L.lda, L.M, L.N, x.data_ptr(), loss_tag, _device.ptr(b),
+                                                     z.data_ptr(), _device.ptr(r), _device.ptr(za0), float(c), _device.ptr(za1),
+                                                     peer["ptrs"][epoch & 1], peer["flags"], peer["rank"], peer["P"],
+                                                     epoch & 0xFFFFFFFF, g.data_ptr(), int(bb), _device.ptr(x0),
+                                                     _device.ptr(xhat), _device.ptr(dx), float(tau), di, dd,
+                                                     ws.scal.data_ptr(), ws.buf.data_ptr(), ws.nbytes, _device.stream_ptr()),
+                    "fb200_dense_sweep_exchange")
+        L.launches += 2
+        self.collectives += 1
+        self.peer_reductions += 1
+
+    def sweep(self, x, loss_tag, b, z, r, g, bb, x0, xhat, dx, tau, ws, decide=None):
         n = g.numel()
+        fused = self._fused(g)
+        if fused is not None:
+            self._sweep_exchange(fused, x, loss_tag, b, z, r, None, 0.0, None, g, bb, x0, xhat, dx, tau, ws, decide)
+            return
+        assert decide is None
         peer = self._peer(n, g.device) if g.is_cuda else None
         if peer is not None:
             slot = peer["calls"] & 1
@@ -251,6 +306,10 @@ class ShardedDriver:
         """FISTA mode of the single pass on the row shard (see DenseDriver.sweep_accel): the partial gradient and BOTH
         loss partials (prox point: line search; extrapolated point) are summed over the ranks in one exchange."""
         n = g.numel()
+        fused = self._fused(g)
+        if fused is not None:
+            self._sweep_exchange(fused, xa1, loss_tag, b, z, r, za0, c, za1, g, bb, x0, xhat, dx, tau, ws, None)
+            return
         peer = self._peer(n, g.device) if g.is_cuda else None
         if peer is not None:
             slot = peer["calls"] & 1
@@ -585,6 +644,7 @@ class FusedBackend:
             p0, p1 = self.pen.params(tau)
         st = self._st()
         kind = None
+        fused_decide = None
         if self.use_tv_fused and self.drv.iter_fused_ok:
             # one kernel per trial; the gradient of an accepted trial is already in G[gc] (speculative, like the sweep)
             self.drv.iterate_fused(x0, g0, tau, self.loss.tag, self.loss.b, x1, self.G[self.gc], self.ws)
@@ -606,14 +666,23 @@ class FusedBackend:
                         "fb200_fbs_step")
             self.launches += 1
             if self.use_sweep:
-                self.drv.sweep(x1, self.loss.tag, self.loss.b, z1, self.R, self.G[self.gc], 2, x0, self.XH, self.DX, tau,
-                               self.ws)
+                if self._spec_mode and getattr(self.drv, "fuses_decide", False):
+                    # row-sharded driver: the exchange kernel behind the sweep also takes the loop's decisions
+                    fused_decide = self._decide[:3] + (int(bt),) + self._decide[3:6] + (int(host[0]), self._decide[6],
+                                                                                         float(host[1]), float(host[2]))
+                    self.drv.sweep(x1, self.loss.tag, self.loss.b, z1, self.R, self.G[self.gc], 2, x0, self.XH, self.DX, tau,
+                                   self.ws, decide=fused_decide)
+                else:
+                    self.drv.sweep(x1, self.loss.tag, self.loss.b, z1, self.R, self.G[self.gc], 2, x0, self.XH, self.DX, tau,
+                                   self.ws)
                 kind = "sweep"
             else:
                 self.drv.forward(x1, self.loss.tag, self.loss.b, z1, self.R, self.ws)
                 kind = "forward"
         if not self._spec_mode:
             return kind, None
+        if fused_decide is not None:
+            return kind, self.ws.snapshot()
         loss_tag, adaptive, backtrack, max_bt, window, rule, tol = self._decide
         _cabi.check(self.lib.fb200_trial_decide(self.ws.scal.data_ptr(), float(tau), loss_tag, adaptive, backtrack, int(bt),
                                                 max_bt, window, rule, tol, int(host[0]), float(host[1]), float(host[2]),

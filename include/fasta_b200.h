@@ -340,6 +340,27 @@ int fb200_dot(const double* a, const double* b, int64_t n, double* out, void* ws
 int fb200_diff_nrm2sq(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream);
 int fb200_asum(const double* a, int64_t n, double* out, void* ws, void* stream);
 
+/* ---- row-sharded map, fused: the single-pass sweep on this rank's rows followed by ONE kernel that finishes it across
+ * the ranks (csrc/dense_sweep.cu, vector_kernels.cu: peer_exchange_kernel) -- band-partial sum into this rank's slice of
+ * the NVLink-mapped exchange buffer, per-chunk flags to the peers, wait for theirs, sum over ranks in rank order, BB
+ * sums, and (decide_i != NULL) the decisions of fb200_trial_decide in the block that finishes last.  Replaces
+ * {fb200_dense_sweep, scalar copy, barrier, fb200_peer_allreduce_bb, fb200_trial_decide} of the row-sharded iteration
+ * (reference __init__.py:187-188,248,254-260 on SURVEY.md 8e's partition).
+ *   peer_data[k]   address in THIS process of rank k's data slot for this call: N doubles + 2 loss partials
+ *                  (two slots alternate from call to call);  peer_data[rank] is this rank's own
+ *   peer_flags[k]  address of rank k's flag table: P x 128 32-bit words, zero-initialised, never written by the host
+ *   epoch          call counter, identical on every rank, +1 per call (also for calls that return at once)
+ *   za0 / c / za1  NULL / 0 / NULL, or the FISTA mode of fb200_dense_sweep_accel
+ *   decide_i       {loss, adaptive, backtrack, bt, max_backtracks, window, stop_rule, host_it} or NULL
+ *   decide_d       {tolerance, host_max_residual, host_g0_sq}                                                      */
+int fb200_sweep_exchange_supported(void);
+int fb200_dense_sweep_exchange(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss,
+                               const double* b, double* z, double* r, const double* za0, double c, double* za1,
+                               const uint64_t* peer_data, const uint64_t* peer_flags, int rank, int P, uint32_t epoch,
+                               double* g, int bb, const double* x0, const double* xhat, const double* dx, double tau,
+                               const int* decide_i, const double* decide_d, double* scal, void* ws, size_t ws_bytes,
+                               void* stream);
+
 /* ---- np.random.randn on the device (csrc/legacy_rng.cu) --------------------------------------------------------
  * Replaces `x1 = np.random.randn(*x0.shape); x2 = np.random.randn(*x0.shape)` (reference fasta/__init__.py:102-103):
  * continues numpy's legacy MT19937 + polar-method Gaussian stream bit for bit from `state` and returns the state

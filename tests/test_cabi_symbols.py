@@ -90,10 +90,10 @@ def test_ctypes_signatures_match_the_header_prototypes():
             return "ptr"
         base = re.sub(r"\b(const|unsigned)\b", "", d).split()
         base = base[0] if base else ""
-        return {"double": "double", "int": "int", "int64_t": "i64", "size_t": "size", "void": "void"}[base]
+        return {"double": "double", "int": "int", "int64_t": "i64", "size_t": "size", "void": "void", "uint32_t": "u32"}[base]
 
     of_ctype = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_double: "double", ctypes.c_int: "int",
-                ctypes.c_int64: "i64", ctypes.c_size_t: "size"}
+                ctypes.c_int64: "i64", ctypes.c_size_t: "size", ctypes.c_uint32: "u32"}
     protos = re.findall(r"(?m)^\s*((?:const\s+)?[A-Za-z_0-9]+\s*\**)\s*(fb200_[a-zA-Z0-9_]+)\s*\(([^;{]*?)\)\s*;", nocomment)
     assert len(protos) >= 40
     seen = set()

@@ -1,5 +1,8 @@
-"""GPU, two ranks: the row-sharded solve with the fused peer-memory all-reduce + BB kernel (NVLink) must follow
-the same golden trajectory as the single-GPU path.  Skipped on boxes with fewer than two GPUs."""
+"""GPU, two / four ranks: the row-sharded solve must follow the same golden trajectory as the single-GPU path with
+each of its three exchanges -- "fused": the sweep followed by ONE kernel of ours that sums, signals, awaits and reduces
+over NVLink peer memory chunk by chunk and takes the loop's decisions (fb200_dense_sweep_exchange); "peer": barrier +
+fb200_peer_allreduce_bb; "nccl": ncclAllReduce + bb kernel.  Lasso (incl. backtracks, FISTA) and logistic losses.
+Skipped on boxes with too few GPUs."""
 import os
 import socket
 
@@ -15,11 +18,16 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, mode, peer, out):
+EXCHANGES = {"fused": dict(FASTA_B200_PEER="1", FASTA_B200_FUSED_EXCHANGE="1"),
+             "peer": dict(FASTA_B200_PEER="1", FASTA_B200_FUSED_EXCHANGE="0"),
+             "nccl": dict(FASTA_B200_PEER="0", FASTA_B200_FUSED_EXCHANGE="0")}
+
+
+def _worker(rank, world, port, case, mode, exchange, out):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [root, os.path.join(root, "fasta-python_b200"), os.path.join(root, "tests")]
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), FASTA_B200_PEER="1" if peer else "0")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), **EXCHANGES[exchange])
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -31,27 +39,30 @@ def _worker(rank, world, port, case, mode, peer, out):
     p = problems.build(case, int(gold["seed"]))
     rows = fasta.distributed.row_slice(p.A.shape[0], rank, world)
     A = fasta.distributed.RowShardedMatrix(np.ascontiguousarray(p.A[rows]))
-    loss, pen = fasta.losses.LeastSquares(p.b[rows]), fasta.proximal.L1Norm(p.mu)
+    Loss = fasta.losses.Logistic if p.loss == "logistic" else fasta.losses.LeastSquares
+    loss, pen = Loss(p.b[rows]), fasta.proximal.L1Norm(p.mu)
     res = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, p.x0, **gold["opts"])
     if rank == 0:
         np.savez(out, iteration_count=res.iteration_count, backtracks=res.backtracks, solution=res.solution,
                  objectives=res.objectives, residuals=res.residuals, stepsizes=res.stepsizes,
-                 norm_residuals=res.norm_residuals, peer=res.peer_reductions, single_pass=res.single_pass)
+                 norm_residuals=res.norm_residuals, peer=res.peer_reductions, single_pass=res.single_pass,
+                 launches=res.kernel_launches)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("peer", [True, False])
-@pytest.mark.parametrize("case,mode", [("lasso_200x1000_k50", "adaptive"), ("lasso_4000x10000_k500", "adaptive"),
-                                       ("lasso_200x1000_k10", "plain"), ("lasso_200x1000_k50", "accelerated"),
-                                       ("lasso_4000x10000_k500", "accelerated")])
-def test_two_rank_sharded_solve_matches_golden(case, mode, peer, tmp_path):
+CASES = [("lasso_200x1000_k50", "adaptive"), ("lasso_4000x10000_k500", "adaptive"), ("lasso_200x1000_k10", "plain"),
+         ("lasso_200x1000_k50", "accelerated"), ("lasso_4000x10000_k500", "accelerated"),
+         ("logistic_1000x2000", "adaptive"), ("logistic_1000x2000", "accelerated")]
+
+
+def _run(world, case, mode, exchange, tmp_path):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from helpers import assert_trajectory, load_golden
     out = str(tmp_path / "rank0.npz")
-    mp.spawn(_worker, args=(2, _free_port(), case, mode, peer, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), case, mode, exchange, out), nprocs=world, join=True)
     with np.load(out) as z:
         class R:
             pass
@@ -60,5 +71,17 @@ def test_two_rank_sharded_solve_matches_golden(case, mode, peer, tmp_path):
             setattr(res, k, z[k])
         res.iteration_count, res.backtracks = int(res.iteration_count), int(res.backtracks)
     assert bool(res.single_pass)
-    assert (int(res.peer) > 0) == peer
-    assert_trajectory(res, load_golden(case, mode), label=f"2-rank/{case}/{mode}/peer={peer}")
+    assert (int(res.peer) > 0) == (exchange != "nccl")
+    assert_trajectory(res, load_golden(case, mode), label=f"{world}-rank/{case}/{mode}/{exchange}")
+    return res
+
+
+@pytest.mark.parametrize("exchange", list(EXCHANGES))
+@pytest.mark.parametrize("case,mode", CASES)
+def test_two_rank_sharded_solve_matches_golden(case, mode, exchange, tmp_path):
+    _run(2, case, mode, exchange, tmp_path)
+
+
+@pytest.mark.parametrize("case,mode", [CASES[0], CASES[1], CASES[4], CASES[5]])
+def test_four_rank_sharded_solve_matches_golden(case, mode, tmp_path):
+    _run(4, case, mode, "fused", tmp_path)
