@@ -312,6 +312,9 @@ class DenseWorkload:
     def instrument(self, timer):
         from fasta import _backends
         timer.wrap(_backends.DenseDriver, "sweep", "sweep")
+        # row-sharded, fused path: the sweep and the exchange kernel behind it are queued by one C call; the events
+        # bracket both (the exchange is ~1 % of the pair)
+        timer.wrap(_backends.ShardedDriver, "_sweep_exchange", "sweep")
         timer.wrap(_backends.DenseDriver, "forward", "stream")
         timer.wrap(_backends.DenseDriver, "adjoint", "stream")
 
@@ -353,6 +356,8 @@ class DenseWorkload:
             traffic = tj.get(self.name, {}).get("gsweep_dram_bytes_per_launch" if single_pass else "stream_dram_bytes_per_launch")
         name = ("dense_gsweep_kernel (single pass: z = A x, loss, g = A^T r in ONE read of A; one launch per iteration covers the "
                 "reference's two contractions)" if single_pass else "dense_stream_kernel (A x and A^T r, one launch each per iteration)")
+        if single_pass and self.ctx.world > 1:
+            name += " + peer_exchange_kernel (band sums, NVLink exchange, BB sums, decisions), timed as a pair"
         dram_gbs = dram_bytes / (avg * 1e-3) / 1e9
         return dict(bound="hbm", kernel=name, achieved=dram_gbs, peak=peak, unit="GB/s", frac=dram_gbs / peak, traffic=traffic,
                     peak_source=src, dram_bytes_per_launch=dram_bytes, avg_launch_ms=avg, launches_timed=len(live),
@@ -997,8 +1002,8 @@ def main():
                                    iterations_min_max=[int(min(r.iteration_count for r in outs[-1])), int(max(r.iteration_count for r in outs[-1]))])
         if world > 1 and isinstance(w, DenseWorkload) and w.scaling == "strong":
             peer = sum(getattr(r, "peer_reductions", 0) for r in flat)
-            line["collective"] = (f"fused peer-memory all-reduce + BB epilogue kernel over NVLink (fb200_peer_allreduce_bb), {peer} calls in "
-                                  f"the timed region" if peer else "ncclAllReduce + bb kernel")
+            line["collective"] = (f"our own exchange over NVLink peer memory ({'fb200_dense_sweep_exchange: sweep + one exchange kernel' if os.environ.get('FASTA_B200_FUSED_EXCHANGE', '1') != '0' else 'barrier + fb200_peer_allreduce_bb'}), "
+                                  f"{peer} calls in the timed region" if peer else "ncclAllReduce + bb kernel")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

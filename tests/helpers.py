@@ -38,13 +38,32 @@ def rel_err(a, b):
     return float(np.linalg.norm((a - b).ravel()) / den)
 
 
-def assert_trajectory(res, gold, sol_tol=1e-9, obj_tol=1e-10, hist_tol=1e-4, label=""):
+# Residual / step-size histories: the bar each case actually needs.  Observed maxima on B200 (round 2, every path:
+# fused, resident, two-pass, speculative, generic, legacy forms; tests run with FB200_RECORD_HIST=file):
+#   lasso_200x1000_k50 / adaptive   8.6e-7   (80 iterations, 5 backtracks: BB amplifies last-bit differences of the sums)
+#   generic / adaptive (same case)  2.0e-7
+#   mmv_20x30x10 / adaptive         4.4e-8
+#   everything else                 <= 5.1e-10
+HIST_TOL_DEFAULT = 1e-8
+HIST_TOL = (("lasso_200x1000_k50/adaptive", 1e-5), ("generic/adaptive", 5e-6), ("mmv_20x30x10/adaptive", 1e-6))
+
+
+def hist_tol_for(label):
+    for key, tol in HIST_TOL:
+        if key in label:
+            return tol
+    return HIST_TOL_DEFAULT
+
+
+def assert_trajectory(res, gold, sol_tol=1e-9, obj_tol=1e-10, hist_tol=None, label=""):
     """The parity bar of BASELINE.json: identical iteration and backtrack counts, final iterate
     within 1e-9 relative, objective history within 1e-10 relative (measured against the scale of
     the initial objective so that objectives decaying to ~0, e.g. NNLS, are compared in absolute
     terms relative to the problem scale).  The residual / step-size histories are not part of that
     bar (near convergence they amplify last-bit differences of the reductions by ~1e9); they are
-    sanity-checked at ``hist_tol``."""
+    checked at ``hist_tol`` (default: per case, see HIST_TOL)."""
+    if hist_tol is None:
+        hist_tol = hist_tol_for(label)
     n = gold["iteration_count"]
     assert res.iteration_count == n, f"{label}: iterations {res.iteration_count} != {n}"
     assert res.backtracks == gold["backtracks"], f"{label}: backtracks {res.backtracks} != {gold['backtracks']}"

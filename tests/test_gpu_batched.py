@@ -90,7 +90,7 @@ def test_multi_rhs_batch_with_backtracking_columns(gemm, monkeypatch):
     np.random.seed(3)
     out = fasta.batched.fasta_batched(p.A, fasta.losses.LeastSquares(bs), fasta.proximal.L1Norm(p.mu),
                                       np.zeros((p.A.shape[1], Bn)), **opts)
-    total_bt, strict = 0, 0
+    total_bt, strict, checked = 0, 0, 0
     for j in range(Bn):
         o = dict(opts, accelerate=False)
         ref = _oracle_column(p, p.mu, bs[:, j], o, 3)
@@ -110,6 +110,9 @@ def test_multi_rhs_batch_with_backtracking_columns(gemm, monkeypatch):
         strict += (sol_tol == 1e-9 and obj_tol == 1e-10)
         _check(out[j], ref, f"rhs[{j}]", sol_tol=sol_tol, obj_tol=obj_tol)
         total_bt += ref.backtracks
+        checked += 1
+    # at most one column may be left out as "the reference does not reproduce itself under reordering"
+    assert checked >= Bn - 1, f"only {checked} of {Bn} columns were checkable"
     assert total_bt > 0 and strict >= 2
 
 
