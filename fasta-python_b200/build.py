@@ -19,6 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE]
+COMMON += os.environ.get("FB200_NVCC_DEFS", "").split()        # developer experiments: extra -D switches
 
 # (source, extra flags)
 UNITS = [

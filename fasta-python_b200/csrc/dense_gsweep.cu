@@ -44,7 +44,10 @@ int launch_bb(int bb, const double* gsrc, int nsplit, int64_t ld, int64_t n, dou
               const double* xhat, const double* dx, double tau, double* scal, Workspace& w, cudaStream_t st);
 
 constexpr int GS_GROUP   = 256;                   // threads in the A-group and in the B-group
-constexpr int GS_XWARPS  = 4;                     // exchange warps: warp w takes the rows it = w (mod GS_XWARPS) of the band
+#ifndef FB200_GS_XWARPS
+#define FB200_GS_XWARPS 1      // measured (M x N = 40000 x 100000 / 5000 x 100000): 1 warp 4.62 / 0.59 ms, 2 warps 5.59 / 0.68, 4 warps 5.62 / 0.69
+#endif
+constexpr int GS_XWARPS  = FB200_GS_XWARPS;       // exchange warps: warp w takes the rows it = w (mod GS_XWARPS) of the band
 constexpr int GS_THREADS = 2 * GS_GROUP + 32 + 32 * GS_XWARPS;     // + producer warp + exchange warps
 constexpr int GS_MAXSTG  = 8;
 constexpr int GS_RSLOT   = 16;                    // r_i ring between the exchange warp and the B-group (> NST)
@@ -52,19 +55,21 @@ constexpr int GS_MAXS    = 32;                    // column slabs per band (one 
 constexpr int GS_TAIL    = 2 * 8 * 8 + GS_RSLOT * 8 + 2 * GS_XWARPS * 8 + (2 * GS_MAXSTG + GS_RSLOT) * 8;    // redA + r ring + loss partials + barriers
 constexpr int GS_SMEM_MAX = 227 * 1024;
 
+// gradient and value of the loss at one row, separately: the B-group waits for r_i = gradf(z_i), nobody waits for f
 template <int LOSS>
-__device__ __forceinline__ void gs_loss(double z, double b, double& r, double& f) {
-    if (LOSS == FB200_LOSS_LEAST_SQUARES) {
-        r = __dsub_rn(z, b);
-        f = __dmul_rn(r, r);
-    } else if (LOSS == FB200_LOSS_LOGISTIC) {
+__device__ __forceinline__ double gs_grad(double z, double b) {
+    if (LOSS == FB200_LOSS_LEAST_SQUARES) return __dsub_rn(z, b);
+    if (LOSS == FB200_LOSS_LOGISTIC) return __ddiv_rn(-b, __dadd_rn(1.0, exp(__dmul_rn(b, z))));
+    return z;           // LOSS_NONE: "gradient" is z itself (g = A^T A x)
+}
+template <int LOSS>
+__device__ __forceinline__ double gs_fval(double z, double b) {
+    if (LOSS == FB200_LOSS_LEAST_SQUARES) { const double r = __dsub_rn(z, b); return __dmul_rn(r, r); }
+    if (LOSS == FB200_LOSS_LOGISTIC) {
         const double ind = (b == 1.0) ? 1.0 : 0.0;
-        f = __dsub_rn(log(__dadd_rn(1.0, exp(z))), __dmul_rn(ind, z));
-        r = __ddiv_rn(-b, __dadd_rn(1.0, exp(__dmul_rn(b, z))));
-    } else {
-        r = z;      // LOSS_NONE: "gradient" is z itself (g = A^T A x), f unused
-        f = 0.0;
+        return __dsub_rn(log(__dadd_rn(1.0, exp(z))), __dmul_rn(ind, z));
     }
+    return 0.0;
 }
 
 // An exchange entry is {lo32(v), lo32(seq), hi32(v), hi32(seq) + 1}: each 8-byte half carries its own piece of the
@@ -158,8 +163,12 @@ __global__ void __launch_bounds__(GS_THREADS, 1) dense_gsweep_kernel(const GsArg
         const int xw = warp - (2 * GS_GROUP / 32 + 1);
         const double* b = a.b;
         const double* za0 = a.za0;
-        double facc = 0.0, facc2 = 0.0;
-        for (int row = row_lo + xw; row < row_hi; row += GS_XWARPS) {
+        // loss VALUES are off the critical path: lane (k mod 32) keeps the k-th row of this warp and every 32 rows all
+        // lanes evaluate theirs in one pass (the logistic log(1 + e^z) costs ~0.25 us if done serially per row)
+        double facc = 0.0, facc2 = 0.0, zkeep = 0.0, zikeep = 0.0, bkeep = 0.0;
+        bool kept = false;
+        int k = 0;
+        for (int row = row_lo + xw; row < row_hi; row += GS_XWARPS, ++k) {
             const int it = row - row_lo;
             const uint64_t flag = a.seq0 + uint64_t(it);
             const uint4* src = xband + size_t(it & (GS_XRING - 1)) * S + lane;
@@ -174,25 +183,39 @@ __global__ void __launch_bounds__(GS_THREADS, 1) dense_gsweep_kernel(const GsArg
             if (lane >= S) v = 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);    // same tree on every CTA of the band
+            const double zi = v;
+            const double ze = za0 ? __dadd_rn(zi, __dmul_rn(a.cacc, __dsub_rn(zi, qi))) : zi;   // p + c*(p - za0), as accel_step
             if (lane == 0) {
-                const double zi = v;
-                const double ze = za0 ? __dadd_rn(zi, __dmul_rn(a.cacc, __dsub_rn(zi, qi))) : zi;   // p + c*(p - za0), as accel_step
-                double ri, fi;
-                gs_loss<LOSS>(ze, bi, ri, fi);
+                const double ri = gs_grad<LOSS>(ze, bi);
                 const int slot = it & (GS_RSLOT - 1);
                 rring[slot] = ri;
                 mbar_arrive(&rfull[slot]);                     // release: the B-group's wait orders the read of rring
                 if (rank == 0) {
-                    facc = __dadd_rn(facc, fi);
                     a.z[row] = ze;
                     if (LOSS != FB200_LOSS_NONE) a.r[row] = ri;
-                    if (za0) {                                 // f at the prox point (line search) and the prox image itself
-                        double rp, fp;
-                        gs_loss<LOSS>(zi, bi, rp, fp);
-                        facc2 = __dadd_rn(facc2, fp);
-                        a.za1[row] = zi;
+                    if (za0) a.za1[row] = zi;                  // the prox image itself
+                }
+            }
+            if (rank == 0 && LOSS != FB200_LOSS_NONE) {
+                if (lane == (k & 31)) { zkeep = ze; zikeep = zi; bkeep = bi; kept = true; }
+                if ((k & 31) == 31) {
+                    if (kept) {
+                        facc = __dadd_rn(facc, gs_fval<LOSS>(zkeep, bkeep));
+                        if (za0) facc2 = __dadd_rn(facc2, gs_fval<LOSS>(zikeep, bkeep));   // f at the prox point (line search)
+                        kept = false;
                     }
                 }
+            }
+        }
+        if (rank == 0 && LOSS != FB200_LOSS_NONE) {
+            if (kept) {
+                facc = __dadd_rn(facc, gs_fval<LOSS>(zkeep, bkeep));
+                if (za0) facc2 = __dadd_rn(facc2, gs_fval<LOSS>(zikeep, bkeep));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {                   // fixed tree over the lanes
+                facc = __dadd_rn(facc, __shfl_xor_sync(0xffffffffu, facc, o));
+                facc2 = __dadd_rn(facc2, __shfl_xor_sync(0xffffffffu, facc2, o));
             }
         }
         if (rank == 0) {                                       // the warps' loss partials, added in warp order

@@ -72,6 +72,32 @@ __device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_
     return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
 
+// new block n[0..624) from the old block o[0..624); threads 0..226 make three words each: word i + 624 depends on words
+// i, i + 1, i + 397, so the "far" input of a thread's second word is its first, of its third its second -- its own
+// results -- and ONE barrier per block (by the caller) suffices.  Word 623 also needs the NEW word 0 (thread 0's): it is
+// recomputed from old words instead of waiting for it.  out != nullptr receives the tempered words.
+__device__ __forceinline__ void mt_regen_block(const uint32_t* o, uint32_t* n, uint32_t* out, int tid) {
+    if (tid < MT_LAG) {
+        const uint32_t v0 = mt_twist(o[tid], o[tid + 1], o[tid + MT_M]);
+        n[tid] = v0;
+        const int i1 = tid + MT_LAG;
+        const uint32_t v1 = mt_twist(o[i1], o[i1 + 1], v0);
+        n[i1] = v1;
+        const int i2 = tid + 2 * MT_LAG;
+        uint32_t v2 = 0;
+        if (i2 < MT_N) {
+            const uint32_t nxt = (i2 == MT_N - 1) ? mt_twist(o[0], o[1], o[MT_M]) : o[i2 + 1];
+            v2 = mt_twist(o[i2], nxt, v1);
+            n[i2] = v2;
+        }
+        if (out) {
+            out[tid] = mt_temper(v0);
+            out[i1] = mt_temper(v1);
+            if (i2 < MT_N) out[i2] = mt_temper(v2);
+        }
+    }
+}
+
 // One CTA.  d[0 .. c0) = tempered rest of the entry block, then nb regenerated blocks of 624 words.
 __global__ void __launch_bounds__(256, 1)
 mt_stream_kernel(const uint32_t* __restrict__ state, long long want_words, uint32_t* __restrict__ d, RngMeta* meta) {
@@ -94,27 +120,107 @@ mt_stream_kernel(const uint32_t* __restrict__ state, long long want_words, uint3
     uint32_t* out = d + c0;
     int cur = 0;
     for (long long b = 0; b < nb; ++b, cur ^= 1, out += MT_N) {
-        const uint32_t* o = buf[cur];
-        uint32_t* n = buf[cur ^ 1];
-        if (tid < MT_LAG) {
-            // thread tid makes words tid, tid + 227 and tid + 454 of the new block: the "far" input of the second is the
-            // first, of the third the second -- its own results, so ONE barrier per block suffices.  Word 623 also needs
-            // the NEW word 0 (thread 0's): it is recomputed here from old words instead of waiting for it.
-            const uint32_t v0 = mt_twist(o[tid], o[tid + 1], o[tid + MT_M]);
-            n[tid] = v0;
-            out[tid] = mt_temper(v0);
-            const int i1 = tid + MT_LAG;
-            const uint32_t v1 = mt_twist(o[i1], o[i1 + 1], v0);
-            n[i1] = v1;
-            out[i1] = mt_temper(v1);
-            const int i2 = tid + 2 * MT_LAG;
-            if (i2 < MT_N) {
-                const uint32_t nxt = (i2 == MT_N - 1) ? mt_twist(o[0], o[1], o[MT_M]) : o[i2 + 1];
-                const uint32_t v2 = mt_twist(o[i2], nxt, v1);
-                n[i2] = v2;
-                out[i2] = mt_temper(v2);
+        mt_regen_block(buf[cur], buf[cur ^ 1], out, tid);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same stream from MANY thread blocks (large draws: the two 33.5M-element probes of a 4096^2 TV solve are 274k
+// MT19937 blocks -- 35 ms each from one CTA).  MT19937's words satisfy a linear recurrence over GF(2) with a
+// characteristic polynomial phi of degree 19937, so  y[n + J] = XOR_{j : g_j = 1} y[n + j]  with g = t^J mod phi
+// (Haramoto et al. 2008): a CTA that holds 19937 + 623 consecutive words (33 blocks) produces the block J words
+// further on by a 19937-tap XOR convolution.  tools/make_mt_jump.py computes g for the strides 64 * 16^level * digit
+// blocks (fasta/mt19937_jump.npz, verified against numpy); segment s starts s * seg_units * 64 blocks into the
+// stream and is reached with one jump per non-zero hexadecimal digit of s * seg_units.
+//   y[n] = untempered word n after the entry block;  d[c0 + n] = temper(y[n]).
+// ---------------------------------------------------------------------------------------------------
+constexpr int MTJ_PREFIX = 33;                       // blocks a CTA holds: 33 * 624 = 20592 >= 19937 + 623 words
+constexpr int MTJ_UNIT = 64;                         // blocks per stride unit of the polynomial table
+constexpr int MTJ_LEVELS = 4, MTJ_DIGITS = 16;
+constexpr int MTJ_SMEM = (MTJ_PREFIX * MT_N + 2 * MT_N) * 4;      // prefix + polynomial + jumped block
+constexpr long long MTJ_PARALLEL_MIN_BLOCKS = 2048;  // below ~0.5M draws one CTA is as fast as the jumps
+
+__global__ void __launch_bounds__(256, 2)
+mt_parallel_stream_kernel(const uint32_t* __restrict__ state, const uint32_t* __restrict__ polys, long long want_words,
+                          int seg_units, uint32_t* __restrict__ d, RngMeta* meta) {
+    extern __shared__ __align__(16) uint32_t mtj_smem[];
+    uint32_t* pre  = mtj_smem;                       // [33][624], flat: pre[k] = y[J + k]
+    uint32_t* g    = pre + MTJ_PREFIX * MT_N;        // [624] polynomial words
+    uint32_t* knew = g + MT_N;                       // [624] jumped block
+    const int tid = threadIdx.x;
+    const int pos = int(state[MT_N]);
+    const long long c0 = MT_N - pos;
+    const long long nb = want_words > c0 ? (want_words - c0 + MT_N - 1) / MT_N : 0;
+    const long long seg_blocks = (long long)seg_units * MTJ_UNIT;
+    const long long b_lo = (long long)blockIdx.x * seg_blocks;
+    if (blockIdx.x == 0) {
+        if (tid == 0) {
+            meta->c0 = c0;
+            meta->wtot = c0 + nb * MT_N;
+            meta->tries_used = 0ull;
+            meta->gauss = 0.0;
+            meta->has_gauss = 0u;
+            meta->fail = 0u;
+        }
+        for (int i = tid; i < c0; i += blockDim.x) d[i] = mt_temper(state[pos + i]);
+    }
+    if (b_lo >= nb) return;
+    const long long b_hi = (b_lo + seg_blocks < nb) ? b_lo + seg_blocks : nb;
+    // prefix of the stream: y[0 .. 33 * 624)
+    for (int i = tid; i < MT_N; i += blockDim.x) knew[i] = state[i];
+    __syncthreads();
+    mt_regen_block(knew, pre, nullptr, tid);
+    __syncthreads();
+    for (int b = 1; b < MTJ_PREFIX; ++b) {
+        mt_regen_block(pre + (b - 1) * MT_N, pre + b * MT_N, nullptr, tid);
+        __syncthreads();
+    }
+    // one jump per non-zero hexadecimal digit of the segment's offset (in units of 64 blocks)
+    const unsigned U = unsigned(blockIdx.x) * unsigned(seg_units);
+    for (int level = 0; level < MTJ_LEVELS; ++level) {
+        const unsigned digit = (U >> (4 * level)) & 15u;
+        if (digit == 0) continue;                                              // uniform over the block
+        const uint32_t* gp = polys + (size_t(level) * MTJ_DIGITS + digit) * MT_N;
+        for (int i = tid; i < MT_N; i += blockDim.x) g[i] = gp[i];
+        __syncthreads();
+        const int i0 = tid, i1 = tid + 256, i2 = tid + 512;
+        uint32_t a0 = 0, a1 = 0, a2 = 0;
+        const bool has2 = i2 < MT_N;
+        for (int jw = 0; jw < MT_N; ++jw) {
+            uint32_t gw = g[jw];                                               // the same word in every thread: no divergence
+            const uint32_t* base = pre + 32 * jw;
+            while (gw) {
+                const int j = __ffs(gw) - 1;
+                gw &= gw - 1;
+                a0 ^= base[i0 + j];
+                a1 ^= base[i1 + j];
+                if (has2) a2 ^= base[i2 + j];
             }
         }
+        knew[i0] = a0;
+        knew[i1] = a1;
+        if (has2) knew[i2] = a2;
+        __syncthreads();
+        for (int i = tid; i < MT_N; i += blockDim.x) pre[i] = knew[i];
+        __syncthreads();
+        for (int b = 1; b < MTJ_PREFIX; ++b) {
+            mt_regen_block(pre + (b - 1) * MT_N, pre + b * MT_N, nullptr, tid);
+            __syncthreads();
+        }
+    }
+    // the segment: its first 33 blocks are at hand, the rest is regenerated block by block in the prefix area
+    uint32_t* out = d + c0 + b_lo * MT_N;
+    const long long have = (b_hi - b_lo < MTJ_PREFIX) ? b_hi - b_lo : MTJ_PREFIX;
+    for (long long k = tid; k < have * MT_N; k += blockDim.x) out[k] = mt_temper(pre[k]);
+    out += have * MT_N;
+    if (b_lo + have >= b_hi) return;
+    for (int i = tid; i < MT_N; i += blockDim.x) knew[i] = pre[(MTJ_PREFIX - 1) * MT_N + i];
+    __syncthreads();
+    uint32_t* bufs[2] = {knew, pre};
+    int cur = 0;
+    for (long long b = b_lo + have; b < b_hi; ++b, cur ^= 1, out += MT_N) {
+        mt_regen_block(bufs[cur], bufs[cur ^ 1], out, tid);
         __syncthreads();
     }
 }
@@ -298,8 +404,10 @@ extern "C" size_t fb200_randn_scratch_bytes(int64_t n) { return n > 0 ? rng_layo
 // n standard normals continuing the numpy legacy stream held in `state` (device: key[624], pos, has_gauss, gauss).
 // state_out (device, 632 words): the state after the draws + status word [628] (1 = the planned number of candidate
 // points did not yield enough accepted pairs; nothing may be used then -- probability < 1e-11) + tries used [630..632).
+// jump_polys (device, [4][16][624] words from fasta/mt19937_jump.npz, or NULL): lets large draws generate the word
+// stream from many thread blocks.
 extern "C" int fb200_randn_legacy(const void* state, int64_t n, double* out, void* scratch, size_t scratch_bytes,
-                                  void* state_out, void* stream) {
+                                  void* state_out, const void* jump_polys, void* stream) {
     if (n <= 0) { set_error("randn_legacy: n must be positive"); return 1; }
     const RngLayout L = rng_layout(n);
     if (scratch_bytes < L.total) { set_error("randn_legacy: scratch too small (%zu < %zu)", scratch_bytes, L.total); return 1; }
@@ -312,7 +420,28 @@ extern "C" int fb200_randn_legacy(const void* state, int64_t n, double* out, voi
     unsigned* counts = reinterpret_cast<unsigned*>(base + L.off_counts);
     unsigned long long* offsets = reinterpret_cast<unsigned long long*>(base + L.off_offsets);
     const uint32_t* s = static_cast<const uint32_t*>(state);
-    mt_stream_kernel<<<1, 256, 0, st>>>(s, 4 * L.tries, words, meta);
+    const long long want = 4 * L.tries;
+    const long long nb_max = (want + MT_N - 1) / MT_N;                     // blocks to regenerate if the entry block is spent
+    const long long units = (nb_max + MTJ_UNIT - 1) / MTJ_UNIT;
+    if (jump_polys && nb_max >= MTJ_PARALLEL_MIN_BLOCKS && units < (1ll << (4 * MTJ_LEVELS))) {
+        static DeviceOnce once;
+        if (once.run([] {
+                if (cudaFuncSetAttribute(mt_parallel_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MTJ_SMEM) != cudaSuccess) {
+                    set_error("randn_legacy: shared-memory attribute: %s", cudaGetErrorString(cudaGetLastError()));
+                    return 1;
+                }
+                return 0;
+            }))
+            return 1;
+        const long long target = 2ll * sm_count();                         // two 85 KB CTAs are resident per SM
+        long long seg_units = (units + target - 1) / target;
+        if (seg_units < 1) seg_units = 1;
+        const long long nseg = (units + seg_units - 1) / seg_units;
+        mt_parallel_stream_kernel<<<unsigned(nseg), 256, MTJ_SMEM, st>>>(s, static_cast<const uint32_t*>(jump_polys), want,
+                                                                         int(seg_units), words, meta);
+    } else {
+        mt_stream_kernel<<<1, 256, 0, st>>>(s, want, words, meta);
+    }
     polar_count_kernel<<<unsigned(L.nblk), POLAR_THREADS, 0, st>>>(words, L.tries, counts);
     polar_scan_kernel<<<1, 1024, 0, st>>>(counts, L.nblk, offsets);
     polar_emit_kernel<<<unsigned(L.nblk), POLAR_THREADS, 0, st>>>(words, L.tries, offsets, s, n, out, meta);

@@ -503,11 +503,6 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
 
 template <int BB>
 __global__ void __launch_bounds__(VEC_THREADS)
@@ -525,13 +520,22 @@ peer_exchange_kernel(PeerPtrs pp, int rank, int P, uint32_t epoch, int64_t n, co
     const double tau_v = isnan(tau) ? __ldcg(&scal[FB200_S_TAU]) : tau;
     const int c = blockIdx.x;
     const int64_t per = ((n + PEER_CHUNKS - 1) / PEER_CHUNKS + 1) / 2 * 2;      // even: chunks start 16-byte aligned
-    const int64_t lo = int64_t(c) * per, hi = (lo + per < n) ? lo + per : n;
+    const int64_t lo = int64_t(c) * per, hi = (lo + per < n) ? lo + per : n;    // n is even (the sweep requires it)
     double* mine = pp.data[rank];
-    // 1. this rank's partial of the chunk: the band partials of the local sweep in index order
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        double gi = __ldcg(&gsrc[i]);
-        for (int k = 1; k < nsplit; ++k) gi += __ldcg(&gsrc[int64_t(k) * ld + i]);
-        mine[i] = gi;
+    // 1. this rank's partial of the chunk: the band partials of the local sweep in index order (loads batched: they
+    //    are independent, only the additions are ordered)
+    for (int64_t i = lo + 2 * threadIdx.x; i < hi; i += 2 * blockDim.x) {
+        double2 acc = __ldcg(reinterpret_cast<const double2*>(gsrc + i));
+        for (int k0 = 1; k0 < nsplit; k0 += 8) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (k0 + u < nsplit) v[u] = __ldcg(reinterpret_cast<const double2*>(gsrc + int64_t(k0 + u) * ld + i));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (k0 + u < nsplit) { acc.x += v[u].x; acc.y += v[u].y; }
+        }
+        *reinterpret_cast<double2*>(mine + i) = acc;
     }
     if (c == 0 && threadIdx.x == 0 && with_loss) {
         double f = 0.0;
@@ -552,26 +556,36 @@ peer_exchange_kernel(PeerPtrs pp, int rank, int P, uint32_t epoch, int64_t n, co
         while (int32_t(ld_acquire_sys_u32(f) - epoch) < 0) {}
     }
     __syncthreads();
-    // 4. g = sum over ranks in rank order, Barzilai-Borwein sums
+    // 4. g = sum over ranks in rank order, Barzilai-Borwein sums.  The P remote loads of an element pair are issued
+    //    together (one NVLink round trip per pair, not P): L1 is bypassed (.cg), the acquire above orders them.
     double s[3] = {0.0, 0.0, 0.0};
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        double gi = ld_relaxed_sys_f64(pp.data[0] + i);
-        for (int k = 1; k < P; ++k) gi += ld_relaxed_sys_f64(pp.data[k] + i);
-        g[i] = gi;
-        if (BB >= 1) s[2] += gi * gi;
+    for (int64_t i = lo + 2 * threadIdx.x; i < hi; i += 2 * blockDim.x) {
+        double2 v[FB200_MAX_PEERS];
+#pragma unroll
+        for (int k = 0; k < FB200_MAX_PEERS; ++k)
+            if (k < P) v[k] = __ldcg(reinterpret_cast<const double2*>(pp.data[k] + i));
+        double2 gi = v[0];
+#pragma unroll
+        for (int k = 1; k < FB200_MAX_PEERS; ++k)
+            if (k < P) { gi.x += v[k].x; gi.y += v[k].y; }
+        *reinterpret_cast<double2*>(g + i) = gi;
+        if (BB >= 1) { s[2] += gi.x * gi.x; s[2] += gi.y * gi.y; }
         if (BB >= 2) {
-            const double dg = gi + (xhat[i] - x0[i]) / tau_v;   // __init__.py:254
-            s[0] += dx[i] * dg;                                  // :255
-            s[1] += dg * dg;                                     // :260
+            const double2 xh = *reinterpret_cast<const double2*>(xhat + i), xo = *reinterpret_cast<const double2*>(x0 + i);
+            const double2 dd = *reinterpret_cast<const double2*>(dx + i);
+            const double dg0 = gi.x + (xh.x - xo.x) / tau_v;     // __init__.py:254
+            const double dg1 = gi.y + (xh.y - xo.y) / tau_v;
+            s[0] += dd.x * dg0; s[0] += dd.y * dg1;              // :255
+            s[1] += dg0 * dg0;  s[1] += dg1 * dg1;               // :260
         }
     }
     if (with_loss && c == 0 && threadIdx.x == 0) {
-        double f = ld_relaxed_sys_f64(pp.data[0] + n);
-        for (int k = 1; k < P; ++k) f += ld_relaxed_sys_f64(pp.data[k] + n);
+        double f = __ldcg(pp.data[0] + n);
+        for (int k = 1; k < P; ++k) f += __ldcg(pp.data[k] + n);
         scal[FB200_S_F] = f;
         if (with_loss >= 2) {                               // FISTA sweep: second loss partial (extrapolated point)
-            double f2 = ld_relaxed_sys_f64(pp.data[0] + n + 1);
-            for (int k = 1; k < P; ++k) f2 += ld_relaxed_sys_f64(pp.data[k] + n + 1);
+            double f2 = __ldcg(pp.data[0] + n + 1);
+            for (int k = 1; k < P; ++k) f2 += __ldcg(pp.data[k] + n + 1);
             scal[FB200_S_AUX3] = f2;
         }
     }

@@ -86,7 +86,7 @@ SIGNATURES = {
     "fb200_dense_sweep_exchange": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _dbl, _p, _p, _p, _int, _int, ctypes.c_uint32,
                                           _p, _int, _p, _p, _p, _dbl, _p, _p, _p, _p, _sz, _p]),
     "fb200_randn_scratch_bytes": (_sz, [_i64]),
-    "fb200_randn_legacy": (_int, [_p, _i64, _p, _p, _sz, _p, _p]),
+    "fb200_randn_legacy": (_int, [_p, _i64, _p, _p, _sz, _p, _p, _p]),
 }
 
 _lib = None

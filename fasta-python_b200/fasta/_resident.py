@@ -59,16 +59,28 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
 
     s = be.start()                                          # ref :135-143
     dev = be.X[0].device
-    f64 = lambda n: t.zeros(n, dtype=t.float64, device=dev)
-    resid_d, nresid_d, tau_d = f64(max_iters), f64(max_iters), f64(max_iters)
-    f_d, obj_d = f64(max_iters + 1), f64(max_iters + 1)
-    bt_d = t.zeros(max_iters, dtype=t.int32, device=dev)
-    clk_d = t.zeros(max_iters + 1, dtype=t.int64, device=dev)
-    out_d = f64(4)
+    # every history the kernel fills lives in ONE zero-initialised device block (one memset, one D2H copy at the end):
+    # doubles resid | nresid | tau | alpha [max_iters each] | f | obj [max_iters + 1 each] | out [4] | clk (int64)
+    # [max_iters + 1] | bt (int32) [max_iters, padded to a multiple of 8 bytes]
+    mi = int(max_iters)
+    nd = 4 * mi + 2 * (mi + 1) + 4 + (mi + 1) + (mi + 1) // 2 + 1
+    block = t.zeros(nd, dtype=t.float64, device=dev)
+    o = 0
+    resid_d, nresid_d, tau_d, alpha_all = (block[o + k * mi: o + (k + 1) * mi] for k in range(4))
+    o += 4 * mi
+    f_d, obj_d = block[o: o + mi + 1], block[o + mi + 1: o + 2 * (mi + 1)]
+    o += 2 * (mi + 1)
+    out_d = block[o: o + 4]
+    o += 4
+    clk_d = block[o: o + mi + 1].view(t.int64)
+    o += mi + 1
+    bt_d = block[o:].view(t.int32)[:mi]
     part = t.empty(int(lib.fb200_resident_scratch_doubles(be.drv.M, be.drv.N)), dtype=t.float64, device=dev)
-    head = np.array([s.f, (s.f + s.pen) if evaluate_objective else 0.0])
-    f_d[0:1].copy_(t.from_numpy(head[0:1]))
-    obj_d[0:1].copy_(t.from_numpy(head[1:2]))
+    head = be.ws.stage(0, 2)
+    head[0] = float(s.f)
+    head[1] = float(s.f + s.pen) if evaluate_objective else 0.0
+    f_d[0:1].copy_(head[0:1], non_blocking=True)
+    obj_d[0:1].copy_(head[1:2], non_blocking=True)
 
     pen = be.pen
     mu = float(pen.mu) if pen.tag == S.PROX_SHRINK else 0.0
@@ -77,7 +89,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
     xa, xb, best = be.X[ia], be.X[ib_], be.X[ibest]
     best.copy_(xa)                                          # stays the answer if no iterate ever improves (nan quality)
     ga, gb = be.G[be.gc], be.G[(be.gc + 1) % 3]
-    alpha_d = f64(max_iters) if accelerate else None
+    alpha_d = alpha_all if accelerate else None
     fista = [be.XA[be.ac], be.XA[(be.ac + 1) % 3], be.ZA[be.ac], be.ZA[(be.ac + 1) % 3], alpha_d] if accelerate else [None] * 5
     t_launch = time()
     _cabi.check(lib.fb200_resident_fbs(
@@ -90,18 +102,31 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
         int(bool(evaluate_objective)), int(bool(accelerate)), int(bool(restart)), *[_device.ptr(v) for v in fista],
         _device.stream_ptr()), "fb200_resident_fbs")
     be.launches += 1
-    out = out_d.cpu().numpy()                               # the one sync of the solve
+    host = t.empty(nd, dtype=t.float64).pin_memory() if getattr(be.ws, "_resident_host", None) is None or be.ws._resident_host.numel() != nd \
+        else be.ws._resident_host
+    be.ws._resident_host = host
+    host.copy_(block, non_blocking=True)
+    t.cuda.current_stream().synchronize()                   # the one sync of the solve
+    hb = host.numpy().copy()                                # the pinned mirror is reused by the next solve
+    o = 0
+    residual_hist, norm_residual_hist, tau_hist, alphas_all = (hb[o + k * mi: o + (k + 1) * mi] for k in range(4))
+    o += 4 * mi
+    f_hist_h, obj_h = hb[o: o + mi + 1], hb[o + mi + 1: o + 2 * (mi + 1)]
+    o += 2 * (mi + 1)
+    out = hb[o: o + 4]
+    o += 4
+    clk = hb[o: o + mi + 1].view(np.int64).astype(np.float64)
+    o += mi + 1
+    bts_all = hb[o:].view(np.int32)[:mi]
     n = int(out[0])
     be.ic, be.ip = (ib_, ia) if int(out[2]) != 0 else (ia, ib_)      # which buffer holds the last iterate
     be.ib = ibest                                           # the kernel copies an improving iterate there (N is small)
-    residual_hist, norm_residual_hist, tau_hist = (v.cpu().numpy() for v in (resid_d, nresid_d, tau_d))
-    objective_hist = obj_d.cpu().numpy() if evaluate_objective else None
-    clk = clk_d.cpu().numpy().astype(np.float64)
+    objective_hist = obj_h if evaluate_objective else None
     times = np.zeros(max_iters + 1)
     times[:n + 1] = t_launch + (clk[:n + 1] - clk[0]) * 1e-9     # %globaltimer stamps mapped onto the host clock
     if verbose:                                             # ref :235,302-306, printed after the fact
-        bts = bt_d.cpu().numpy()
-        alphas = alpha_d.cpu().numpy() if accelerate else None
+        bts = bts_all
+        alphas = alphas_all if accelerate else None
         for i in range(n):
             if bts[i] & (1 << 30):
                 print("Restarted acceleration.")

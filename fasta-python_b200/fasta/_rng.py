@@ -25,6 +25,24 @@ OUT_WORDS = 632          # + status word [628], tries used [630..632)
 MIN_DEVICE_DRAWS = 4096  # below this the host's two draws cost less than ten kernel launches
 
 _checked = {}            # device index -> bool
+_polys = {}              # device index -> device tensor of the MT19937 jump polynomials (or None)
+
+
+def jump_polys(device):
+    """fasta/mt19937_jump.npz ([4][16][624] words: t^J mod phi for J = 64 * 16^level * digit blocks) on `device`."""
+    key = device.index if device.index is not None else _device.torch().cuda.current_device()
+    if key not in _polys:
+        t = _device.torch()
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mt19937_jump.npz")
+        try:
+            with np.load(path) as z:
+                table = np.ascontiguousarray(z["polys"], dtype=np.uint32)
+            assert table.shape == (4, 16, 624)
+            _polys[key] = t.from_numpy(table.view(np.int32)).to(device)
+        except Exception as exc:               # without the table large draws come from one thread block: slower, same values
+            warnings.warn(f"fasta-b200: {path} not usable ({exc}); large device draws stay sequential")
+            _polys[key] = None
+    return _polys[key]
 
 
 def mode():
@@ -80,8 +98,9 @@ class DeviceRandn:
         nbytes = int(self.lib.fb200_randn_scratch_bytes(n))
         scratch = t.empty(nbytes, dtype=t.uint8, device=self.device)
         nxt = t.empty(OUT_WORDS, dtype=t.int32, device=self.device)
+        polys = jump_polys(self.device) if os.environ.get("FASTA_B200_MT_JUMP", "1") != "0" else None
         _cabi.check(self.lib.fb200_randn_legacy(self._states[-1].data_ptr(), n, out.data_ptr(), scratch.data_ptr(), nbytes,
-                                                nxt.data_ptr(), _device.stream_ptr()), "fb200_randn_legacy")
+                                                nxt.data_ptr(), _device.ptr(polys), _device.stream_ptr()), "fb200_randn_legacy")
         self._states.append(nxt)
         self._scratch.append(scratch)      # keep alive until the stream has passed (finish)
         return 5                           # kernels launched

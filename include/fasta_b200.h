@@ -369,10 +369,13 @@ int fb200_dense_sweep_exchange(const double* A, int64_t lda, int64_t M, int64_t 
  *   out        device, n doubles
  *   scratch    device, >= fb200_randn_scratch_bytes(n) bytes, 256-byte aligned
  *   state_out  device, 632 words: the end state (628 words), status (word 628: 0 ok / 1 too few accepted candidate
- *              points -- then nothing may be used; probability < 1e-11), tries used (64-bit at word 630) */
+ *              points -- then nothing may be used; probability < 1e-11), tries used (64-bit at word 630)
+ *   jump_polys device, [4][16][624] 32-bit words (fasta/mt19937_jump.npz: t^J mod phi for J = 64 * 16^level * digit
+ *              MT19937 blocks, tools/make_mt_jump.py), or NULL: with it, draws beyond ~0.5M values generate the word
+ *              stream from many thread blocks (jump-ahead) instead of one */
 size_t fb200_randn_scratch_bytes(int64_t n);
 int fb200_randn_legacy(const void* state, int64_t n, double* out, void* scratch, size_t scratch_bytes,
-                       void* state_out, void* stream);
+                       void* state_out, const void* jump_polys, void* stream);
 
 #ifdef __cplusplus
 }
