@@ -570,7 +570,8 @@ class TVWorkload:
         dram = 9 * U                                             # read x0 (2U), g0 (2U), b (U); write x1 (2U), g1 (2U)
         alg = 11 * U                                             # SURVEY 8d's accounting of one iteration
         gbs = dram / (avg * 1e-3) / 1e9
-        return dict(bound="hbm", kernel="tv_iter_march_kernel (whole trial in one pass: step, ball projection, div, loss, grad, 7 sums)",
+        return dict(bound="hbm", kernel="tv_iter_tma_kernel (whole trial in one pass: step, ball projection, div, loss, grad, 7 sums; rows "
+                                        "streamed into a shared-memory ring by bulk copies, 16 compute warps march down the tile)",
                     achieved=gbs, peak=peak, unit="GB/s", frac=gbs / peak, traffic=None, peak_source=src, dram_bytes_per_launch=dram,
                     avg_launch_ms=avg, launches_timed=len(live), speculative_launches_returned_at_once=len(ms) - len(live),
                     achieved_algorithmic=alg / (avg * 1e-3) / 1e9, frac_algorithmic=alg / (avg * 1e-3) / 1e9 / peak,

@@ -363,7 +363,10 @@ static GsPlan gs_make_plan(int64_t M, int64_t N, int nsm) {
         if (nst > GS_MAXSTG) nst = GS_MAXSTG;
         if (nst < 3) continue;
         int64_t bands = nsm / S;
-        if (bands > M) bands = M;
+        // short matrices: every band costs the epilogue one more partial vector to add (measured at 200 x 1000: 148 bands
+        // of one or two rows made the 1000-element band sum a 46 us kernel), so keep at least 32 rows per band
+        const int64_t by_rows = M / 32 > 0 ? M / 32 : 1;
+        if (bands > by_rows) bands = by_rows;
         if (bands < 1) continue;
         const double cost = double((M + bands - 1) / bands) * (10.0 + cpt);      // measured at N = 100000: S = 16 / 18 / 21 -> 4.56 / 4.77 / 5.05 ms
         if (!best.ok || cost < best_cost) {

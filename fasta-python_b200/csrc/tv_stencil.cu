@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace fb200 {
 
@@ -545,6 +546,184 @@ tv_iter_march_kernel(const double2* __restrict__ x0, const double2* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------
+// The marching iteration fed by bulk copies (large images).  tv_iter_march_kernel issues its own global loads, four
+// rows ahead, from the same warps that run the fp64 sqrt / divide chains: 16 warps per SM at 124 registers, 57-75 % of
+// the HBM rate (long_scoreboard + fixed-latency stalls, profiles/r01_tv_iter_march_full_metrics.csv).  Here a producer
+// warp streams the rows of x0, g0 and b of a (strip x 30*CW columns) tile into a shared-memory ring with cp.async.bulk
+// (full / empty mbarriers, ~170 KB in flight per SM at zero register cost) and CW compute warps march down the tile
+// reading shared memory: same expressions in the same order (tv_prox_point, loss_elem, the Markstein quotient), so
+// x1 and g1 are the same bits.  Periodic wrap: the row index wraps in the address; a tile at the left / right image
+// edge fetches its halo column with a separate 16-byte copy.  Needs even n1 (16-byte aligned rows of b).
+//   ring slot = one image row of the tile:  X[WC] g0-pairs | G[WC] | B[WC + 2],  WC = 30*CW + 2,
+//   column c of the image lives at X[c - jL], B[c - jL + 1] with jL = j0 - 1 (the left halo column).
+// ---------------------------------------------------------------------------------------------------
+template <int CW, int TVT_RING>
+struct TvtShape {
+    static constexpr int WC = TVM_COLS * CW + 2;
+    static constexpr int SLOT = (2 * WC * 16 + (WC + 2) * 8 + 127) / 128 * 128;
+    static constexpr int SMEM = TVT_RING * SLOT + 2 * TVT_RING * 8;
+    static constexpr int THREADS = (CW + 1) * 32;
+};
+
+template <int LOSS, int CW, int U, int TVT_RING>
+__global__ void __launch_bounds__((CW + 1) * 32, 1)
+tv_iter_tma_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, double tau, int n0, int n1,
+                   const double* __restrict__ b, double2* __restrict__ x1, double2* __restrict__ g1, int tiles_x, int strip,
+                   double* scal, double* red, unsigned* counter) {
+    using Sh = TvtShape<CW, TVT_RING>;
+    extern __shared__ __align__(128) unsigned char tvt_smem[];
+    uint64_t* full  = reinterpret_cast<uint64_t*>(tvt_smem + TVT_RING * Sh::SLOT);
+    uint64_t* empty = full + TVT_RING;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (isnan(tau)) {                                       // speculative trial: see fb200_trial_decide
+        if (__ldcg(&scal[FB200_S_SKIP]) != 0.0) return;
+        tau = __ldcg(&scal[FB200_S_TAU]);
+    }
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int j0 = tx * (TVM_COLS * CW), jL = j0 - 1;
+    const int i0 = ty * strip;
+    const int i1 = min(n0, i0 + strip);
+    const int nrows = i1 - i0 + 2;                          // image rows i0-1 .. i1 (wrapped)
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < TVT_RING; ++k) {
+            mbar_init(&full[k], 1);
+            mbar_init(&empty[k], CW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    double s[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (warp == CW) {
+        // ===================================== producer =====================================
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            const int jR = j0 + TVM_COLS * CW;                              // right halo column (unwrapped)
+            const int cbeg = jL < 0 ? 0 : jL, cend = jR < n1 ? jR : n1 - 1; // contiguous image columns of the tile
+            const uint32_t main_xg = uint32_t(cend - cbeg + 1) * 16u;
+            const int bbeg = jL < 0 ? 0 : jL - 1;                           // even (j0 is even)
+            int bend = cend;
+            if (((bend - bbeg + 1) & 1) && bend + 1 < n1) ++bend;           // even element count (n1 is even)
+            const uint32_t main_b = uint32_t(bend - bbeg + 1) * 8u;
+            const uint32_t total = 2u * main_xg + main_b + (jL < 0 ? 2u * 16u + 16u : 0u) + (jR >= n1 ? 2u * 16u : 0u);
+            for (int k = 0; k < nrows; ++k) {
+                const int slot = k % TVT_RING;
+                mbar_wait(&empty[slot], ((k / TVT_RING) & 1) ^ 1u);
+                unsigned char* base = tvt_smem + size_t(slot) * Sh::SLOT;
+                double2* X = reinterpret_cast<double2*>(base);
+                double2* G = X + Sh::WC;
+                double*  B = reinterpret_cast<double*>(G + Sh::WC);
+                const int64_t row = int64_t(tv_wrap(i0 - 1 + k, n0)) * n1;
+                mbar_expect_tx(&full[slot], total);
+                bulk_load(X + (cbeg - jL), x0 + row + cbeg, main_xg, &full[slot], pol);
+                bulk_load(G + (cbeg - jL), g0 + row + cbeg, main_xg, &full[slot], pol);
+                bulk_load(B + (bbeg - jL + 1), b + row + bbeg, main_b, &full[slot], pol);
+                if (jL < 0) {                                               // left image edge: halo column n1 - 1
+                    bulk_load(X, x0 + row + n1 - 1, 16u, &full[slot], pol);
+                    bulk_load(G, g0 + row + n1 - 1, 16u, &full[slot], pol);
+                    bulk_load(B, b + row + n1 - 2, 16u, &full[slot], pol);  // B[1] = b(., n1 - 1)
+                }
+                if (jR >= n1) {                                             // right image edge: column 0 follows column n1 - 1
+                    bulk_load(X + (n1 - jL), x0 + row, 16u, &full[slot], pol);
+                    bulk_load(G + (n1 - jL), g0 + row, 16u, &full[slot], pol);
+                }
+            }
+        }
+    } else {
+        // ===================================== compute warps: the marching scheme from shared memory ==========
+        const int j = j0 + TVM_COLS * warp - 1 + lane;      // unwrapped column of this lane
+        const int cx = TVM_COLS * warp + lane;              // its offset in a ring row
+        const bool out_lane = lane >= 1 && lane <= TVM_COLS && j < n1;
+        const double rtau = 1.0 / tau;
+        auto slot_ptr = [&](int k) { return tvt_smem + size_t(k % TVT_RING) * Sh::SLOT; };
+        auto wait_row = [&](int k) { mbar_wait(&full[k % TVT_RING], (k / TVT_RING) & 1); };
+        auto free_row = [&](int k) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[k % TVT_RING]);
+        };
+        auto load_xg = [&](int k, double2& a, double2& gr) {
+            const double2* X = reinterpret_cast<const double2*>(slot_ptr(k));
+            a = X[cx];
+            gr = X[Sh::WC + cx];
+        };
+        auto load_b = [&](int k) { return reinterpret_cast<const double*>(slot_ptr(k) + 2 * Sh::WC * 16)[cx + 1]; };
+        double2 a_c, g_c, a_t, g_t, h;
+        wait_row(0);
+        load_xg(0, a_t, g_t);
+        const double2 y_m = tv_prox_point(a_t, g_t, tau, h);       // row i0-1
+        wait_row(1);
+        load_xg(1, a_c, g_c);
+        double2 y_c = tv_prox_point(a_c, g_c, tau, h);             // row i0
+        double r_up;
+        {
+            const double rty = __shfl_down_sync(0xffffffffu, y_m.y, 1);
+            const double zi = (y_c.x - y_m.x) + (rty - y_m.y);
+            double fv;
+            loss_elem<LOSS>(zi, load_b(0), r_up, fv);              // r(i0-1, j)
+        }
+        free_row(0);
+        for (int ib = i0; ib < i1; ib += U) {
+            double2 an[U], gn[U];
+            double bb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                          // rows ib+1 .. ib+U and b of rows ib .. ib+U-1
+                const int i = ib + u;
+                if (i < i1) {
+                    const int k = i - i0 + 2;                      // ring index of image row i + 1
+                    wait_row(k);
+                    load_xg(k, an[u], gn[u]);
+                    bb[u] = load_b(k - 1);
+                } else {
+                    an[u] = gn[u] = make_double2(0.0, 0.0);
+                    bb[u] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)                            // rows ib .. ib+U-1 are in registers now
+                if (ib + u < i1) free_row(ib + u - i0 + 1);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = ib + u;
+                if (i >= i1) break;                                // warp-uniform
+                double2 hn;
+                const double2 y_n = tv_prox_point(an[u], gn[u], tau, hn);        // row i+1
+                const double rty = __shfl_down_sync(0xffffffffu, y_c.y, 1);
+                const double zi = (y_n.x - y_c.x) + (rty - y_c.y);
+                double rc, fc;
+                loss_elem<LOSS>(zi, bb[u], rc, fc);
+                const double r_left = __shfl_up_sync(0xffffffffu, rc, 1);
+                if (out_lane) {
+                    const int64_t o = int64_t(i) * n1 + j;
+                    double2 gi;
+                    gi.x = r_up - rc;
+                    gi.y = r_left - rc;
+                    x1[o] = y_c;
+                    g1[o] = gi;
+                    const double hx = a_c.x - tau * g_c.x, hy = a_c.y - tau * g_c.y;
+                    const double dxx = y_c.x - a_c.x, dxy = y_c.y - a_c.y, ex = y_c.x - hx, ey = y_c.y - hy;
+                    s[0] += dxx * g_c.x; s[0] += dxy * g_c.y;
+                    s[1] += dxx * dxx;   s[1] += dxy * dxy;
+                    s[2] += ex * ex;     s[2] += ey * ey;
+                    s[3] += fc;
+                    const double dg0 = gi.x + tv_div_tau<true>(hx - a_c.x, tau, rtau);
+                    const double dg1 = gi.y + tv_div_tau<true>(hy - a_c.y, tau, rtau);
+                    s[4] += dxx * dg0;   s[4] += dxy * dg1;
+                    s[5] += dg0 * dg0;   s[5] += dg1 * dg1;
+                    s[6] += gi.x * gi.x; s[6] += gi.y * gi.y;
+                }
+                r_up = rc;
+                y_c = y_n;
+                a_c = an[u];
+                g_c = gn[u];
+            }
+        }
+        free_row(nrows - 1);                                       // the last row's slot (its b is never read)
+    }
+    double* const out[7] = {scal + FB200_S_DX_G0, scal + FB200_S_DX_SQ, scal + FB200_S_XMXH_SQ, scal + FB200_S_F,
+                            scal + FB200_S_DX_DG, scal + FB200_S_DG_SQ, scal + FB200_S_G1_SQ};
+    grid_sum<7>(s, red, counter, out);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // FISTA (accelerated) iteration, same marching scheme: forward step and ball projection give the prox point
 // x_accel1 (reference __init__.py:181-186), its image z_accel1 = div(x_accel1) and f there feed the line search
 // (:187-217); the extrapolation x1 = x_accel1 + c (x_accel1 - x_accel0), z1 = z_accel1 + c (z_accel1 - z_accel0)
@@ -708,6 +887,88 @@ static int tvm_plan(int64_t n0, int64_t n1, int64_t* warps_x_out, int64_t* strip
     return 0;
 }
 
+// Tiles of the bulk-copy-fed kernel: tiles_x x strips CTAs, one CTA per SM, the grid a whole number of waves.
+template <int CW>
+static int tvt_plan(int64_t n0, int64_t n1, int64_t* tiles_x_out, int64_t* strip_out) {
+    const int64_t tiles_x = (n1 + TVM_COLS * CW - 1) / (TVM_COLS * CW);
+    const int64_t nsm = sm_count();
+    double best = 1e300;
+    int64_t strip = 0;
+    for (int k = 1; k <= 8; ++k) {
+        const int64_t strips = (k * nsm) / tiles_x;
+        if (strips < 1) continue;
+        const int64_t st = (n0 + strips - 1) / strips;
+        if (st < 32 || st > 512) continue;
+        const double cost = double(k) * (double(st) + 4.0);         // halo rows + pipeline fill per tile
+        if (cost < best - 1e-9) { best = cost; strip = st; }
+    }
+    if (!strip) return 1;
+    if (tiles_x * ((n0 + strip - 1) / strip) > MAX_RED_BLOCKS) return 1;
+    if (double(n1) < 0.9 * double(tiles_x * TVM_COLS * CW)) return 1;      // a mostly empty last column tile: not worth it
+    *tiles_x_out = tiles_x;
+    *strip_out = strip;
+    return 0;
+}
+
+// 0: never, 1: large even-width images (default), 2: whenever the layout allows (tests)
+static int tvt_mode() {
+    const char* e = getenv("FASTA_B200_TV_TMA");
+    if (!e) return 1;
+    if (e[0] == '0') return 0;
+    return (e[0] == 'f' || e[0] == '2') ? 2 : 1;
+}
+
+template <int LOSS, int CW, int U, int RING>
+static int tvt_launch_as(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, const double* b, double* x1, double* g1,
+                         double* scal, Workspace& w, cudaStream_t st, int mode, bool* done) {
+    using Sh = TvtShape<CW, RING>;
+    int64_t tiles_x = 0, strip = 0;
+    if (tvt_plan<CW>(n0, n1, &tiles_x, &strip)) {
+        if (mode != 2) return 0;
+        tiles_x = (n1 + TVM_COLS * CW - 1) / (TVM_COLS * CW);      // tests: any image, one strip per 64 rows
+        strip = n0 < 64 ? n0 : 64;
+        if (tiles_x * ((n0 + strip - 1) / strip) > MAX_RED_BLOCKS) return 0;
+    }
+    static DeviceOnce once;
+    if (once.run([] {
+            if (cudaFuncSetAttribute(tv_iter_tma_kernel<LOSS, CW, U, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sh::SMEM) != cudaSuccess) {
+                set_error("tv_iter_tma: shared-memory attribute: %s", cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+            return 0;
+        }))
+        return 1;
+    const int64_t blocks = tiles_x * ((n0 + strip - 1) / strip);
+    tv_iter_tma_kernel<LOSS, CW, U, RING><<<unsigned(blocks), Sh::THREADS, Sh::SMEM, st>>>(
+        (const double2*)x0, (const double2*)g0, tau, int(n0), int(n1), b, (double2*)x1, (double2*)g1, int(tiles_x), int(strip), scal,
+        w.red, w.counter);
+    *done = true;
+    return check_launch("tv_iter_tma");
+}
+
+template <int LOSS>
+static int tvt_launch(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, const double* b, double* x1, double* g1,
+                      double* scal, Workspace& w, cudaStream_t st, bool* done) {
+    *done = false;
+    const int mode = tvt_mode();
+    if (mode == 0 || (n1 & 1) || n1 < 4 || n0 < 1) return 0;
+    if ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(g0) | reinterpret_cast<uintptr_t>(b)) & 15) return 0;
+    if (mode == 1 && n0 * n1 < (int64_t(1) << 21)) return 0;       // small images: the register-marching kernel
+    // measured at 4096^2 (us per launch; compute warps / rows in flight per warp / ring slots): 12/2/12 239.7, 12/4/12 234.2,
+    // 14/2/12 218.5, 16/2/10 213.6, 16/4/10 291.4 (spills), 17/2/10 215.9, 18/2/9 235.0, 20/2/8 262.9 (spills); the
+    // register-marching kernel 235.7
+    int v = 0;
+    if (const char* e = getenv("FASTA_B200_TVT_VARIANT")) v = atoi(e);       // experiments
+    if (LOSS == FB200_LOSS_LEAST_SQUARES) {
+        switch (v) {
+            case 1: return tvt_launch_as<LOSS, 12, 2, 12>(x0, g0, tau, n0, n1, b, x1, g1, scal, w, st, mode, done);
+            case 2: return tvt_launch_as<LOSS, 14, 2, 12>(x0, g0, tau, n0, n1, b, x1, g1, scal, w, st, mode, done);
+            default: break;
+        }
+    }
+    return tvt_launch_as<LOSS, 16, 2, 10>(x0, g0, tau, n0, n1, b, x1, g1, scal, w, st, mode, done);
+}
+
 }  // namespace fb200
 
 using namespace fb200;
@@ -803,6 +1064,13 @@ extern "C" int fb200_tv_iter_fused(const double* x0, const double* g0, double ta
         variant = (e && e[0] == '1') ? 1 : 0;
     }
     if (variant == 0) {
+        bool done = false;
+        if (loss == FB200_LOSS_LEAST_SQUARES) {
+            if (tvt_launch<FB200_LOSS_LEAST_SQUARES>(x0, g0, tau, n0, n1, b, x1, g1, scal, w, st, &done)) return 1;
+        } else if (loss == FB200_LOSS_LOGISTIC) {
+            if (tvt_launch<FB200_LOSS_LOGISTIC>(x0, g0, tau, n0, n1, b, x1, g1, scal, w, st, &done)) return 1;
+        }
+        if (done) return 0;
         int64_t warps_x, strip, blocks;
         if (tvm_plan(n0, n1, &warps_x, &strip, &blocks)) { set_error("tv_iter_fused: image too large"); return 1; }
         static int mv = -1;                 // experiment knob: unroll depth / occupancy target of the marching kernel

@@ -209,11 +209,16 @@ def test_tv_stencils(n0, n1):
     assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), 1.0)                  # adjointness
 
 
-@pytest.mark.parametrize("n0,n1", [(64, 64), (128, 96), (33, 130), (1, 7), (5, 1), (2, 2), (300, 257), (70, 64)])
-def test_tv_whole_iteration_kernel(n0, n1):
+@pytest.mark.parametrize("tma", ["0", "force"])
+@pytest.mark.parametrize("n0,n1", [(64, 64), (128, 96), (33, 130), (1, 7), (5, 1), (2, 2), (300, 257), (70, 64),
+                                   (130, 360), (5, 362), (200, 724), (97, 1084), (3, 4)])
+def test_tv_whole_iteration_kernel(n0, n1, tma, monkeypatch):
     """fb200_tv_iter_fused: x1 and g1 bit-identical to the numpy expressions of the reference lines
-    (tv_denoising.py:26-63,85-96; __init__.py:181-188,248-260), the seven sums to reduction rounding."""
+    (tv_denoising.py:26-63,85-96; __init__.py:181-188,248-260), the seven sums to reduction rounding -- with the
+    register-marching kernel and with the bulk-copy-fed one (one, two, three column tiles, image edges inside a tile,
+    strips shorter than the ring; odd widths fall back to the marching kernel by design)."""
     from fasta import _cabi, _device
+    monkeypatch.setenv("FASTA_B200_TV_TMA", tma)
     from oracle import problems
     torch = _t()
     lib = _cabi.load()
