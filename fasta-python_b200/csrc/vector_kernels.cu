@@ -167,7 +167,9 @@ l1ball_threshold_kernel(const double* __restrict__ v, int64_t n, double radius, 
     __shared__ double sh_count;
     double theta = -1.0;    // first pass: every element is active (|v| > -1)
     double prev_count = -1.0;
-    for (int pass = 0; pass < 256; ++pass) {
+    // Michelot's fixed point: every pass drops at least one element from the active set or stops, so n + 1 passes bound it
+    // (typically ~10); no artificial cap -- a capped run would silently return a wrong threshold on adversarial input
+    for (int64_t pass = 0; pass <= n + 1; ++pass) {
         double s[2] = {0.0, 0.0};
         for (int64_t i = threadIdx.x; i < n; i += L1B_THREADS) {
             const double m = fabs(v[i]);
@@ -650,6 +652,24 @@ reduce_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_
     grid_sum<1>(s, red, counter, o);
 }
 
+// max |a_i| (np.abs(x).max(), reference democratic_representation.py:43): the bit patterns of non-negative doubles order
+// like unsigned integers (a nan sorts above inf, so it propagates as in numpy); max is order-independent: deterministic
+__global__ void amax_zero_kernel(double* out) { *out = 0.0; }
+__global__ void __launch_bounds__(VEC_THREADS) amax_kernel(const double* __restrict__ a, int64_t n, double* out) {
+    unsigned long long m = 0ull;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long v = (unsigned long long)__double_as_longlong(fabs(a[i]));
+        m = v > m ? v : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o);
+        m = v > m ? v : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned long long*>(out), m);
+}
+
 // ---- row-wise prox operators of the matrix-iterate examples ------------------------------------------
 // X is rows x cols row-major; one warp per row: nrm = sqrt(sum_j X[i][j]^2) (lane-strided partial sums,
 // butterfly combine), then
@@ -852,4 +872,10 @@ extern "C" int fb200_diff_nrm2sq(const double* a, const double* b, int64_t n, do
 }
 extern "C" int fb200_asum(const double* a, int64_t n, double* out, void* ws, void* stream) {
     return launch_reduce<2>(a, nullptr, n, out, ws, stream, "asum");
+}
+extern "C" int fb200_amax(const double* a, int64_t n, double* out, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    amax_zero_kernel<<<1, 1, 0, st>>>(out);
+    if (n > 0) amax_kernel<<<vec_grid(n), VEC_THREADS, 0, st>>>(a, n, out);
+    return check_launch("amax");
 }

@@ -808,7 +808,10 @@ class FusedBackend:
         self.ib = self.ip if self._ahead else self.ic      # by index: no copy (advance() never hands out X[ib])
 
     def iterate(self):
-        return _device.like_input(self._current().view(self.shape), self.x0_in)
+        cur = self._current().view(self.shape)
+        if not isinstance(self.x0_in, np.ndarray) and _device.is_array(self.x0_in):
+            cur = cur.clone()          # the rotating buffer is overwritten by later trials: a hook may keep its argument
+        return _device.like_input(cur, self.x0_in)
 
     def solution(self):
         # X[ib] belongs to this backend alone and the backend ends with the solve: hand the buffer over
@@ -841,6 +844,7 @@ class GenericBackend:
         self.x1 = self.x0 = self.g1 = self.g0 = self.z1 = None
         self.xhat = self.dx = self.best = None
         self.xa1 = self.xa0 = self.za1 = self.za0 = None
+        self._scratch, self._flip = None, 0
 
     def total_launches(self):
         return self.launches
@@ -901,13 +905,17 @@ class GenericBackend:
         t = self.t
         st = _device.stream_ptr()
         x0f, g0f = self._flat(self.x0), self._flat(self.g0)
-        self.xhat = t.empty_like(self.x0)
+        # two scratch pairs alternate (the previous trial's xhat / dx may still be referenced by its x1 when the user's prox
+        # returns its argument): no allocation per trial
+        if self._scratch is None:
+            self._scratch = [(t.empty_like(self.x0), t.empty_like(self.x0)) for _ in range(2)]
+        self._flip ^= 1
+        self.xhat, self.dx = self._scratch[self._flip]
         _cabi.check(self.lib.fb200_forward_step(x0f.data_ptr(), g0f.data_ptr(), float(tau), self.n,
                                                 self.xhat.data_ptr(), st), "fb200_forward_step")
         x1 = self._dev(self.proxg(self.xhat, tau))
         if x1.data_ptr() == self.xhat.data_ptr():       # identity prox returns its argument
             x1 = x1.clone()
-        self.dx = t.empty_like(self.x0)
         xa_prev = self._flat(self.xa0) if self.accelerate else None
         _cabi.check(self.lib.fb200_step_reduce(x0f.data_ptr(), self._flat(x1).data_ptr(), self.xhat.data_ptr(),
                                                g0f.data_ptr(), _device.ptr(xa_prev), self.n, self.dx.data_ptr(),

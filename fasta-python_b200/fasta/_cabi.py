@@ -81,6 +81,7 @@ SIGNATURES = {
     "fb200_dot": (_int, [_p, _p, _i64, _p, _p, _p]),
     "fb200_diff_nrm2sq": (_int, [_p, _p, _i64, _p, _p, _p]),
     "fb200_asum": (_int, [_p, _i64, _p, _p, _p]),
+    "fb200_amax": (_int, [_p, _i64, _p, _p]),
     "fb200_prox_apply": (_int, [_p, _int, _dbl, _dbl, _i64, _p, _p, _p]),
     "fb200_sweep_exchange_supported": (_int, []),
     "fb200_dense_sweep_exchange": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _dbl, _p, _p, _p, _int, _int, ctypes.c_uint32,

@@ -270,15 +270,23 @@ class _Batch:
 
 
 def _lipschitz(A, loss, x_shape_n):
-    """One randomised estimate shared by the batch: L = |A^T A (v1 - v2)| / |v1 - v2| (reference :100-113)."""
+    """The randomised estimate L = |A^T gradf(A v1) - A^T gradf(A v2)| / |v1 - v2| (reference :100-113), two probes drawn
+    once for the whole batch.  For least squares the data term cancels in the difference (gradf is affine), so one
+    estimate serves every column exactly as a single run seeded identically would see it; for other losses with one
+    right-hand side per column (logistic: gradf is not affine in b) the estimate is formed per column."""
     v1 = np.random.randn(x_shape_n)
     v2 = np.random.randn(x_shape_n)
-    b0 = loss.b if loss.b.ndim == 1 else loss.b[:, 0].contiguous()
-    single = type(loss)(b0)
-    d1 = A.H(single.gradf(A(_device.to_device(v1))))
-    d2 = A.H(single.gradf(A(_device.to_device(v2))))
-    num = float(_device.torch().linalg.norm(d1 - d2))
-    L = np.float64(num) / np.float64(np.linalg.norm(v1 - v2))
+    t = _device.torch()
+    dv = np.float64(np.linalg.norm(v1 - v2))
+    d1v, d2v = A(_device.to_device(v1)), A(_device.to_device(v2))
+    cols = [None] if (loss.b.ndim == 1 or isinstance(loss, losses.LeastSquares)) else range(loss.b.shape[1])
+    Ls = []
+    for j in cols:
+        bj = loss.b if loss.b.ndim == 1 else loss.b[:, 0 if j is None else j].contiguous()
+        single = type(loss)(bj)
+        num = float(t.linalg.norm(A.H(single.gradf(d1v)) - A.H(single.gradf(d2v))))
+        Ls.append(np.float64(num) / dv)
+    L = Ls[0] if len(Ls) == 1 else np.array(Ls)
     return L, (2 / L) / 10
 
 
@@ -315,10 +323,8 @@ def fasta_batched(A, loss, penalty, X0, *, adaptive=True, accelerate=False, verb
 
     if stepsize_shrink is None and backtrack:
         stepsize_shrink = 0.2 if adaptive else 0.5
-    if not L or not tau0:
+    if L is None or tau0 is None or not np.all(L) or not np.all(tau0):
         L, tau0 = _lipschitz(A, loss, st.N)
-    if not tau0:
-        tau0 = 1 / L
     if verbose:
         print(f"Initializing batched FASTA: {B} columns\n")
 

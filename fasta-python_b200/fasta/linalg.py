@@ -188,7 +188,8 @@ class DenseMap(LinearMap):
         st = _device.stream_ptr
         sweep = bool(lib.fb200_sweep_supported(A.data_ptr(), lda, M, N))
         lam_prev, lam = 0.0, 0.0
-        g_sq = float((g * g).sum().item())
+        _cabi.check(lib.fb200_dot(g.data_ptr(), g.data_ptr(), N, ws.scal[S.S_AUX0:].data_ptr(), ws.buf.data_ptr(), st()), "fb200_dot")
+        g_sq = float(ws.fetch()[S.S_AUX0])
         for it in range(1, iters + 1):
             # x = g / |g|  (xhat = x0 - tau * g0 with x0 = 0, tau = -1 / |g|)
             _cabi.check(lib.fb200_forward_step(zero_n.data_ptr(), g.data_ptr(), -1.0 / np.sqrt(g_sq), N, x.data_ptr(), st()),

@@ -208,8 +208,12 @@ class RowGroupL2(_Penalty):
         self.mu = mu
 
     def g(self, X):
-        n = row_norms(X)
-        return self.mu * (n.sum() if _device.is_numpy(n) else n.sum().item())
+        _, n = _rows(X, 0, 0.0, want_out=False, want_norms=True)        # device row norms (non-negative: asum is their sum)
+        lib = _cabi.load()
+        ws = _device.shared_workspace(n.numel(), 1)
+        _cabi.check(lib.fb200_asum(n.data_ptr(), n.numel(), ws.scal[_cabi.S_AUX0:].data_ptr(), ws.buf.data_ptr(),
+                                   _device.stream_ptr()), "fb200_asum")
+        return self.mu * ws.fetch()[_cabi.S_AUX0]
 
     def prox(self, X, t):
         return shrink_rows(X, t * self.mu)
@@ -234,8 +238,11 @@ class LinfNorm(_Penalty):
         self.mu = mu
 
     def g(self, x):
-        a = abs(x).max()
-        return self.mu * (a if _device.is_numpy(x) else a.item())
+        lib = _cabi.load()
+        xd = _device.to_device(x).contiguous()
+        ws = _device.shared_workspace(1, 1)
+        _cabi.check(lib.fb200_amax(xd.data_ptr(), xd.numel(), ws.scal[_cabi.S_AUX0:].data_ptr(), _device.stream_ptr()), "fb200_amax")
+        return self.mu * ws.fetch()[_cabi.S_AUX0]
 
     def prox(self, x, t):
         return project_Linf_ball(x, t * self.mu)

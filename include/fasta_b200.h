@@ -339,6 +339,8 @@ int fb200_prox_nuclear(const double* X, int64_t M, int64_t N, int64_t ldx, doubl
 int fb200_dot(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream);
 int fb200_diff_nrm2sq(const double* a, const double* b, int64_t n, double* out, void* ws, void* stream);
 int fb200_asum(const double* a, int64_t n, double* out, void* ws, void* stream);
+/* out = max |a_i|  (np.abs(x).max(), reference democratic_representation.py:43; nan propagates as in numpy) */
+int fb200_amax(const double* a, int64_t n, double* out, void* stream);
 
 /* ---- row-sharded map, fused: the single-pass sweep on this rank's rows followed by ONE kernel that finishes it across
  * the ranks (csrc/dense_sweep.cu, vector_kernels.cu: peer_exchange_kernel) -- band-partial sum into this rank's slice of
