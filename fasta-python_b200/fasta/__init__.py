@@ -17,8 +17,9 @@ the C ABI in ``include/fasta_b200.h``; the ``while`` loop and its scalar algebra
     pen  = fasta.proximal.L1Norm(mu) | L1Ball(r) | NonNegative() | Box(lo, hi) | TVBall()
     res  = fasta.fasta(A, loss.f, loss.gradf, pen.g, pen.prox, x0)
 
--- every iteration is fused into the epilogues of the two contractions (A is streamed exactly
-twice).  Any other callables run through the generic path and receive torch CUDA tensors.
+-- every iteration is one pass over A (z = A x, the loss and g = A^T gradf(z) in a single sweep, the
+step / prox / reductions in two small kernels around it).  Any other callables run through the
+generic path and receive torch CUDA tensors.
 There is no CPU fallback: without a CUDA device or the built library, fasta() raises.
 """
 
