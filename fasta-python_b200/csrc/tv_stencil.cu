@@ -887,6 +887,63 @@ static int tvm_plan(int64_t n0, int64_t n1, int64_t* warps_x_out, int64_t* strip
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Rank-generic grad / div / ball projection (reference tv_denoising.py:26-63,89-96 are written for N-d arrays; the
+// fused kernels above cover the 2-D images of BASELINE config 4, these cover every other rank through the generic
+// back-end).  One thread per element; same expressions and summation order as the numpy loops, so the same bits.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TVN_MAX_RANK = 6;
+struct TvnShape { int64_t n[TVN_MAX_RANK]; int64_t stride[TVN_MAX_RANK]; int rank; int64_t total; };
+
+__global__ void __launch_bounds__(256) tv_grad_nd_kernel(const double* __restrict__ X, TvnShape sh, double* __restrict__ G) {
+    const int64_t step = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < sh.total; e += step) {
+        const double c = X[e];
+        for (int d = 0; d < sh.rank; ++d) {
+            const int64_t i = (e / sh.stride[d]) % sh.n[d];
+            const int64_t prev = (i == 0) ? e + (sh.n[d] - 1) * sh.stride[d] : e - sh.stride[d];
+            G[e * sh.rank + d] = X[prev] - c;                 // np.roll(X, 1, axis=d) - X
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) tv_div_nd_kernel(const double* __restrict__ Y, TvnShape sh, double* __restrict__ D) {
+    const int64_t step = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < sh.total; e += step) {
+        double acc = 0.0;
+        for (int d = 0; d < sh.rank; ++d) {
+            const int64_t i = (e / sh.stride[d]) % sh.n[d];
+            const int64_t next = (i == sh.n[d] - 1) ? e - (sh.n[d] - 1) * sh.stride[d] : e + sh.stride[d];
+            acc += Y[next * sh.rank + d] - Y[e * sh.rank + d];    // divergence += roll(dX, -1, axis=d) - dX
+        }
+        D[e] = acc;
+    }
+}
+
+// Y / max(|Y|_2 along the last axis, 1)   (tv_denoising.py:89-96)
+__global__ void __launch_bounds__(256) tv_ball_nd_kernel(const double* __restrict__ Y, int64_t npix, int k, double* __restrict__ out) {
+    const int64_t step = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < npix; e += step) {
+        double ss = 0.0;
+        for (int d = 0; d < k; ++d) ss += Y[e * k + d] * Y[e * k + d];
+        const double nrm = fmax(sqrt(ss), 1.0);
+        for (int d = 0; d < k; ++d) out[e * k + d] = Y[e * k + d] / nrm;
+    }
+}
+
+static int tvn_shape(const int64_t* shape, int rank, TvnShape* sh) {
+    if (rank < 1 || rank > TVN_MAX_RANK) { set_error("tv (N-d): rank %d not in 1..%d", rank, TVN_MAX_RANK); return 1; }
+    sh->rank = rank;
+    sh->total = 1;
+    for (int d = rank - 1; d >= 0; --d) {
+        if (shape[d] < 1) { set_error("tv (N-d): empty axis"); return 1; }
+        sh->n[d] = shape[d];
+        sh->stride[d] = sh->total;
+        sh->total *= shape[d];
+    }
+    return 0;
+}
+
 // Tiles of the bulk-copy-fed kernel: tiles_x x strips CTAs, one CTA per SM, the grid a whole number of waves.
 template <int CW>
 static int tvt_plan(int64_t n0, int64_t n1, int64_t* tiles_x_out, int64_t* strip_out) {
@@ -972,6 +1029,26 @@ static int tvt_launch(const double* x0, const double* g0, double tau, int64_t n0
 }  // namespace fb200
 
 using namespace fb200;
+
+extern "C" int fb200_tv_grad_nd(const double* X, const int64_t* shape, int rank, double* G, void* stream) {
+    TvnShape sh;
+    if (tvn_shape(shape, rank, &sh)) return 1;
+    tv_grad_nd_kernel<<<vec_grid(sh.total, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(X, sh, G);
+    return check_launch("tv_grad_nd");
+}
+
+extern "C" int fb200_tv_div_nd(const double* Y, const int64_t* shape, int rank, double* D, void* stream) {
+    TvnShape sh;
+    if (tvn_shape(shape, rank, &sh)) return 1;
+    tv_div_nd_kernel<<<vec_grid(sh.total, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(Y, sh, D);
+    return check_launch("tv_div_nd");
+}
+
+extern "C" int fb200_tv_ball_nd(const double* Y, int64_t npix, int k, double* out, void* stream) {
+    if (npix < 1 || k < 1) { set_error("tv_ball_nd: bad shape"); return 1; }
+    tv_ball_nd_kernel<<<vec_grid(npix, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(Y, npix, k, out);
+    return check_launch("tv_ball_nd");
+}
 
 extern "C" int fb200_tv_div_loss(const double* Y, int64_t n0, int64_t n1, int loss, const double* b, double* z,
                                  double* r, double* scal, void* ws, void* stream) {

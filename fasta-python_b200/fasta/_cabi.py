@@ -68,6 +68,9 @@ SIGNATURES = {
     "fb200_batched_bb": (_int, [_p, _int, _i64, _p, _p, _p, _p, _p, _int, _i64, _i64, _p, _p, _p, _p]),
     "fb200_batched_select": (_int, [_p, _p, _p, _i64, _i64, _p]),
     "fb200_batched_copy_cols": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _int, _p]),
+    "fb200_tv_grad_nd": (_int, [_p, _p, _int, _p, _p]),
+    "fb200_tv_div_nd": (_int, [_p, _p, _int, _p, _p]),
+    "fb200_tv_ball_nd": (_int, [_p, _i64, _int, _p, _p]),
     "fb200_tv_div_loss": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_tv_grad_bb": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),
     "fb200_tv_step_div_loss": (_int, [_p, _p, _dbl, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),

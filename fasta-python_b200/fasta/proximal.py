@@ -196,8 +196,15 @@ class TVBall(_Penalty):
     tag = _cabi.PROX_TV_BALL
 
     def prox(self, x, t):
-        assert x.shape[-1] == 2
-        return _apply(x, self.tag)
+        if x.shape[-1] == 2:
+            return _apply(x, self.tag)
+        tt = _device.torch()                     # other ranks: Y / max(|Y|_2 along the last axis, 1), tv_denoising.py:89-96
+        lib = _cabi.load()
+        xd = _device.to_device(x).contiguous()
+        out = tt.empty_like(xd)
+        k = int(xd.shape[-1])
+        _cabi.check(lib.fb200_tv_ball_nd(xd.data_ptr(), xd.numel() // k, k, out.data_ptr(), _device.stream_ptr()), "fb200_tv_ball_nd")
+        return _device.like_input(out, x)
 
 
 class RowGroupL2(_Penalty):

@@ -266,6 +266,13 @@ int fb200_tv_grad_bb_fused(const double* R, int64_t n0, int64_t n1, double* g, i
                            const double* g0, const double* x1, double tau, double* scal, void* ws,
                            void* stream);
 
+/* rank-generic forms of the same pair and of the ball projection (the reference's grad / div / prox are written for
+ * N-d arrays, tv_denoising.py:26-63,89-96): X has `rank` axes `shape[0..rank)`, G / Y carry a trailing axis of size `rank`
+ * (size k for the projection); one subtraction per output, the numpy summation order -- bit-identical.          */
+int fb200_tv_grad_nd(const double* X, const int64_t* shape, int rank, double* G, void* stream);
+int fb200_tv_div_nd(const double* Y, const int64_t* shape, int rank, double* D, void* stream);
+int fb200_tv_ball_nd(const double* Y, int64_t npix, int k, double* out, void* stream);
+
 /* whole TV iteration in one pass: step_div_loss plus the speculative g1 = grad(r) and the BB sums
  * scal[S_DX_G0, S_DX_SQ, S_XMXH_SQ, S_F, S_DX_DG, S_DG_SQ, S_G1_SQ]; reads x0, g0, b and writes x1, g1 only
  * (9U bytes, U = n0*n1*8; reference __init__.py:181-188,248-260 with tv_denoising.py:26-63,85-96)        */

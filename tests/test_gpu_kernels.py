@@ -378,3 +378,51 @@ def test_sweep_not_eligible_for_odd_shapes():
     torch = _t()
     assert _backends.DenseDriver(torch.zeros(10, 1001, dtype=torch.float64, device="cuda")).sweep_cluster == 0
     assert _backends.DenseDriver(torch.zeros(4, 212994, dtype=torch.float64, device="cuda")).sweep_cluster == 0
+
+
+@pytest.mark.parametrize("shape", [(7,), (1,), (5, 6, 4), (3, 4, 5, 6), (2, 1, 3), (17, 9, 11)])
+def test_tv_operators_of_any_rank(shape):
+    """fasta.tv.grad / div / TVBall.prox on N-d arrays (the reference's functions are rank-generic, tv_denoising.py:26-63,
+    89-96): bit-identical to the numpy loops, grad adjoint to div."""
+    import fasta
+    from oracle import problems
+    rng = np.random.RandomState(sum(shape))
+    X = rng.randn(*shape)
+    Y = rng.randn(*(shape + (len(shape),))) * 1.5
+    G = fasta.tv.grad(X)
+    D = fasta.tv.div(Y)
+    assert G.shape == shape + (len(shape),) and D.shape == shape
+    assert np.array_equal(G, problems.tv_grad(X)) and np.array_equal(D, problems.tv_div(Y))
+    lhs, rhs = float(np.sum(D * X)), float(np.sum(Y * G))
+    assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), 1.0)
+    P = fasta.proximal.TVBall().prox(Y, 0.3)
+    assert np.array_equal(P, problems._tv_ball(Y, 0.3))
+    A = fasta.tv.divergence_map(shape)
+    assert A.Vshape == shape + (len(shape),) and A.Wshape == shape and np.array_equal(A(Y), D) and np.array_equal(A.H(X), G)
+
+
+def test_tv_denoising_of_a_volume_matches_the_oracle():
+    """The reference's TV-denoising call (legacy form with the div / grad callables, tv_denoising.py:99) on a 3-D volume:
+    the generic back-end drives the N-d kernels; trajectory against the oracle on the same seed."""
+    import fasta
+    from oracle import fasta_oracle, problems
+    rng = np.random.RandomState(4)
+    n = (12, 10, 8)
+    vol = np.zeros(n)
+    vol[3:9, 2:7, 1:6] = 1.0
+    vol += 0.1 * rng.randn(*n)
+    mu = 0.1
+    b = vol / mu
+    Y0 = np.zeros(n + (3,))
+    opts = dict(adaptive=False, accelerate=True, verbose=False, tolerance=1e-5, max_iters=60, evaluate_objective=True)
+    np.random.seed(2)
+    ref = fasta_oracle.solve(problems.tv_div, problems.tv_grad, lambda Z: .5 * np.linalg.norm((Z - b).ravel()) ** 2, lambda Z: Z - b,
+                             lambda Y: 0, problems._tv_ball, Y0, **opts)
+    loss, pen = fasta.losses.LeastSquares(b), fasta.proximal.TVBall()
+    np.random.seed(2)
+    res = fasta.fasta(fasta.tv.div, fasta.tv.grad, loss.f, loss.gradf, pen.g, pen.prox, Y0, **opts)
+    assert res.backend == "GenericBackend"
+    assert (res.iteration_count, res.backtracks) == (ref.iteration_count, ref.backtracks)
+    n_it = ref.iteration_count
+    assert np.linalg.norm(res.solution - ref.solution) <= 1e-9 * np.linalg.norm(ref.solution)
+    assert np.max(np.abs(res.objectives[:n_it + 1] - ref.objectives[:n_it + 1]) / np.abs(ref.objectives[:n_it + 1])) <= 1e-10
