@@ -482,6 +482,7 @@ class FusedBackend:
         """Queue start(); its sums are snapshotted on the stream, start() later only fetches them."""
         self._queue_start()
         self.ws.scal_saved.copy_(self.ws.scal, non_blocking=True)
+        self.ws._saved_ready = False
         self._start_queued = True
 
     def _probe_outputs(self):
@@ -560,7 +561,7 @@ class FusedBackend:
             _cabi.check(self.lib.fb200_diff_nrm2sq(a.data_ptr(), b.data_ptr(), self.n, sc[S.S_AUX1:].data_ptr(),
                                                    self.ws.buf.data_ptr(), self._st()), "fb200_diff_nrm2sq")
             self.launches += 1
-            s = self.ws.fetch()
+            s = self.ws.fetch(with_saved=getattr(self, "_start_queued", False))
             return np.sqrt(s[S.S_G1_SQ]), np.sqrt(s[S.S_AUX1])
         d1, d2 = self._probe_outputs()
         _cabi.check(self.lib.fb200_diff_nrm2sq(d1.data_ptr(), d2.data_ptr(), self.n, sc[S.S_AUX0:].data_ptr(),
@@ -568,7 +569,7 @@ class FusedBackend:
         _cabi.check(self.lib.fb200_diff_nrm2sq(a.data_ptr(), b.data_ptr(), self.n, sc[S.S_AUX1:].data_ptr(),
                                                self.ws.buf.data_ptr(), self._st()), "fb200_diff_nrm2sq")
         self.launches += 2
-        s = self.ws.fetch()
+        s = self.ws.fetch(with_saved=getattr(self, "_start_queued", False))
         return np.sqrt(s[S.S_AUX0]), np.sqrt(s[S.S_AUX1])
 
     def lipschitz(self, v1, v2):

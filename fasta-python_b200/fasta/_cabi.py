@@ -126,8 +126,16 @@ def check(rc, what=""):
         raise Fb200Error(f"{what or 'fb200 call'} failed ({rc}): {msg}")
 
 
+_torch = None
+
+
 def require_cuda():
+    """torch, once a CUDA device has been seen (the check costs ~5 us per call through torch's NVML probe: remembered)."""
+    global _torch
+    if _torch is not None:
+        return _torch
     import torch
     if not torch.cuda.is_available():
         raise Fb200Error("no CUDA device: fasta-b200 computes only on sm_100a GPUs (no CPU fallback)")
+    _torch = torch
     return torch

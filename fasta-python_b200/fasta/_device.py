@@ -46,7 +46,29 @@ def ptr(tensor):
 
 
 def stream_ptr():
-    return torch().cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream on the current device (the raw accessor: torch.cuda.current_stream()
+    costs ~14 us per call, and a solve asks nine times)."""
+    t = torch()
+    try:
+        return t._C._cuda_getCurrentRawStream(t._C._cuda_getDevice())
+    except AttributeError:                      # pragma: no cover  (other torch builds)
+        return t.cuda.current_stream().cuda_stream
+
+
+_stream_objs = {}
+
+
+def current_stream():
+    """torch's current stream object, cached by (device, raw handle)."""
+    t = torch()
+    try:
+        key = (t._C._cuda_getDevice(), t._C._cuda_getCurrentRawStream(t._C._cuda_getDevice()))
+    except AttributeError:                      # pragma: no cover
+        return t.cuda.current_stream()
+    s = _stream_objs.get(key)
+    if s is None:
+        s = _stream_objs[key] = t.cuda.current_stream()
+    return s
 
 
 class Workspace:
@@ -61,6 +83,9 @@ class Workspace:
         self.scal = t.zeros(_cabi.NSCAL, dtype=t.float64, device=self.device)
         self.host = t.zeros(_cabi.NSCAL, dtype=t.float64).pin_memory()
         self._np = self.host.numpy()
+        self.host_saved = t.zeros(_cabi.NSCAL, dtype=t.float64).pin_memory()
+        self._np_saved = self.host_saved.numpy()
+        self._saved_ready = False
         self.scal_saved = t.zeros(_cabi.NSCAL, dtype=t.float64, device=self.device)   # snapshot of the start() sums
         self._stage = None                                                            # pinned upload staging (2 vectors)
         # in-stream snapshots of the scalar block: a trial queued ahead overwrites `scal` before the host has read the
@@ -77,11 +102,17 @@ class Workspace:
             self.buf = t.zeros(need, dtype=t.uint8, device=self.device)
             self.nbytes = need
 
-    def fetch(self, saved=False):
-        """One D2H copy of the scalar block + one stream sync: the per-decision-point sync."""
-        t = torch()
+    def fetch(self, saved=False, with_saved=False):
+        """One D2H copy of the scalar block + one stream sync: the per-decision-point sync.  with_saved: the snapshot of
+        the start() sums rides along in the same sync (fetch_saved() then returns it without another one)."""
+        if saved and self._saved_ready:
+            self._saved_ready = False
+            return self._np_saved
         self.host.copy_(self.scal_saved if saved else self.scal, non_blocking=True)
-        t.cuda.current_stream().synchronize()
+        if with_saved:
+            self.host_saved.copy_(self.scal_saved, non_blocking=True)
+        current_stream().synchronize()
+        self._saved_ready = bool(with_saved)
         return self._np      # np.float64 elements
 
     def snapshot(self):

@@ -106,7 +106,7 @@ def run(be, x0_shape, *, adaptive=True, accelerate=False, verbose=True, max_iter
         else be.ws._resident_host
     be.ws._resident_host = host
     host.copy_(block, non_blocking=True)
-    t.cuda.current_stream().synchronize()                   # the one sync of the solve
+    _device.current_stream().synchronize()                  # the one sync of the solve
     hb = host.numpy().copy()                                # the pinned mirror is reused by the next solve
     o = 0
     residual_hist, norm_residual_hist, tau_hist, alphas_all = (hb[o + k * mi: o + (k + 1) * mi] for k in range(4))
