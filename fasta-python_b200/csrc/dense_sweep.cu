@@ -443,7 +443,7 @@ namespace fb200 {
 int launch_peer_exchange(const uint64_t* peer_data, const uint64_t* peer_flags, int rank, int P, uint32_t epoch, int64_t n,
                          const double* gsrc, int nsplit, int64_t ld, const double* fpart, const double* fpart2, int with_loss,
                          double* g, int bb, const double* x0, const double* xhat, const double* dx, double tau,
-                         const int* decide_i, const double* decide_d, double* scal, Workspace& w, cudaStream_t st);
+                         const int* decide_i, const double* decide_d, double* host_out, double* scal, Workspace& w, cudaStream_t st);
 }
 
 extern "C" int fb200_sweep_exchange_supported(void) { return use_grid_sweep() ? 1 : 0; }
@@ -453,7 +453,7 @@ extern "C" int fb200_dense_sweep_exchange(const double* A, int64_t lda, int64_t 
                                           const uint64_t* peer_data, const uint64_t* peer_flags, int rank, int P,
                                           uint32_t epoch, double* g, int bb, const double* x0, const double* xhat,
                                           const double* dx, double tau, const int* decide_i, const double* decide_d,
-                                          double* scal, void* ws, size_t ws_bytes, void* stream) {
+                                          double* host_out, double* scal, void* ws, size_t ws_bytes, void* stream) {
     if (!use_grid_sweep()) { set_error("dense_sweep_exchange: needs the grid sweep kernel"); return 1; }
     if (P < 1 || P > FB200_MAX_PEERS || rank < 0 || rank >= P) { set_error("dense_sweep_exchange: bad rank / world size"); return 1; }
     int64_t raw[2] = {0, 0};
@@ -466,7 +466,7 @@ extern "C" int fb200_dense_sweep_exchange(const double* A, int64_t lda, int64_t 
     const double* f_first = za0 ? w.fpart + FPART_MAX / 2 : w.fpart;
     const double* f_second = za0 ? w.fpart : nullptr;
     return launch_peer_exchange(peer_data, peer_flags, rank, P, epoch, N, w.dense, int(raw[0]), raw[1], f_first, f_second, with_loss,
-                                g, bb, x0, xhat, dx, tau, decide_i, decide_d, scal, w, static_cast<cudaStream_t>(stream));
+                                g, bb, x0, xhat, dx, tau, decide_i, decide_d, host_out, scal, w, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int fb200_dense_sweep_accel(const double* A, int64_t lda, int64_t M, int64_t N, const double* xa1, int loss,

@@ -474,7 +474,15 @@ __device__ void decide_core(double* scal, double tau, const DecideArgs& d) {
     scal[FB200_S_SKIP] = stop ? 1.0 : 0.0;
 }
 
-__global__ void trial_decide_kernel(double* scal, double tau, DecideArgs d) { decide_core(scal, tau, d); }
+// host_out (optional): pinned, device-visible host memory that receives the scalar block once the decisions are taken --
+// the per-trial snapshot without a memcpy node in the stream (the host waits on an event recorded behind the kernel)
+__global__ void __launch_bounds__(FB200_NSCAL)
+trial_decide_kernel(double* scal, double tau, DecideArgs d, double* __restrict__ host_out) {
+    if (threadIdx.x == 0) decide_core(scal, tau, d);
+    if (!host_out) return;
+    __syncthreads();
+    host_out[threadIdx.x] = __ldcg(&scal[threadIdx.x]);
+}
 
 // =================================================================================================
 // Row-sharded map, ONE kernel for what follows the local sweep (reference __init__.py:248,254-260,195-201,253-281 on the
@@ -512,10 +520,16 @@ peer_exchange_kernel(PeerPtrs pp, int rank, int P, uint32_t epoch, int64_t n, co
                      int64_t ld, const double* __restrict__ fpart, const double* __restrict__ fpart2, int with_loss,
                      double* __restrict__ g, const double* __restrict__ x0, const double* __restrict__ xhat,
                      const double* __restrict__ dx, double tau, int decide, DecideArgs dargs, double* scal, double* red,
-                     unsigned* counter) {
+                     unsigned* counter, double* __restrict__ host_out) {
     if (isnan(tau)) {                                       // speculative trial: see fb200_trial_decide
         if (__ldcg(&scal[FB200_S_SKIP]) != 0.0) {
-            if (decide && blockIdx.x == 0 && threadIdx.x == 0) decide_core(scal, tau, dargs);    // reports S_SKIPPED
+            if (decide && blockIdx.x == 0) {
+                if (threadIdx.x == 0) decide_core(scal, tau, dargs);    // reports S_SKIPPED
+                if (host_out) {
+                    __syncthreads();
+                    if (threadIdx.x < FB200_NSCAL) host_out[threadIdx.x] = __ldcg(&scal[threadIdx.x]);
+                }
+            }
             return;
         }
     }
@@ -594,16 +608,22 @@ peer_exchange_kernel(PeerPtrs pp, int rank, int P, uint32_t epoch, int64_t n, co
     double* const out[3] = {BB >= 2 ? scal + FB200_S_DX_DG : nullptr, BB >= 2 ? scal + FB200_S_DG_SQ : nullptr,
                             BB >= 1 ? scal + FB200_S_G1_SQ : nullptr};
     const bool last = grid_sum_last<3>(s, red, counter, out);
-    if (last && decide && threadIdx.x == 0) {
-        __threadfence();                                    // block 0's S_F precedes its ticket; ours came after
-        decide_core(scal, tau, dargs);
+    if (last && decide) {
+        if (threadIdx.x == 0) {
+            __threadfence();                                // block 0's S_F precedes its ticket; ours came after
+            decide_core(scal, tau, dargs);
+        }
+        if (host_out) {                                     // the snapshot, straight into pinned host memory
+            __syncthreads();
+            if (threadIdx.x < FB200_NSCAL) host_out[threadIdx.x] = __ldcg(&scal[threadIdx.x]);
+        }
     }
 }
 
 int launch_peer_exchange(const uint64_t* peer_data, const uint64_t* peer_flags, int rank, int P, uint32_t epoch, int64_t n,
                          const double* gsrc, int nsplit, int64_t ld, const double* fpart, const double* fpart2, int with_loss,
                          double* g, int bb, const double* x0, const double* xhat, const double* dx, double tau,
-                         const int* decide_i, const double* decide_d, double* scal, Workspace& w, cudaStream_t st) {
+                         const int* decide_i, const double* decide_d, double* host_out, double* scal, Workspace& w, cudaStream_t st) {
     PeerPtrs pp;
     for (int k = 0; k < FB200_MAX_PEERS; ++k) {
         pp.data[k] = reinterpret_cast<double*>(peer_data[k < P ? k : 0]);
@@ -618,7 +638,7 @@ int launch_peer_exchange(const uint64_t* peer_data, const uint64_t* peer_flags, 
         if (d.window > FB200_FRING) { set_error("peer_exchange: window %d exceeds the device ring (%d)", d.window, FB200_FRING); return 1; }
     }
     if (sm_count() < PEER_CHUNKS) { set_error("peer_exchange: needs %d resident blocks", PEER_CHUNKS); return 1; }
-#define FB200_PEERX(BBV) peer_exchange_kernel<BBV><<<PEER_CHUNKS, VEC_THREADS, 0, st>>>(pp, rank, P, epoch, n, gsrc, nsplit, ld, fpart, fpart2, with_loss, g, x0, xhat, dx, tau, decide, d, scal, w.red, w.counter)
+#define FB200_PEERX(BBV) peer_exchange_kernel<BBV><<<PEER_CHUNKS, VEC_THREADS, 0, st>>>(pp, rank, P, epoch, n, gsrc, nsplit, ld, fpart, fpart2, with_loss, g, x0, xhat, dx, tau, decide, d, scal, w.red, w.counter, decide ? host_out : nullptr)
     switch (bb) {
         case 0: FB200_PEERX(0); break;
         case 1: FB200_PEERX(1); break;
@@ -831,14 +851,14 @@ extern "C" int fb200_decide_init(double* scal, double f0, double g0_sq, void* st
 
 extern "C" int fb200_trial_decide(double* scal, double tau, int loss, int adaptive, int backtrack, int bt,
                                   int max_backtracks, int window, int stop_rule, double tolerance, int host_it,
-                                  double host_max_residual, double host_g0_sq, void* stream) {
+                                  double host_max_residual, double host_g0_sq, double* host_out, void* stream) {
     if (!scal) { set_error("trial_decide: null scalar block"); return 1; }
     if (window < 1 || window > FB200_FRING) { set_error("trial_decide: window %d not in 1..%d", window, FB200_FRING); return 1; }
     DecideArgs d{};
     d.loss = loss; d.adaptive = adaptive; d.backtrack = backtrack; d.bt = bt; d.max_backtracks = max_backtracks;
     d.window = window; d.stop_rule = stop_rule; d.host_it = host_it;
     d.tolerance = tolerance; d.host_max_residual = host_max_residual; d.host_g0_sq = host_g0_sq;
-    trial_decide_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(scal, tau, d);
+    trial_decide_kernel<<<1, FB200_NSCAL, 0, static_cast<cudaStream_t>(stream)>>>(scal, tau, d, host_out);
     return check_launch("trial_decide");
 }
 

@@ -239,7 +239,7 @@ class ShardedDriver:
                                              and self.local.lib.fb200_sweep_exchange_supported())
         return probe
 
-    def _sweep_exchange(self, peer, x, loss_tag, b, z, r, za0, c, za1, g, bb, x0, xhat, dx, tau, ws, decide):
+    def _sweep_exchange(self, peer, x, loss_tag, b, z, r, za0, c, za1, g, bb, x0, xhat, dx, tau, ws, decide, host_out=0):
         peer["calls"] += 1
         epoch = peer["calls"]
         di = dd = None
@@ -252,18 +252,18 @@ class ShardedDriver:
                                                      z.data_ptr(), _device.ptr(r), _device.ptr(za0), float(c), _device.ptr(za1),
                                                      peer["ptrs"][epoch & 1], peer["flags"], peer["rank"], peer["P"],
                                                      epoch & 0xFFFFFFFF, g.data_ptr(), int(bb), _device.ptr(x0),
-                                                     _device.ptr(xhat), _device.ptr(dx), float(tau), di, dd,
+                                                     _device.ptr(xhat), _device.ptr(dx), float(tau), di, dd, host_out,
                                                      ws.scal.data_ptr(), ws.buf.data_ptr(), ws.nbytes, _device.stream_ptr()),
                     "fb200_dense_sweep_exchange")
         L.launches += 2
         self.collectives += 1
         self.peer_reductions += 1
 
-    def sweep(self, x, loss_tag, b, z, r, g, bb, x0, xhat, dx, tau, ws, decide=None):
+    def sweep(self, x, loss_tag, b, z, r, g, bb, x0, xhat, dx, tau, ws, decide=None, host_out=0):
         n = g.numel()
         fused = self._fused(g)
         if fused is not None:
-            self._sweep_exchange(fused, x, loss_tag, b, z, r, None, 0.0, None, g, bb, x0, xhat, dx, tau, ws, decide)
+            self._sweep_exchange(fused, x, loss_tag, b, z, r, None, 0.0, None, g, bb, x0, xhat, dx, tau, ws, decide, host_out)
             return
         assert decide is None
         peer = self._peer(n, g.device) if g.is_cuda else None
@@ -646,6 +646,9 @@ class FusedBackend:
         st = self._st()
         kind = None
         fused_decide = None
+        slot, host_out = (None, 0)
+        if self._spec_mode and self.ws.zero_copy:
+            slot, host_out = self.ws.snapshot_begin()     # the deciding kernel writes the sums straight into this pinned slot
         if self.use_tv_fused and self.drv.iter_fused_ok:
             # one kernel per trial; the gradient of an accepted trial is already in G[gc] (speculative, like the sweep)
             self.drv.iterate_fused(x0, g0, tau, self.loss.tag, self.loss.b, x1, self.G[self.gc], self.ws)
@@ -672,7 +675,7 @@ class FusedBackend:
                     fused_decide = self._decide[:3] + (int(bt),) + self._decide[3:6] + (int(host[0]), self._decide[6],
                                                                                          float(host[1]), float(host[2]))
                     self.drv.sweep(x1, self.loss.tag, self.loss.b, z1, self.R, self.G[self.gc], 2, x0, self.XH, self.DX, tau,
-                                   self.ws, decide=fused_decide)
+                                   self.ws, decide=fused_decide, host_out=host_out)
                 else:
                     self.drv.sweep(x1, self.loss.tag, self.loss.b, z1, self.R, self.G[self.gc], 2, x0, self.XH, self.DX, tau,
                                    self.ws)
@@ -683,13 +686,13 @@ class FusedBackend:
         if not self._spec_mode:
             return kind, None
         if fused_decide is not None:
-            return kind, self.ws.snapshot()
+            return kind, (self.ws.snapshot_end(slot) if slot is not None else self.ws.snapshot())
         loss_tag, adaptive, backtrack, max_bt, window, rule, tol = self._decide
         _cabi.check(self.lib.fb200_trial_decide(self.ws.scal.data_ptr(), float(tau), loss_tag, adaptive, backtrack, int(bt),
                                                 max_bt, window, rule, tol, int(host[0]), float(host[1]), float(host[2]),
-                                                st), "fb200_trial_decide")
+                                                host_out, st), "fb200_trial_decide")
         self.launches += 1
-        return kind, self.ws.snapshot()
+        return kind, (self.ws.snapshot_end(slot) if slot is not None else self.ws.snapshot())
 
     def _collect_trial(self, handle):
         kind, ticket = handle

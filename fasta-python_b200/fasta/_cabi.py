@@ -76,7 +76,7 @@ SIGNATURES = {
     "fb200_tv_step_div_loss": (_int, [_p, _p, _dbl, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_tv_grad_bb_fused": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),
     "fb200_decide_init": (_int, [_p, _dbl, _dbl, _p]),
-    "fb200_trial_decide": (_int, [_p, _dbl, _int, _int, _int, _int, _int, _int, _int, _dbl, _int, _dbl, _dbl, _p]),
+    "fb200_trial_decide": (_int, [_p, _dbl, _int, _int, _int, _int, _int, _int, _int, _dbl, _int, _dbl, _dbl, _p, _p]),
     "fb200_tv_fista_fused": (_int, [_p, _p, _dbl, _dbl, _i64, _i64, _int] + [_p] * 10),
     "fb200_tv_iter_fused": (_int, [_p, _p, _dbl, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_peer_allreduce_bb": (_int, [_p, _int, _i64, _p, _int, _p, _p, _p, _dbl, _int, _p, _p, _p]),
@@ -88,7 +88,7 @@ SIGNATURES = {
     "fb200_prox_apply": (_int, [_p, _int, _dbl, _dbl, _i64, _p, _p, _p]),
     "fb200_sweep_exchange_supported": (_int, []),
     "fb200_dense_sweep_exchange": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _p, _p, _p, _dbl, _p, _p, _p, _int, _int, ctypes.c_uint32,
-                                          _p, _int, _p, _p, _p, _dbl, _p, _p, _p, _p, _sz, _p]),
+                                          _p, _int, _p, _p, _p, _dbl, _p, _p, _p, _p, _p, _sz, _p]),
     "fb200_randn_scratch_bytes": (_sz, [_i64]),
     "fb200_randn_legacy": (_int, [_p, _i64, _p, _p, _sz, _p, _p, _p]),
 }

@@ -296,11 +296,13 @@ int fb200_tv_iter_fused(const double* x0, const double* g0, double tau, int64_t 
  * device's loop state from the host's (host_it = loop index i, host_max_residual, host_g0_sq = |gradf0|^2), so a
  * last-bit disagreement between the two algebras can cost a wasted or repeated trial but never a wrong result: the
  * host decides from the sums it reads, uses scal[FB200_S_TAU_USED] as the step size of a speculative trial, and
- * repeats by value a trial that reports FB200_S_SKIPPED.                                                      */
+ * repeats by value a trial that reports FB200_S_SKIPPED.  host_out (or NULL): FB200_NSCAL doubles of pinned,
+ * device-visible HOST memory that receive the scalar block after the decisions -- the per-trial snapshot without a
+ * memcpy in the stream (the caller waits on an event recorded behind the kernel).                                */
 int fb200_decide_init(double* scal, double f0, double g0_sq, void* stream);
 int fb200_trial_decide(double* scal, double tau, int loss, int adaptive, int backtrack, int bt, int max_backtracks,
                        int window, int stop_rule, double tolerance, int host_it, double host_max_residual,
-                       double host_g0_sq, void* stream);
+                       double host_g0_sq, double* host_out, void* stream);
 
 /* whole accelerated (FISTA) TV trial in one pass (reference __init__.py:181-188,220-260 with tv_denoising.py:26-63,
  * 85-96): prox point xa1 and its image za1 = div(xa1), extrapolation x1 = xa1 + c (xa1 - xa0), z1 = za1 + c (za1 - za0),
@@ -361,14 +363,15 @@ int fb200_amax(const double* a, int64_t n, double* out, void* stream);
  *   epoch          call counter, identical on every rank, +1 per call (also for calls that return at once)
  *   za0 / c / za1  NULL / 0 / NULL, or the FISTA mode of fb200_dense_sweep_accel
  *   decide_i       {loss, adaptive, backtrack, bt, max_backtracks, window, stop_rule, host_it} or NULL
- *   decide_d       {tolerance, host_max_residual, host_g0_sq}                                                      */
+ *   decide_d       {tolerance, host_max_residual, host_g0_sq}
+ *   host_out       as for fb200_trial_decide (used only with decide_i)                                              */
 int fb200_sweep_exchange_supported(void);
 int fb200_dense_sweep_exchange(const double* A, int64_t lda, int64_t M, int64_t N, const double* x, int loss,
                                const double* b, double* z, double* r, const double* za0, double c, double* za1,
                                const uint64_t* peer_data, const uint64_t* peer_flags, int rank, int P, uint32_t epoch,
                                double* g, int bb, const double* x0, const double* xhat, const double* dx, double tau,
-                               const int* decide_i, const double* decide_d, double* scal, void* ws, size_t ws_bytes,
-                               void* stream);
+                               const int* decide_i, const double* decide_d, double* host_out, double* scal, void* ws,
+                               size_t ws_bytes, void* stream);
 
 /* ---- np.random.randn on the device (csrc/legacy_rng.cu) --------------------------------------------------------
  * Replaces `x1 = np.random.randn(*x0.shape); x2 = np.random.randn(*x0.shape)` (reference fasta/__init__.py:102-103):
