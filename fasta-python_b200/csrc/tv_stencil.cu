@@ -568,8 +568,8 @@ struct TvtShape {
 template <int LOSS, int CW, int U, int TVT_RING>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
 tv_iter_tma_kernel(const double2* __restrict__ x0, const double2* __restrict__ g0, double tau, int n0, int n1,
-                   const double* __restrict__ b, double2* __restrict__ x1, double2* __restrict__ g1, int tiles_x, int strip,
-                   double* scal, double* red, unsigned* counter) {
+                   const double* __restrict__ b, double2* __restrict__ x1, double2* __restrict__ g1, int tiles_x, int tile_cols,
+                   int strip, double* scal, double* red, unsigned* counter) {
     using Sh = TvtShape<CW, TVT_RING>;
     extern __shared__ __align__(128) unsigned char tvt_smem[];
     uint64_t* full  = reinterpret_cast<uint64_t*>(tvt_smem + TVT_RING * Sh::SLOT);
@@ -580,7 +580,8 @@ tv_iter_tma_kernel(const double2* __restrict__ x0, const double2* __restrict__ g
         tau = __ldcg(&scal[FB200_S_TAU]);
     }
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    const int j0 = tx * (TVM_COLS * CW), jL = j0 - 1;
+    const int j0 = tx * tile_cols, jL = j0 - 1;             // tile_cols: even, <= 30 * CW; equal tiles, the last one maybe narrower
+    const int j_end = min(n1, j0 + tile_cols);              // one past the tile's last column
     const int i0 = ty * strip;
     const int i1 = min(n0, i0 + strip);
     const int nrows = i1 - i0 + 2;                          // image rows i0-1 .. i1 (wrapped)
@@ -597,14 +598,14 @@ tv_iter_tma_kernel(const double2* __restrict__ x0, const double2* __restrict__ g
         // ===================================== producer =====================================
         if (lane == 0) {
             const uint64_t pol = policy_evict_first();
-            const int jR = j0 + TVM_COLS * CW;                              // right halo column (unwrapped)
+            const int jR = j_end;                                           // right halo column (unwrapped; n1 at the image edge)
             const int cbeg = jL < 0 ? 0 : jL, cend = jR < n1 ? jR : n1 - 1; // contiguous image columns of the tile
             const uint32_t main_xg = uint32_t(cend - cbeg + 1) * 16u;
             const int bbeg = jL < 0 ? 0 : jL - 1;                           // even (j0 is even)
             int bend = cend;
             if (((bend - bbeg + 1) & 1) && bend + 1 < n1) ++bend;           // even element count (n1 is even)
             const uint32_t main_b = uint32_t(bend - bbeg + 1) * 8u;
-            const uint32_t total = 2u * main_xg + main_b + (jL < 0 ? 2u * 16u + 16u : 0u) + (jR >= n1 ? 2u * 16u : 0u);
+            const uint32_t total = 2u * main_xg + main_b + (jL < 0 ? 2u * 16u + 16u : 0u) + (jR >= n1 ? 2u * 16u : 0u);     // jR == n1: the tile touches the right image edge
             for (int k = 0; k < nrows; ++k) {
                 const int slot = k % TVT_RING;
                 mbar_wait(&empty[slot], ((k / TVT_RING) & 1) ^ 1u);
@@ -632,7 +633,8 @@ tv_iter_tma_kernel(const double2* __restrict__ x0, const double2* __restrict__ g
         // ===================================== compute warps: the marching scheme from shared memory ==========
         const int j = j0 + TVM_COLS * warp - 1 + lane;      // unwrapped column of this lane
         const int cx = TVM_COLS * warp + lane;              // its offset in a ring row
-        const bool out_lane = lane >= 1 && lane <= TVM_COLS && j < n1;
+        const bool out_lane = lane >= 1 && lane <= TVM_COLS && j < j_end;
+        const bool idle_warp = j0 + TVM_COLS * warp >= j_end;      // a warp beyond the tile's columns only keeps the ring turning
         const double rtau = 1.0 / tau;
         auto slot_ptr = [&](int k) { return tvt_smem + size_t(k % TVT_RING) * Sh::SLOT; };
         auto wait_row = [&](int k) { mbar_wait(&full[k % TVT_RING], (k / TVT_RING) & 1); };
@@ -646,6 +648,12 @@ tv_iter_tma_kernel(const double2* __restrict__ x0, const double2* __restrict__ g
             gr = X[Sh::WC + cx];
         };
         auto load_b = [&](int k) { return reinterpret_cast<const double*>(slot_ptr(k) + 2 * Sh::WC * 16)[cx + 1]; };
+        if (idle_warp) {
+            for (int k = 0; k < nrows; ++k) {
+                wait_row(k);
+                free_row(k);
+            }
+        } else {
         double2 a_c, g_c, a_t, g_t, h;
         wait_row(0);
         load_xg(0, a_t, g_t);
@@ -717,6 +725,7 @@ tv_iter_tma_kernel(const double2* __restrict__ x0, const double2* __restrict__ g
             }
         }
         free_row(nrows - 1);                                       // the last row's slot (its b is never read)
+        }
     }
     double* const out[7] = {scal + FB200_S_DX_G0, scal + FB200_S_DX_SQ, scal + FB200_S_XMXH_SQ, scal + FB200_S_F,
                             scal + FB200_S_DX_DG, scal + FB200_S_DG_SQ, scal + FB200_S_G1_SQ};
@@ -946,8 +955,11 @@ static int tvn_shape(const int64_t* shape, int rank, TvnShape* sh) {
 
 // Tiles of the bulk-copy-fed kernel: tiles_x x strips CTAs, one CTA per SM, the grid a whole number of waves.
 template <int CW>
-static int tvt_plan(int64_t n0, int64_t n1, int64_t* tiles_x_out, int64_t* strip_out) {
+static int tvt_plan(int64_t n0, int64_t n1, int64_t* tiles_x_out, int64_t* tile_cols_out, int64_t* strip_out) {
     const int64_t tiles_x = (n1 + TVM_COLS * CW - 1) / (TVM_COLS * CW);
+    // equal column tiles (even width: rows of b stay 16-byte aligned): at 4096 columns 9 tiles of 456 instead of 8 x 480 + 256
+    int64_t tile_cols = ((n1 + tiles_x - 1) / tiles_x + 1) / 2 * 2;
+    if (tile_cols > TVM_COLS * CW) tile_cols = TVM_COLS * CW;
     const int64_t nsm = sm_count();
     double best = 1e300;
     int64_t strip = 0;
@@ -959,10 +971,11 @@ static int tvt_plan(int64_t n0, int64_t n1, int64_t* tiles_x_out, int64_t* strip
         const double cost = double(k) * (double(st) + 4.0);         // halo rows + pipeline fill per tile
         if (cost < best - 1e-9) { best = cost; strip = st; }
     }
+    *tiles_x_out = tiles_x;
+    *tile_cols_out = tile_cols;
     if (!strip) return 1;
     if (tiles_x * ((n0 + strip - 1) / strip) > MAX_RED_BLOCKS) return 1;
-    if (double(n1) < 0.9 * double(tiles_x * TVM_COLS * CW)) return 1;      // a mostly empty last column tile: not worth it
-    *tiles_x_out = tiles_x;
+    if (double(n1) < 0.75 * double(tiles_x * TVM_COLS * CW)) return 1;     // mostly idle compute warps: not worth it
     *strip_out = strip;
     return 0;
 }
@@ -979,11 +992,10 @@ template <int LOSS, int CW, int U, int RING>
 static int tvt_launch_as(const double* x0, const double* g0, double tau, int64_t n0, int64_t n1, const double* b, double* x1, double* g1,
                          double* scal, Workspace& w, cudaStream_t st, int mode, bool* done) {
     using Sh = TvtShape<CW, RING>;
-    int64_t tiles_x = 0, strip = 0;
-    if (tvt_plan<CW>(n0, n1, &tiles_x, &strip)) {
+    int64_t tiles_x = 0, tile_cols = 0, strip = 0;
+    if (tvt_plan<CW>(n0, n1, &tiles_x, &tile_cols, &strip)) {
         if (mode != 2) return 0;
-        tiles_x = (n1 + TVM_COLS * CW - 1) / (TVM_COLS * CW);      // tests: any image, one strip per 64 rows
-        strip = n0 < 64 ? n0 : 64;
+        strip = n0 < 64 ? n0 : 64;                                 // tests: any image, one strip per 64 rows
         if (tiles_x * ((n0 + strip - 1) / strip) > MAX_RED_BLOCKS) return 0;
     }
     static DeviceOnce once;
@@ -997,8 +1009,8 @@ static int tvt_launch_as(const double* x0, const double* g0, double tau, int64_t
         return 1;
     const int64_t blocks = tiles_x * ((n0 + strip - 1) / strip);
     tv_iter_tma_kernel<LOSS, CW, U, RING><<<unsigned(blocks), Sh::THREADS, Sh::SMEM, st>>>(
-        (const double2*)x0, (const double2*)g0, tau, int(n0), int(n1), b, (double2*)x1, (double2*)g1, int(tiles_x), int(strip), scal,
-        w.red, w.counter);
+        (const double2*)x0, (const double2*)g0, tau, int(n0), int(n1), b, (double2*)x1, (double2*)g1, int(tiles_x), int(tile_cols),
+        int(strip), scal, w.red, w.counter);
     *done = true;
     return check_launch("tv_iter_tma");
 }
