@@ -75,6 +75,7 @@ SIGNATURES = {
     "fb200_tv_grad_bb": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),
     "fb200_tv_step_div_loss": (_int, [_p, _p, _dbl, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "fb200_tv_grad_bb_fused": (_int, [_p, _i64, _i64, _p, _int, _p, _p, _p, _dbl, _p, _p, _p]),
+    "fb200_snapshot_copy": (_int, [_p, _p, _sz, _p, _p, _p, _p]),
     "fb200_decide_init": (_int, [_p, _dbl, _dbl, _p]),
     "fb200_trial_decide": (_int, [_p, _dbl, _int, _int, _int, _int, _int, _int, _int, _dbl, _int, _dbl, _dbl, _p, _p]),
     "fb200_tv_fista_fused": (_int, [_p, _p, _dbl, _dbl, _i64, _i64, _int] + [_p] * 10),

@@ -125,20 +125,43 @@ class Workspace:
         self._events[k].record()
         return k
 
-    # the same snapshot WITHOUT a memcpy in the stream: the kernel that takes the decisions writes the block straight
-    # into the pinned slot (torch's pinned memory is device-visible under unified addressing).  Measured and left OFF:
-    # same box, TV 4096^2 2779 it/s in loop against 2881 with the in-stream copy (the deciding kernel retires only
-    # after its PCIe writes have), config 2 206.9 against 207.8 (profiles/r02_zerocopy_ab.log)
-    zero_copy = os.environ.get("FASTA_B200_ZEROCOPY_SNAPSHOT", "0") != "0"
+    # The same snapshot WITHOUT a memcpy node on the compute stream.  FASTA_B200_SNAPSHOT selects how:
+    #   stream   (the round-1 way) D2H copy of `scal` queued on the compute stream behind the deciding kernel
+    #   side     the deciding kernel copies the block into a device ring slot; a side stream waits for it and copies the
+    #            slot to pinned memory (fb200_snapshot_copy): the next trial's kernel starts right behind the deciding one
+    #   zerocopy the deciding kernel writes the block straight into the pinned slot (device-visible under unified
+    #            addressing); measured slower: it retires only after its PCIe writes (profiles/r02_zerocopy_ab.log)
+    mode = os.environ.get("FASTA_B200_SNAPSHOT", "side")
+    if os.environ.get("FASTA_B200_ZEROCOPY_SNAPSHOT", "0") != "0":
+        mode = "zerocopy"
+    zero_copy = mode in ("side", "zerocopy")          # the deciding kernel takes a destination pointer
+
+    def _side_setup(self):
+        t = torch()
+        self._ring = t.zeros((4, _cabi.NSCAL), dtype=t.float64, device=self.device)
+        self._side = t.cuda.Stream(device=self.device)
+        self._ev_main = [t.cuda.Event() for _ in range(4)]
+        for e in self._ev_main + self._events:       # a torch event gets its CUDA handle on first record
+            e.record()
+        t.cuda.current_stream().synchronize()
 
     def snapshot_begin(self):
-        """Next pinned slot: (ticket, host pointer for the deciding kernel)."""
+        """Next pinned slot: (ticket, destination pointer for the deciding kernel)."""
         k = self._ticket & 3
         self._ticket += 1
+        if self.mode == "side":
+            if getattr(self, "_ring", None) is None:
+                self._side_setup()
+            return k, self._ring[k].data_ptr()
         return k, self._slots[k].data_ptr()
 
     def snapshot_end(self, k):
-        self._events[k].record()
+        if self.mode == "side":
+            _cabi.check(self.lib.fb200_snapshot_copy(self._slots[k].data_ptr(), self._ring[k].data_ptr(), 8 * _cabi.NSCAL,
+                                                     stream_ptr(), self._side.cuda_stream, self._ev_main[k].cuda_event,
+                                                     self._events[k].cuda_event), "fb200_snapshot_copy")
+        else:
+            self._events[k].record()
         return k
 
     def collect(self, ticket):

@@ -300,6 +300,11 @@ int fb200_tv_iter_fused(const double* x0, const double* g0, double tau, int64_t 
  * device-visible HOST memory that receive the scalar block after the decisions -- the per-trial snapshot without a
  * memcpy in the stream (the caller waits on an event recorded behind the kernel).                                */
 int fb200_decide_init(double* scal, double f0, double g0_sq, void* stream);
+/* the snapshot of a trial's scalar block off the compute stream: event on `main_stream`, wait + D2H copy + event on
+ * `side_stream` (src_dev = the device slot the deciding kernel filled through its host_out argument, which may be any
+ * device-visible address).  Streams / events are cudaStream_t / cudaEvent_t handles owned by the caller.        */
+int fb200_snapshot_copy(void* dst_host, const void* src_dev, size_t bytes, void* main_stream, void* side_stream,
+                        void* ev_main, void* ev_done);
 int fb200_trial_decide(double* scal, double tau, int loss, int adaptive, int backtrack, int bt, int max_backtracks,
                        int window, int stop_rule, double tolerance, int host_it, double host_max_residual,
                        double host_g0_sq, double* host_out, void* stream);
