@@ -93,3 +93,12 @@ def test_convergence_record_fields():
         assert getattr(c, name) == val
     assert c.objectives is None and c.iterates is None and c.function_hist is None
     assert fasta.EPSILON == 1e-12
+
+
+def test_column_shard_deals_round_robin():
+    """fasta.batched.column_shard: every column to exactly one rank, neighbours in the path to different ranks."""
+    from fasta.batched import column_shard
+    for n, world in ((256, 8), (6, 2), (5, 4), (3, 8)):
+        parts = [column_shard(n, r, world) for r in range(world)]
+        assert sorted(int(c) for p in parts for c in p) == list(range(n))
+        assert all(list(p) == list(range(r, n, world)) for r, p in enumerate(parts))

@@ -61,3 +61,32 @@ def test_state_packing_round_trip():
     _rng.pack_state(st, words)
     back = _rng.unpack_state(words)
     assert np.array_equal(back[1], st[1]) and back[2:] == tuple(st[2:])
+
+
+def test_jump_polynomial_table_matches_recomputation_and_numpy():
+    """fasta/mt19937_jump.npz (tools/make_mt_jump.py): the characteristic polynomial recovered here again by
+    Berlekamp-Massey, two table entries recomputed from it, and the jump y[n+J] = XOR_{g_j} y[n+j] carried out in numpy
+    against numpy's own MT19937 advanced J words -- the table the device's parallel stream relies on is right
+    independently of any GPU run."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("make_mt_jump", os.path.join(root, "tools", "make_mt_jump.py"))
+    mj = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mj)
+    with np.load(os.path.join(root, "fasta-python_b200", "fasta", "mt19937_jump.npz")) as z:
+        polys = z["polys"]
+        assert int(z["unit_blocks"]) == 64 and polys.shape == (4, 16, 624)
+    y = mj.raw_words(4357, 2 * mj.DEG + 700)
+    C, L = mj.berlekamp_massey((y[:2 * mj.DEG + 64] & 1).tolist())
+    assert L == mj.DEG
+    phi = sum(((C >> i) & 1) << (mj.DEG - i) for i in range(mj.DEG + 1))
+    assert bin(phi).count("1") == 135                                   # the known weight of MT19937's characteristic polynomial
+    for level, digit in ((0, 1), (1, 3)):
+        J = 624 * 64 * 16 ** level * digit
+        assert np.array_equal(mj.poly_words(mj.x_pow_mod(J, phi)), polys[level, digit])
+    # the jump itself, on the stream of another seed: 7 x 64 blocks ahead by one convolution
+    pre = mj.raw_words(99, mj.DEG + 624)
+    J = 624 * 64 * 7
+    ref = mj.raw_words(99, J + 624)
+    assert np.array_equal(mj.jump_numpy(pre, polys[0, 7]), ref[J:J + 624])

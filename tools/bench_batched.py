@@ -1,4 +1,7 @@
-"""Measurement of BASELINE.json config 5: batched lasso regularisation path, 256 lambdas x M=20000 N=50000,
+"""SUPERSEDED by `bench.py --workload ...` (round 2), which measures the same configs with the contract keys, the
+unmodified reference as CPU arm and full-size parity; kept as a developer tool.
+
+Measurement of BASELINE.json config 5: batched lasso regularisation path, 256 lambdas x M=20000 N=50000,
 the two contractions per iteration as tensor-core GEMMs (tcgen05 int8 digit planes, fp64 accuracy).
 
     python tools/bench_batched.py [--M 20000 --N 50000 --B 256] [--gemm ozaki|dmma] [--max-iters K] [--check-cols 2]

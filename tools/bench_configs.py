@@ -1,4 +1,7 @@
-"""Measurements of the other BASELINE.json configs (3: sparse logistic, 4: TV denoising; 1: the
+"""SUPERSEDED by `bench.py --workload ...` (round 2), which measures the same configs with the contract keys, the
+unmodified reference as CPU arm and full-size parity; kept as a developer tool.
+
+Measurements of the other BASELINE.json configs (3: sparse logistic, 4: TV denoising; 1: the
 reference's own small lasso) in the style of bench.py: one JSON line per config with iterations/s,
 time-to-tolerance, achieved algorithmic GB/s and the CPU arm (numpy oracle) beside it.
 
