@@ -30,7 +30,7 @@ namespace fb200 {
 
 constexpr int MT_N = 624, MT_M = 397, MT_LAG = MT_N - MT_M;      // 227
 constexpr int RNG_STATE_WORDS = 628;      // key[624], pos, has_gauss, gauss (double, 8-byte aligned at word 626)
-constexpr int RNG_OUT_WORDS   = 632;      // state + status word (0 ok, 1 not enough accepted tries) + tries used (2 words)
+// state_out holds RNG_STATE_WORDS + 4 words: the state, a status word (0 ok, 1 not enough accepted tries), padding, tries used (2 words)
 constexpr int POLAR_THREADS = 256, POLAR_CHUNKS = 4, POLAR_PER_BLOCK = POLAR_THREADS * POLAR_CHUNKS;
 
 struct RngMeta {                  // lives at the start of the scratch buffer
