@@ -4,10 +4,12 @@
 
 Draws `count` random small problems (lasso / non-negative least squares / L1-ball / logistic; random shapes, sparsity,
 modes and solver options) and compares the numpy oracle with the UNMODIFIED live reference on each, bit for bit
-(same process, same numpy / BLAS).  Prints one line per problem and `live_check ok <count>` at the end; exit code 1
+(same process, same numpy / BLAS), every third one also on the verbose text fasta() prints.  Prints one line per problem and `live_check ok <count>` at the end; exit code 1
 on the first difference.  Used by tests/test_oracle_live_reference.py (skipped where the reference is absent) --
 a randomized complement to the committed fixtures of tests/golden/.
 """
+import contextlib
+import io
 import os
 import sys
 
@@ -39,14 +41,22 @@ def main(count=12, seed=2024):
         rule = ("residual", "norm_residual", "ratio_residual", "hybrid_residual")[rng.randint(4)]
         f, gradf, g, proxg = problems.numpy_callables(p)
         apply, adjoint, vshape, wshape = problems.numpy_operator(p)
+        opts["verbose"] = (k % 3 == 0)              # every third problem also compares the printed text byte for byte
         state = np.random.get_state()
+        texts = []
         with np.errstate(all="ignore"):
-            want = ref.fasta(ref.linalg.LinearMap(apply, adjoint, vshape, wshape), f, gradf, g, proxg, p.x0,
-                             stop_rule=getattr(ref.stopping, rule), **opts)
-            np.random.set_state(state)
-            got = fasta_oracle.solve(apply, adjoint, f, gradf, g, proxg, p.x0,
-                                     stop_rule=getattr(fasta_oracle, "stop_" + rule), **opts)
-        ok = (got.iteration_count == want.iteration_count and got.backtracks == want.backtracks
+            for which in ("ref", "oracle"):
+                buf = io.StringIO()
+                with contextlib.redirect_stdout(buf):
+                    if which == "ref":
+                        want = ref.fasta(ref.linalg.LinearMap(apply, adjoint, vshape, wshape), f, gradf, g, proxg, p.x0,
+                                         stop_rule=getattr(ref.stopping, rule), **opts)
+                        np.random.set_state(state)
+                    else:
+                        got = fasta_oracle.solve(apply, adjoint, f, gradf, g, proxg, p.x0,
+                                                 stop_rule=getattr(fasta_oracle, "stop_" + rule), **opts)
+                texts.append(buf.getvalue())
+        ok = (texts[0] == texts[1] and got.iteration_count == want.iteration_count and got.backtracks == want.backtracks
               and np.array_equal(got.solution, want.solution, equal_nan=True)
               and np.array_equal(got.residuals, want.residuals, equal_nan=True)
               and np.array_equal(got.norm_residuals, want.norm_residuals, equal_nan=True)
