@@ -1,13 +1,16 @@
 """Device back-ends of the FBS loop (see ``_loop.py`` for the protocol).
 
-``FusedBackend``   tagged operator + tagged loss + tagged penalty: an iteration is
-                   fbs_step -> (A x + loss epilogue) -> sync -> (A^H r + BB epilogue) -> sync,
-                   all hand-written sm_100a kernels behind the C ABI (include/fasta_b200.h).
+``FusedBackend``   tagged operator + tagged loss + tagged penalty.  Dense maps: an iteration is
+                   fbs_step -> single-pass sweep (z = A x, loss, g = A^H r in ONE read of A) -> BB sums ->
+                   device-side decisions -> snapshot, queued ahead of the host's bookkeeping (two-pass
+                   fallback: fbs_step -> A x + loss -> sync -> A^H r + BB -> sync); TV: one kernel per
+                   trial.  All hand-written sm_100a kernels behind the C ABI (include/fasta_b200.h).
 ``GenericBackend`` arbitrary user callables (f, gradf, g, proxg, A) that accept torch CUDA
                    tensors; the library's own pieces (forward step, reductions, extrapolation,
                    dense contractions) still run as the same kernels.
-Operator drivers:  ``DenseDriver`` (TMA streaming GEMV / GEMV-T), ``TVDriver`` (stencils),
-                   ``ShardedDriver`` (row-partitioned A over torch.distributed ranks).
+Operator drivers:  ``DenseDriver`` (single-pass sweep, TMA streaming GEMV / GEMV-T), ``TVDriver`` (stencils),
+                   ``ShardedDriver`` (row-partitioned A over torch.distributed ranks: the local sweep + ONE
+                   exchange kernel over NVLink peer memory; barrier + all-reduce kernel or NCCL as fallbacks).
 There is no CPU implementation anywhere in this module.
 """
 
